@@ -1,0 +1,215 @@
+/*
+ * flexgpu.h -- C ABI of the B200-native batched flex_provision environment.
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of kosmylo/Safe-MARL: the
+ * flex_provision environment step on a radial feeder (IEEE 33-bus), batched over N
+ * independent environments that live as device-resident state behind an opaque handle.
+ *
+ * The reference has no FFI: its boundary is the duck-typed Python MultiAgentEnv API
+ * (madrl/environments/multiagentenv.py:1-67) as implemented by
+ * madrl/environments/flex_provision/flexibility_provision_env.py.  Each entry point below
+ * names the reference function(s) it replaces.  The Python host layer
+ * (safe-marl_b200/flexgpu) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FP_E* code otherwise; the message is
+ *     available from fp_last_error().  Power-flow non-convergence is NOT an error: it is
+ *     reported per environment (flags / info) with the reference's -200 / terminate /
+ *     roll-back semantics (flexibility_provision_env.py:314-337).
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors);
+ *     pointers named h_* are HOST pointers.  Nothing is retained after the call returns
+ *     except by fp_load_profiles / fp_predictor_load, which copy.
+ *   - all work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t cast
+ *     to void*; NULL = legacy default stream).  No entry point synchronises the device
+ *     unless it says so.  One handle per GPU per process; a handle is not thread-safe.
+ *   - there is no CPU fallback: without a CUDA device fp_create fails.
+ *
+ * Layouts (all row-major, env-major -- one warp owns one environment, so an env's row is
+ * the coalesced unit):
+ *   buses are addressed by POSITION in the reference's `bus_numbers` list, slack first
+ *   (position 0), as flexibility_provision_env.py:489-490 assumes.  "nl" = n_bus-1 lines;
+ *   line k is the line feeding bus position k+1.  "na" = number of agents/buildings.
+ */
+#ifndef FLEXGPU_H_
+#define FLEXGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP_MAX_BUS     33   /* one lane per line: nl <= 32 */
+#define FP_MAX_AGENTS  5
+#define FP_INFO_STRIDE 8    /* doubles per env in the info row */
+#define FP_NSTATS      16   /* doubles in the episode-statistics vector */
+
+enum {
+    FP_OK = 0,
+    FP_EINVAL = -1,   /* bad argument / bad topology */
+    FP_ECUDA = -2,    /* CUDA runtime error (message has the CUDA string) */
+    FP_ESTATE = -3,   /* call sequence error (e.g. step before load_profiles) */
+    FP_ENOMEM = -4
+};
+
+/* action dtypes accepted by fp_step */
+enum { FP_F32 = 0, FP_F64 = 1 };
+
+/* info row slots (FP_INFO_STRIDE doubles per env); keys of calculate_reward's dict
+ * (flexibility_provision_env.py:696-704) plus the solver_failed flag (:337). */
+enum {
+    FP_INFO_REWARD = 0, FP_INFO_REVENUE = 1, FP_INFO_DER_COST = 2, FP_INFO_ESS_COST = 3,
+    FP_INFO_DISCOMFORT = 4, FP_INFO_VOLTAGE_PENALTY = 5, FP_INFO_CUMULATIVE = 6,
+    FP_INFO_SOLVER_FAILED = 7
+};
+
+/* flag bits in the per-env record */
+enum {
+    FP_FLAG_DONE = 1,          /* terminated at the last step (:345-348) */
+    FP_FLAG_FAILED = 2,        /* last step's power flow failed (:314-337) */
+    FP_FLAG_RESET_FAILED = 4   /* the reset power flow failed; caller must re-draw (:150-153) */
+};
+
+/* per-env record: FP_REC_STRIDE 8-byte slots */
+#define FP_REC_STRIDE 16
+enum {
+    FP_REC_E_INIT = 0,     /* [na] double  initial_ess_energy (what the solver sees, quirk Q2) */
+    FP_REC_E_CUR = 5,      /* [na] double  current_ess_energy */
+    FP_REC_CUM = 10,       /* double       cumulative_reward */
+    FP_REC_TIME = 11,      /* int32 start_idx (lo), int32 steps (hi) */
+    FP_REC_HIST = 12,      /* int32 obs-history pushes since reset (lo), int32 episode counter (hi) */
+    FP_REC_VMASK = 13,     /* uint64 voltage-violation mask, bit b = bus position b */
+    FP_REC_COUNTS = 14,    /* int32 violation count (lo), int32 flags (hi) */
+    FP_REC_LINES = 15      /* uint32 line-limit mask, bit k = line k (lo), int32 sweep iterations (hi) */
+};
+
+/* Configuration = madrl/args/env_args/flex_provision.yaml:3-33 + the topology dict of
+ * utils/create_net.py:27-38, already converted to per unit (create_net.py:17-24). */
+typedef struct FpConfig {
+    int32_t n_bus;               /* len(bus_numbers); slack must be position 0 */
+    int32_t n_agents;            /* len(buildings) == len(pv_nodes) == len(ess_nodes) (quirk Q8) */
+    int32_t history;             /* yaml history */
+    int32_t episode_limit;       /* yaml episode_limit */
+    int32_t raw_actions;         /* 1 = 'safemaddpg' branch of step (:268-274): setpoints unscaled */
+    int32_t pf_max_iter;         /* sweep iteration cap; exceeding it == solver failure */
+    double pf_tol;               /* convergence: max |v_new - v_old| over buses (squared voltage) */
+    double v_min, v_max;
+    double e_min, e_max;
+    double p_ch_max, p_dis_max;
+    double eta_ch, eta_dis;
+    double max_power_reduction;
+    double kappa;                /* tan(acos(cos_phi_max)) from the HOST libm (:623) */
+    double pv_cost, ess_cost, discomfort_coeff, voltage_coeff;
+    double delta_t;              /* 24 / episode_limit (utils/pf.py:23-24) */
+    double fail_penalty;         /* 200 (:336) */
+    double e_next_lb;            /* E_next lower bound; -1e-8 = IPOPT bound_relax_factor (pf.py:46) */
+    int32_t parent[FP_MAX_BUS];  /* parent POSITION of each bus; -1 for the slack */
+    double r[FP_MAX_BUS];        /* p.u. resistance of the line feeding bus i (unused for slack) */
+    double x[FP_MAX_BUS];
+    double imax[FP_MAX_BUS];     /* p.u. rating of that line (max_line_currents) */
+    int32_t agent_bus[FP_MAX_AGENTS];  /* bus POSITION of each building */
+} FpConfig;
+
+typedef struct FpHandle FpHandle;
+
+/* -- lifetime ------------------------------------------------------------------------- */
+
+/* Replaces FlexibilityProvisionEnv.__init__ (:34-72) + create_network (create_net.py:8-38)
+ * for n_envs environments on CUDA device `device`.  Allocates all per-env state. */
+int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out);
+int fp_destroy(FpHandle* h);
+const char* fp_last_error(const FpHandle* h);   /* h may be NULL: last fp_create error */
+int64_t fp_n_envs(const FpHandle* h);
+
+/* Replaces _load_{pv,active_demand,reactive_demand,price}_data (:431-465) after resampling:
+ * HOST arrays P[T][nl], Q[T][nl] (non-slack buses, bus order), PV[T][na], price[T].
+ * Copies them to the device (synchronous). */
+int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const double* h_PV,
+                     const double* h_price, int64_t T);
+
+/* -- episode control -------------------------------------------------------------------- */
+
+/* Replaces reset()/manual_reset() (:74-155, :157-239) for every env whose d_mask byte is
+ * non-zero (d_mask == NULL: all).  The caller supplies what the reference draws from
+ * np.random (quirk Q9): d_start[N] int32 row of the episode slice (:477), d_e0[N][na]
+ * initial ESS energy (:100), d_a0[N][na*4] initial actions (:103), all fp64.
+ * Envs whose initial power flow fails get FP_FLAG_RESET_FAILED (the reference re-draws). */
+int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const double* d_a0,
+             const uint8_t* d_mask, void* stream);
+
+/* Same, but the draws come from a counter-based Philox4x32-10 stream keyed by
+ * (seed, global env id = env_offset + e, per-env episode counter): results do not depend
+ * on how envs are sharded over GPUs.  Used by throughput rollouts (auto-reset). */
+int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask,
+                    void* stream);
+
+/* Replaces step() (:241-356): d_actions[N][na*4] (agent-major, k = P_red, P_esc, P_esd, Q_pv)
+ * of dtype act_dtype; outputs d_reward[N] fp64, d_done[N] uint8, d_info[N][FP_INFO_STRIDE]
+ * fp64 (d_info may be NULL).  d_mask (may be NULL): envs with a zero byte are not stepped
+ * (their outputs are left untouched). */
+int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
+            uint8_t* d_done, double* d_info, const uint8_t* d_mask, void* stream);
+
+/* HOST-buffer variant of fp_step (the end-to-end path): copies h_actions to the device,
+ * steps, copies reward/done/info back and synchronises the stream.  Pinned host memory is
+ * recommended.  h_info may be NULL. */
+int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_reward,
+                 uint8_t* h_done, double* h_info, void* stream);
+
+/* -- observations ----------------------------------------------------------------------- */
+
+/* Replaces get_obs() (:370-403): out[N][na][history*6], dtype FP_F32 or FP_F64.
+ * push != 0 reproduces the reference's side effect (quirk Q7): the current 6-vector is
+ * appended to the per-agent history before the window is read. push == 0 is a pure read
+ * of what the next pushing call would return minus the append. */
+int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream);
+
+/* Replaces get_state() (:358-368): out[N][2*n_bus + na + n_bus + 1 + na]. */
+int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream);
+
+/* Device pointers to live state (valid until fp_destroy; rows are per env):
+ *   rec      uint64/double [N][FP_REC_STRIDE]   (see FP_REC_*)
+ *   voltage  double [N][n_bus]                  current_voltage, bus order (:146, :310)
+ *   setpoint double [N][4][na]                  power_reduction, ess_charging,
+ *                                               ess_discharging, q_pv (:293, :287-290, :281)
+ *   pflow/qflow/isq double [N][nl]              receiving-end line flows and squared currents
+ *                                               of the last solve (utils/pf.py:109-110); only
+ *                                               maintained when fp_set_keep_flows(h, 1)
+ *   stats    double [FP_NSTATS]                 see fp_stats_* */
+int fp_state_ptrs(FpHandle* h, void** d_rec, void** d_voltage, void** d_setpoint,
+                  void** d_pflow, void** d_qflow, void** d_isq);
+int fp_set_keep_flows(FpHandle* h, int keep);
+
+/* -- power flow only (BASELINE config 2) -------------------------------------------------- */
+
+/* Replaces power_flow_solver_simplified (utils/pf.py:115-192), batched: d_p/d_q[N][nl] net
+ * consumption of the non-slack buses (bus order) -> d_V[N][n_bus] voltage magnitudes,
+ * d_Pl/d_Ql/d_Isq[N][nl] (may be NULL), d_iters[N] int32 (may be NULL), d_fail[N] uint8
+ * (may be NULL).  n may differ from the handle's n_envs. */
+int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, double* d_V,
+                  double* d_Pl, double* d_Ql, double* d_Isq, int32_t* d_iters, uint8_t* d_fail,
+                  void* stream);
+
+/* -- episode statistics (the only cross-GPU reduction; madrl/models/model.py:247-265) ----- */
+
+/* Every fp_step adds, per stepped env, to a device vector of FP_NSTATS doubles:
+ *   [0..6] sums of the info slots 0..6, [7] solver failures, [8] violation count,
+ *   [9] env-steps, [10] episodes finished, [11] line-limit violations, [12..15] reserved.
+ * fp_stats_read folds the per-block partials (deterministic order) into d_out[FP_NSTATS];
+ * the caller all-reduces d_out across ranks (NCCL) if it shards envs. */
+int fp_stats_read(FpHandle* h, double* d_out, void* stream);
+int fp_stats_reset(FpHandle* h, void* stream);
+
+/* -- test hooks ------------------------------------------------------------------------- */
+
+/* Fault injection: envs whose d_mask byte is non-zero fail their next power
+ * flow as if the solver had not converged.  NULL clears. The mask is read at step time. */
+int fp_inject_failure(FpHandle* h, const uint8_t* d_mask);
+
+/* Kernel launches issued through this handle since creation (bench's gpu_launches). */
+int64_t fp_launch_count(const FpHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXGPU_H_ */

@@ -1,0 +1,412 @@
+// flex_api.cu -- C-ABI host layer of libflexgpu (see include/flexgpu.h).
+//
+// Owns the per-GPU handle: configuration, the lane-ordered topology tables (the host-side
+// equivalent of utils/create_net.py:8-38 plus the DFS pre-order the kernels need), the
+// device-resident profile dataset and the per-env state arrays.  No torch types cross this
+// boundary; every pointer is a plain host or device pointer.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "flex_kernels.cuh"
+#include "predictor.cuh"
+
+struct FpHandle {
+    FpConfig cfg;
+    DevCfg dc;
+    DevTopo topo;
+    int64_t n = 0;
+    int device = 0;
+    int64_t T = 0;
+    int32_t start_range = 0;
+    // device buffers
+    DevTopo* d_topo = nullptr;
+    double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr;
+    uint64_t* d_rec = nullptr;
+    double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
+    double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
+    double* d_stats_partial = nullptr;
+    int stats_rows = 0;
+    const uint8_t* d_inject = nullptr;
+    int keep_flows = 0;
+    // staging for the host-buffer entry points
+    void* d_act_stage = nullptr; double* d_reward_stage = nullptr; uint8_t* d_done_stage = nullptr;
+    double* d_info_stage = nullptr;
+    int grid_step = 0, grid_reset = 0, grid_pf = 0;
+    int64_t launches = 0;
+    std::string err;
+    PredictorState pred;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(FpHandle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (expr);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail((h), FP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------ topology preprocessing
+// Pre-order numbering (children visited in ascending bus position) + per-lane tables.
+static int build_topology(const FpConfig& c, DevTopo& t, std::string& err) {
+    const int nb = c.n_bus, nl = nb - 1;
+    if (nb < 2 || nb > FP_MAX_BUS) { err = "n_bus must be in [2, 33]"; return FP_EINVAL; }
+    if (c.n_agents < 1 || c.n_agents > FP_MAX_AGENTS) { err = "n_agents must be in [1, 5]"; return FP_EINVAL; }
+    if (c.parent[0] != -1) { err = "slack bus must be position 0 (parent[0] == -1)"; return FP_EINVAL; }
+    std::vector<std::vector<int>> kids(nb);
+    for (int b = 1; b < nb; ++b) {
+        int p = c.parent[b];
+        if (p < 0 || p >= nb || p == b) { err = "parent[] out of range"; return FP_EINVAL; }
+        kids[p].push_back(b);                          // ascending b by construction
+    }
+    std::vector<int> lane_of(nb, -1), bus_of(FP_NL, -1), size(nb, 1);
+    // iterative pre-order
+    std::vector<int> stack;
+    int next = 0;
+    for (int i = (int)kids[0].size() - 1; i >= 0; --i) stack.push_back(kids[0][i]);
+    std::vector<int> order;
+    while (!stack.empty()) {
+        int b = stack.back(); stack.pop_back();
+        if (lane_of[b] >= 0) { err = "topology has a cycle"; return FP_EINVAL; }
+        lane_of[b] = next; bus_of[next] = b; ++next;
+        order.push_back(b);
+        for (int i = (int)kids[b].size() - 1; i >= 0; --i) stack.push_back(kids[b][i]);
+    }
+    if (next != nl) { err = "topology is not a connected radial tree rooted at the slack bus"; return FP_EINVAL; }
+    for (int i = nl - 1; i >= 0; --i) {                // subtree sizes, children before parents
+        int b = order[i];
+        if (c.parent[b] != 0) size[c.parent[b]] += size[b];
+    }
+    std::memset(&t, 0, sizeof(t));
+    for (int k = 0; k < FP_NL; ++k) {
+        t.end[k] = k; t.col[k] = 0; t.agent[k] = -1;
+        t.imax2[k] = std::numeric_limits<double>::infinity();
+        uint32_t anc = 0;
+        for (int r = 0; r < 5; ++r) anc |= (ANC_NONE << (6 * r));
+        t.anc[k] = anc;
+    }
+    for (int k = 0; k < nl; ++k) {
+        int b = bus_of[k];
+        if (!(c.r[b] >= 0.0) || !std::isfinite(c.x[b])) { err = "line impedance must be finite"; return FP_EINVAL; }
+        t.R[k] = c.r[b]; t.X[k] = c.x[b];
+        t.Z2[k] = c.r[b] * c.r[b] + c.x[b] * c.x[b];   // utils/pf.py:93 R**2 + X**2
+        t.imax2[k] = (c.imax[b] > 0.0) ? c.imax[b] * c.imax[b] : std::numeric_limits<double>::infinity();
+        t.end[k] = k + size[b] - 1;
+        t.col[k] = b - 1;
+        uint32_t anc = 0;
+        for (int r = 0; r < 5; ++r) {
+            int a = b;
+            for (int s = 0; s < (1 << r) && a > 0; ++s) a = c.parent[a];
+            uint32_t al = (a > 0) ? (uint32_t)lane_of[a] : ANC_NONE;
+            anc |= (al << (6 * r));
+        }
+        t.anc[k] = anc;
+    }
+    for (int i = 0; i < c.n_agents; ++i) {
+        int b = c.agent_bus[i];
+        if (b < 1 || b >= nb) { err = "agent_bus must be a non-slack bus position"; return FP_EINVAL; }
+        if (t.agent[lane_of[b]] >= 0) { err = "two agents on the same bus"; return FP_EINVAL; }
+        t.agent[lane_of[b]] = i;
+        t.agent_lane[i] = lane_of[b];
+        t.agent_col[i] = b - 1;
+    }
+    return FP_OK;
+}
+
+static void fill_devcfg(const FpConfig& c, DevCfg& d) {
+    std::memset(&d, 0, sizeof(d));
+    d.nb = c.n_bus; d.nl = c.n_bus - 1; d.na = c.n_agents; d.history = c.history;
+    d.episode_limit = c.episode_limit; d.raw_actions = c.raw_actions; d.pf_max_iter = c.pf_max_iter;
+    d.obs_w = 6 * c.history;
+    d.pf_tol = c.pf_tol; d.v_min = c.v_min; d.v_max = c.v_max; d.e_min = c.e_min; d.e_max = c.e_max;
+    d.p_ch_max = c.p_ch_max; d.p_dis_max = c.p_dis_max; d.eta_ch = c.eta_ch; d.eta_dis = c.eta_dis;
+    d.inv_eta_dis = 1.0 / c.eta_dis;                   // python evaluates (1 / eta_dis) first (:634, pf.py:97)
+    d.mpr = c.max_power_reduction; d.kappa = c.kappa; d.pv_cost = c.pv_cost; d.ess_cost = c.ess_cost;
+    d.discomfort_coeff = c.discomfort_coeff; d.voltage_coeff = c.voltage_coeff; d.delta_t = c.delta_t;
+    d.fail_penalty = c.fail_penalty; d.e_next_lb = c.e_next_lb;
+    // slack bus: V = sqrt(1) = 1 (pf.py:51-53); its penalty term is a constant
+    const double over = 1.0 - c.v_max, under = c.v_min - 1.0;
+    d.slack_viol = (over > 0.0 || under > 0.0) ? 1 : 0;
+    d.slack_pen = d.slack_viol ? c.voltage_coeff * ((over > under) ? over : under) : 0.0;
+}
+
+static int grid_for(int64_t n, int cap) {
+    int64_t ctas = (n + (FP_CTA_THREADS / 32) - 1) / (FP_CTA_THREADS / 32);
+    if (ctas < 1) ctas = 1;
+    return (int)((ctas < cap) ? ctas : cap);
+}
+
+extern "C" {
+
+int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
+    if (!cfg || !out || n_envs < 1) return fail(nullptr, FP_EINVAL, "fp_create: bad arguments");
+    if (cfg->history < 1 || cfg->episode_limit < 2 || cfg->pf_max_iter < 1 || !(cfg->pf_tol > 0.0) ||
+        !(cfg->eta_ch > 0.0) || !(cfg->eta_dis > 0.0))
+        return fail(nullptr, FP_EINVAL, "fp_create: bad scalar configuration");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(nullptr, FP_ECUDA, "fp_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, FP_EINVAL, "fp_create: bad device index");
+    FpHandle* h = new (std::nothrow) FpHandle();
+    if (!h) return fail(nullptr, FP_ENOMEM, "fp_create: out of host memory");
+    h->cfg = *cfg; h->n = n_envs; h->device = device;
+    std::string err;
+    int rc = build_topology(*cfg, h->topo, err);
+    if (rc != FP_OK) { delete h; return fail(nullptr, rc, "fp_create: " + err); }
+    fill_devcfg(*cfg, h->dc);
+    const int nb = cfg->n_bus, na = cfg->n_agents, H = cfg->history;
+#define CREATE_TRY(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            std::string m = std::string("fp_create: " #expr ": ") + cudaGetErrorString(e_); \
+            fp_destroy(h);                                                                 \
+            return fail(nullptr, e_ == cudaErrorMemoryAllocation ? FP_ENOMEM : FP_ECUDA, m); \
+        }                                                                                  \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaMalloc(&h->d_topo, sizeof(DevTopo)));
+    CREATE_TRY(cudaMemcpy(h->d_topo, &h->topo, sizeof(DevTopo), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&h->d_rec, (size_t)n_envs * FP_REC_STRIDE * 8));
+    CREATE_TRY(cudaMemset(h->d_rec, 0, (size_t)n_envs * FP_REC_STRIDE * 8));
+    CREATE_TRY(cudaMalloc(&h->d_V, (size_t)n_envs * nb * 8));
+    CREATE_TRY(cudaMemset(h->d_V, 0, (size_t)n_envs * nb * 8));
+    CREATE_TRY(cudaMalloc(&h->d_setp, (size_t)n_envs * 4 * na * 8));
+    CREATE_TRY(cudaMemset(h->d_setp, 0, (size_t)n_envs * 4 * na * 8));
+    CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_envs * na * H * 6 * 8));
+    CREATE_TRY(cudaMemset(h->d_hist, 0, (size_t)n_envs * na * H * 6 * 8));
+    h->grid_step = grid_for(n_envs, max_resident_grid(MODE_STEP));
+    h->grid_reset = grid_for(n_envs, max_resident_grid(MODE_RESET));
+    h->grid_pf = max_resident_grid(MODE_PF);
+    h->stats_rows = max_resident_grid(MODE_STEP);
+    CREATE_TRY(cudaMalloc(&h->d_stats_partial, (size_t)h->stats_rows * FP_NSTATS * 8));
+    CREATE_TRY(cudaMemset(h->d_stats_partial, 0, (size_t)h->stats_rows * FP_NSTATS * 8));
+#undef CREATE_TRY
+    *out = h;
+    return FP_OK;
+}
+
+int fp_destroy(FpHandle* h) {
+    if (!h) return FP_OK;
+    cudaSetDevice(h->device);
+    predictor_free(&h->pred);
+    cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP);
+    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist);
+    cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
+    cudaFree(h->d_act_stage); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
+    delete h;
+    return FP_OK;
+}
+
+const char* fp_last_error(const FpHandle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int64_t fp_n_envs(const FpHandle* h) { return h ? h->n : 0; }
+int64_t fp_launch_count(const FpHandle* h) { return h ? h->launches : 0; }
+
+int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const double* h_PV,
+                     const double* h_price, int64_t T) {
+    if (!h) return FP_EINVAL;
+    if (!h_P || !h_Q || !h_PV || !h_price) return fail(h, FP_EINVAL, "fp_load_profiles: null array");
+    const int nl = h->dc.nl, na = h->dc.na;
+    // the reference slices episode_limit + history + 1 rows per episode (:478)
+    const int64_t need = (int64_t)h->cfg.episode_limit + h->cfg.history + 1;
+    if (T < need) return fail(h, FP_EINVAL, "fp_load_profiles: fewer rows than one episode slice");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP);
+    h->d_P = h->d_Q = h->d_PVP = nullptr;
+    double *d_pv = nullptr, *d_price = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->d_P, (size_t)T * nl * 8));
+    CUDA_TRY(h, cudaMalloc(&h->d_Q, (size_t)T * nl * 8));
+    CUDA_TRY(h, cudaMalloc(&h->d_PVP, (size_t)T * FP_PVP_STRIDE * 8));
+    CUDA_TRY(h, cudaMalloc(&d_pv, (size_t)T * na * 8));
+    CUDA_TRY(h, cudaMalloc(&d_price, (size_t)T * 8));
+    CUDA_TRY(h, cudaMemcpy(h->d_P, h_P, (size_t)T * nl * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_Q, h_Q, (size_t)T * nl * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(d_pv, h_PV, (size_t)T * na * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(d_price, h_price, (size_t)T * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, launch_pack_pvp(d_pv, d_price, na, T, h->d_PVP, 0));
+    h->launches++;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    cudaFree(d_pv); cudaFree(d_price);
+    h->T = T;
+    h->start_range = (int32_t)((T - need + 1 < 2147483647LL) ? (T - need + 1) : 2147483647LL);
+    return FP_OK;
+}
+
+static void fill_env_params(FpHandle* h, EnvParams& p) {
+    std::memset(&p, 0, sizeof(p));
+    p.c = h->dc; p.topo = h->d_topo; p.n = h->n;
+    p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP;
+    p.rec = h->d_rec; p.V = h->d_V; p.setp = h->d_setp;
+    if (h->keep_flows) { p.pfl = h->d_pfl; p.qfl = h->d_qfl; p.isq = h->d_isq; }
+    p.inject = h->d_inject;
+    p.start_range = h->start_range;
+}
+
+int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const double* d_a0,
+             const uint8_t* d_mask, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_reset: call fp_load_profiles first");
+    if (!d_start || !d_e0 || !d_a0) return fail(h, FP_EINVAL, "fp_reset: null input");
+    EnvParams p; fill_env_params(h, p);
+    p.start = d_start; p.e0 = d_e0; p.a0 = d_a0; p.mask = d_mask; p.random = 0;
+    p.inject = nullptr;
+    CUDA_TRY(h, launch_env(MODE_RESET, p, h->grid_reset, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_reset_random: call fp_load_profiles first");
+    EnvParams p; fill_env_params(h, p);
+    p.mask = d_mask; p.random = 1; p.seed = seed; p.env_offset = env_offset;
+    p.inject = nullptr;
+    CUDA_TRY(h, launch_env(MODE_RESET, p, h->grid_reset, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done,
+            double* d_info, const uint8_t* d_mask, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_step: call fp_load_profiles first");
+    if (!d_actions || !d_reward || !d_done) return fail(h, FP_EINVAL, "fp_step: null input/output");
+    if (act_dtype != FP_F32 && act_dtype != FP_F64) return fail(h, FP_EINVAL, "fp_step: bad action dtype");
+    EnvParams p; fill_env_params(h, p);
+    p.actions = d_actions; p.act_f64 = (act_dtype == FP_F64);
+    p.reward = d_reward; p.done = d_done; p.info = d_info; p.mask = d_mask;
+    p.stats_partial = h->d_stats_partial;
+    CUDA_TRY(h, launch_env(MODE_STEP, p, h->grid_step, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_reward, uint8_t* h_done,
+                 double* h_info, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h_actions || !h_reward || !h_done) return fail(h, FP_EINVAL, "fp_step_host: null buffer");
+    if (act_dtype != FP_F32 && act_dtype != FP_F64) return fail(h, FP_EINVAL, "fp_step_host: bad action dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->n, na = (size_t)h->dc.na;
+    if (!h->d_act_stage) {
+        CUDA_TRY(h, cudaMalloc(&h->d_act_stage, n * na * 4 * 8));
+        CUDA_TRY(h, cudaMalloc(&h->d_reward_stage, n * 8));
+        CUDA_TRY(h, cudaMalloc(&h->d_done_stage, n));
+        CUDA_TRY(h, cudaMalloc(&h->d_info_stage, n * FP_INFO_STRIDE * 8));
+    }
+    const size_t abytes = n * na * 4 * (act_dtype == FP_F64 ? 8 : 4);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_act_stage, h_actions, abytes, cudaMemcpyHostToDevice, st));
+    int rc = fp_step(h, h->d_act_stage, act_dtype, h->d_reward_stage, h->d_done_stage,
+                     h_info ? h->d_info_stage : nullptr, nullptr, stream);
+    if (rc != FP_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h_reward, h->d_reward_stage, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h_done, h->d_done_stage, n, cudaMemcpyDeviceToHost, st));
+    if (h_info) CUDA_TRY(h, cudaMemcpyAsync(h_info, h->d_info_stage, n * FP_INFO_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return FP_OK;
+}
+
+static void fill_obs_params(FpHandle* h, ObsParams& p, void* out, int push) {
+    std::memset(&p, 0, sizeof(p));
+    p.c = h->dc; p.n = h->n; p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP;
+    p.rec = h->d_rec; p.V = h->d_V; p.hist = h->d_hist;
+    for (int i = 0; i < 8; ++i) p.agent_col[i] = h->topo.agent_col[i];
+    p.out = out; p.push = push;
+}
+
+int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs: call fp_load_profiles first");
+    if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_obs: bad arguments");
+    ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
+    CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_step, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_state: call fp_load_profiles first");
+    if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_state: bad arguments");
+    ObsParams p; fill_obs_params(h, p, d_out, 0);
+    CUDA_TRY(h, launch_state(p, dtype == FP_F64, h->grid_step, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_state_ptrs(FpHandle* h, void** d_rec, void** d_voltage, void** d_setpoint, void** d_pflow,
+                  void** d_qflow, void** d_isq) {
+    if (!h) return FP_EINVAL;
+    if (d_rec) *d_rec = h->d_rec;
+    if (d_voltage) *d_voltage = h->d_V;
+    if (d_setpoint) *d_setpoint = h->d_setp;
+    if (d_pflow) *d_pflow = h->d_pfl;
+    if (d_qflow) *d_qflow = h->d_qfl;
+    if (d_isq) *d_isq = h->d_isq;
+    return FP_OK;
+}
+
+int fp_set_keep_flows(FpHandle* h, int keep) {
+    if (!h) return FP_EINVAL;
+    if (keep && !h->d_pfl) {
+        const size_t bytes = (size_t)h->n * h->dc.nl * 8;
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaMalloc(&h->d_pfl, bytes));
+        CUDA_TRY(h, cudaMalloc(&h->d_qfl, bytes));
+        CUDA_TRY(h, cudaMalloc(&h->d_isq, bytes));
+        CUDA_TRY(h, cudaMemset(h->d_pfl, 0, bytes));
+        CUDA_TRY(h, cudaMemset(h->d_qfl, 0, bytes));
+        CUDA_TRY(h, cudaMemset(h->d_isq, 0, bytes));
+    }
+    h->keep_flows = keep ? 1 : 0;
+    return FP_OK;
+}
+
+int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, double* d_V, double* d_Pl,
+                  double* d_Ql, double* d_Isq, int32_t* d_iters, uint8_t* d_fail, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (n < 1 || !d_p || !d_q || !d_V) return fail(h, FP_EINVAL, "fp_power_flow: bad arguments");
+    PfParams p;
+    p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol;
+    p.p = d_p; p.q = d_q; p.V = d_V; p.Pl = d_Pl; p.Ql = d_Ql; p.Isq = d_Isq; p.iters = d_iters; p.fail = d_fail;
+    CUDA_TRY(h, launch_power_flow(p, grid_for(n, h->grid_pf), (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_stats_read(FpHandle* h, double* d_out, void* stream) {
+    if (!h || !d_out) return FP_EINVAL;
+    CUDA_TRY(h, launch_stats_fold(h->d_stats_partial, h->stats_rows, d_out, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+int fp_stats_reset(FpHandle* h, void* stream) {
+    if (!h) return FP_EINVAL;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stats_partial, 0, (size_t)h->stats_rows * FP_NSTATS * 8, (cudaStream_t)stream));
+    return FP_OK;
+}
+
+int fp_inject_failure(FpHandle* h, const uint8_t* d_mask) {
+    if (!h) return FP_EINVAL;
+    h->d_inject = d_mask;
+    return FP_OK;
+}
+
+}  // extern "C"
+
+// accessors used by the predictor / replay translation unit
+PredictorState* fp_internal_predictor(FpHandle* h) { return &h->pred; }
+int fp_internal_fail(FpHandle* h, int code, const char* msg) { return fail(h, code, msg); }
+void fp_internal_count_launch(FpHandle* h, int k) { h->launches += k; }
+int fp_internal_device(FpHandle* h) { return h->device; }

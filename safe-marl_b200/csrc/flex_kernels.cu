@@ -1,0 +1,513 @@
+// flex_kernels.cu -- the fused flex_provision kernels (sm_100a).
+//
+//   k_env<STEP>   replaces FlexibilityProvisionEnv.step           (flexibility_provision_env.py:241-356)
+//   k_env<RESET>  replaces reset()/manual_reset()                  (:74-155, :157-239)
+//   k_power_flow  replaces power_flow_solver_simplified, batched   (utils/pf.py:115-192)
+//   k_obs         replaces get_obs() incl. its history side effect (:370-403)
+//   k_state       replaces get_state()                             (:358-368)
+//   k_stats_fold  folds the per-CTA episode-statistics partials    (madrl/models/model.py:247-265)
+//
+// Mapping: one warp == one environment, lane k == line k (see flex_common.cuh).  Persistent
+// CTAs grid-stride over environments; the topology table is staged into shared memory once
+// per CTA; profile rows are read with one coalesced 8-byte load per lane (a 256-byte row per
+// warp); everything between those loads and the state write-back stays in registers and
+// warp shuffles.  No atomics, no inter-warp communication on the step path.
+#include "flex_kernels.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_CTA = FP_CTA_THREADS / 32;
+constexpr int SCRATCH_DOUBLES = 32;   // per-warp shared scratch
+
+__device__ __forceinline__ uint64_t pack2(int32_t lo, int32_t hi) {
+    return (uint64_t)(uint32_t)lo | ((uint64_t)(uint32_t)hi << 32);
+}
+
+// Setpoints of one agent (executed by the agent's lane).
+struct Setpoint { double pred, ch, dis, qpv; };
+
+// flexibility_provision_env.py:628-661 (no delta_t here -- quirk Q3)
+__device__ __forceinline__ void ess_energy_clip(const DevCfg& c, double& ch, double& dis, double e_now) {
+    ch = clipd(ch, 0.0, c.p_ch_max);
+    dis = clipd(dis, 0.0, c.p_dis_max);
+    double e_next = (e_now + c.eta_ch * ch) - c.inv_eta_dis * dis;
+    if (e_next > c.e_max) {
+        double excess = e_next - c.e_max;
+        double t = excess / c.eta_ch;
+        if (ch > t) {
+            ch = ch - t;
+        } else {
+            dis = dis + (excess - ch * c.eta_ch) * c.eta_dis;
+            ch = 0.0;
+        }
+    } else if (e_next < c.e_min) {
+        double lack = c.e_min - e_next;
+        double t = lack * c.eta_dis;
+        if (dis > t) {
+            dis = dis - t;
+        } else {
+            ch = ch + (lack - dis / c.eta_dis) / c.eta_ch;
+            dis = 0.0;
+        }
+    }
+    ch = clipd(ch, 0.0, c.p_ch_max);
+    dis = clipd(dis, 0.0, c.p_dis_max);
+}
+
+// :262-293 (step) / :113-130 (reset): raw action -> applied setpoints.
+__device__ __forceinline__ Setpoint apply_actions(const DevCfg& c, bool scale, double a0, double a1,
+                                                  double a2, double a3, double pload, double ppv,
+                                                  double e_clip) {
+    double pct, ch, dis, qpv;
+    if (scale) {
+        pct = c.mpr * a0;                                   // :278
+        ch = c.p_ch_max * a1;                               // :279
+        dis = c.p_dis_max * a2;                             // :280
+        double lim = c.kappa * ppv;                         // :623
+        double lo = -lim;
+        qpv = clipd(lo + a3 * (lim - lo), lo, lim);         // :626
+    } else {                                                // 'safemaddpg' branch :268-274
+        pct = a0; ch = a1; dis = a2; qpv = a3;
+    }
+    pct = clipd(pct, 0.0, c.mpr);                           // :676-677
+    if (ch > 0.0 && dis > 0.0) {                            // :663-674
+        if (ch > dis) { ch = ch - dis; dis = 0.0; }
+        else          { dis = dis - ch; ch = 0.0; }
+    }
+    ess_energy_clip(c, ch, dis, e_clip);                    // :289-290
+    Setpoint s;
+    s.pred = pload * pct;                                   // :293
+    s.ch = ch; s.dis = dis; s.qpv = qpv;
+    return s;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_env(const EnvParams prm) {
+    __shared__ DevTopo s_topo;
+    __shared__ double s_scratch[WARPS_PER_CTA][SCRATCH_DOUBLES];
+    __shared__ double s_stats[WARPS_PER_CTA][FP_NSTATS];
+
+    stage_topo(&s_topo, prm.topo);
+    const DevCfg& c = prm.c;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const LaneTopo lt = load_lane_topo(s_topo, lane);
+    const int nl = c.nl, na = c.na;
+    const int my_col = s_topo.col[lane];
+    const int my_agent = s_topo.agent[lane];               // agent living on this lane's bus
+    const int a_lane = (lane < na) ? s_topo.agent_lane[lane] : 0;   // as agent `lane`: my bus's lane
+    const int a_col = (lane < na) ? s_topo.agent_col[lane] : 0;
+    double* scratch = s_scratch[warp];
+    double stat_acc = 0.0;                                 // lane j < FP_NSTATS accumulates stat j
+
+    const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
+    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+        if (prm.mask != nullptr && prm.mask[e] == 0) continue;          // warp-uniform
+
+        uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
+        // ---------------------------------------------------------------- load per-env record
+        int32_t start, steps, hist_n, episode;
+        double e_init = 0.0, e_cur = 0.0, cum = 0.0;
+        double a0, a1, a2, a3;
+        a0 = a1 = a2 = a3 = 0.0;
+        if (MODE == MODE_STEP) {
+            uint64_t tm = rec[FP_REC_TIME];                              // broadcast load
+            start = (int32_t)(uint32_t)tm;
+            steps = (int32_t)(tm >> 32);
+            if (lane < na) {
+                e_init = __longlong_as_double((long long)rec[FP_REC_E_INIT + lane]);
+                e_cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + lane]);
+                if (prm.act_f64) {
+                    const double* a = reinterpret_cast<const double*>(prm.actions) + (e * na + lane) * 4;
+                    a0 = a[0]; a1 = a[1]; a2 = a[2]; a3 = a[3];
+                } else {
+                    // fp32 actions are widened exactly
+                    float4 a = reinterpret_cast<const float4*>(prm.actions)[e * na + lane];
+                    a0 = (double)a.x; a1 = (double)a.y; a2 = (double)a.z; a3 = (double)a.w;
+                }
+            }
+            cum = __longlong_as_double((long long)rec[FP_REC_CUM]);
+            uint64_t hh = rec[FP_REC_HIST];
+            hist_n = (int32_t)(uint32_t)hh;
+            episode = (int32_t)(hh >> 32);
+        } else {
+            uint64_t hh = rec[FP_REC_HIST];
+            episode = (int32_t)(hh >> 32);
+            hist_n = 0;                                                  // :79-80
+            steps = 1;                                                   // :76
+            cum = 0.0;                                                   // :77
+            if (prm.random) {
+                // counter = (global env id lo, hi, episode, block); one Philox block per lane
+                const uint64_t gid = (uint64_t)(prm.env_offset + e);
+                U4 ctr; ctr.x = (uint32_t)gid; ctr.y = (uint32_t)(gid >> 32); ctr.z = (uint32_t)episode; ctr.w = (uint32_t)lane;
+                U4 r = philox4x32_10(ctr, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+                // lane 15: start row; lanes 10..14: E0 of agent lane-10; lanes 0..9 : two actions each
+                double u0 = u53(r.x, r.y), u1 = u53(r.z, r.w);
+                double lo = 0.9 * (c.e_max / 2), hi = 1.1 * (c.e_max / 2);          // :100
+                double e0v = lo + (hi - lo) * u0;
+                int32_t st = (int32_t)(u0 * (double)prm.start_range);
+                start = __shfl_sync(FULL, st, 15);
+                // agent i (lane i) needs actions 4i..4i+3 = blocks (2i, 2i+1)
+                double b0 = __shfl_sync(FULL, u0, (2 * lane) & 31), b1 = __shfl_sync(FULL, u1, (2 * lane) & 31);
+                double b2 = __shfl_sync(FULL, u0, (2 * lane + 1) & 31), b3 = __shfl_sync(FULL, u1, (2 * lane + 1) & 31);
+                double ee = __shfl_sync(FULL, e0v, (10 + lane) & 31);
+                if (lane < na) { a0 = b0; a1 = b1; a2 = b2; a3 = b3; e_init = ee; }
+            } else {
+                start = prm.start[e];
+                if (lane < na) {
+                    e_init = prm.e0[e * na + lane];
+                    const double* a = prm.a0 + (e * na + lane) * 4;
+                    a0 = a[0]; a1 = a[1]; a2 = a[2]; a3 = a[3];
+                }
+            }
+            e_cur = e_init;                                              // reset clips against E0 (:130)
+        }
+
+        // ---------------------------------------------------------------- gather the profile row
+        // Quirk Q1: the row in force is max(steps-1, 1); the row loaded after the solve is `steps`.
+        const int64_t row = (int64_t)start + ((MODE == MODE_STEP && steps > 1) ? (steps - 1) : 1);
+        double pl = 0.0, ql = 0.0;
+        if (lane < nl) {
+            pl = __ldg(prm.P + row * nl + my_col);
+            ql = __ldg(prm.Q + row * nl + my_col);
+        }
+        double pv = 0.0, price = 0.0, pload_b = 0.0;
+        if (lane < na) {
+            pv = __ldg(prm.PVP + row * FP_PVP_STRIDE + lane);
+            price = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
+            pload_b = __ldg(prm.P + row * nl + a_col);
+        }
+
+        // ---------------------------------------------------------------- actions -> setpoints
+        Setpoint sp; sp.pred = sp.ch = sp.dis = sp.qpv = 0.0;
+        double p_bus = 0.0;
+        if (lane < na) {
+            const bool scale = (MODE == MODE_RESET) || !c.raw_actions;
+            sp = apply_actions(c, scale, a0, a1, a2, a3, pload_b, pv, e_cur);
+            // net consumption at the building's bus, balance row utils/pf.py:65-75
+            p_bus = (((pload_b - sp.pred) - pv) + sp.ch) - sp.dis;
+        }
+        // hand the building's net injection to the lane that owns its bus
+        {
+            const int src = (my_agent >= 0) ? my_agent : 0;
+            double pb = __shfl_sync(FULL, p_bus, src);
+            double qb = __shfl_sync(FULL, sp.qpv, src);
+            if (my_agent >= 0) { pl = pb; ql = ql - qb; }               // pf.py:77-83: Qload - Qpv
+        }
+
+        // ---------------------------------------------------------------- power flow
+        const bool inject = (prm.inject != nullptr) && (prm.inject[e] != 0);
+        SweepOut sw = distflow_sweep(lt, pl, ql, lane, c.pf_tol, c.pf_max_iter, inject);
+
+        // ESS update utils/pf.py:96-98 with E_init (quirk Q2) and delta_t
+        double e_next = 0.0;
+        bool e_bad = false;
+        if (lane < na) {
+            e_next = e_init + c.delta_t * (c.eta_ch * sp.ch - c.inv_eta_dis * sp.dis);
+            e_bad = e_next < c.e_next_lb;                                // E_next in NonNegativeReals (pf.py:46)
+        }
+        const bool ok = sw.ok && !__any_sync(FULL, e_bad);              // warp-uniform
+
+        // ---------------------------------------------------------------- voltages, masks
+        double V = sqrt(sw.v);                                           // pf.py:108
+        double* Vrow = prm.V + e * c.nb;
+        if (ok) {
+            if (lane < nl) Vrow[my_col + 1] = V;
+            if (lane == 0) Vrow[0] = 1.0;                                // slack: sqrt(Vsqr = 1), pf.py:51-53
+            if (prm.pfl != nullptr && lane < nl) {
+                prm.pfl[e * nl + my_col] = sw.P;
+                prm.qfl[e * nl + my_col] = sw.Q;
+                prm.isq[e * nl + my_col] = sw.ell;
+            }
+        } else if (MODE == MODE_STEP) {
+            // roll back to the last valid state (:318-328): voltages and setpoints
+            if (lane < nl) V = Vrow[my_col + 1];
+            if (lane < na) {
+                const double* sprow = prm.setp + e * 4 * na;
+                sp.pred = sprow[0 * na + lane]; sp.ch = sprow[1 * na + lane];
+                sp.dis = sprow[2 * na + lane]; sp.qpv = sprow[3 * na + lane];
+            }
+        }
+        const double over = V - c.v_max, under = c.v_min - V;
+        const bool viol = (lane < nl) && ((over > 0.0) || (under > 0.0));
+        double vterm = 0.0;
+        if (viol) vterm = c.voltage_coeff * ((over > under) ? over : under);   // :685 max(0, v-vmax, vmin-v)
+        uint32_t vm = __reduce_or_sync(FULL, viol ? (1u << my_col) : 0u);
+        const uint64_t vmask = ((uint64_t)vm << 1) | (uint64_t)(c.slack_viol & 1);
+        const int vcount = __popc(vm) + (c.slack_viol & 1);
+        const bool lviol = (lane < nl) && ok && (sw.ell > s_topo.imax2[lane]);       // utils/opf.py:124-126
+        const uint32_t lm = __reduce_or_sync(FULL, lviol ? (1u << my_col) : 0u);
+
+        if (MODE == MODE_STEP) {
+            // ------------------------------------------------------------ reward (:679-706)
+            double vpen = warp_sum_xor(vterm) + c.slack_pen;
+            if (lane < na) {
+                scratch[lane * 4 + 0] = price * sp.pred;                          // :681
+                scratch[lane * 4 + 1] = c.pv_cost * sp.qpv;                       // :682 (signed, Q4)
+                scratch[lane * 4 + 2] = c.ess_cost * (sp.ch + sp.dis);            // :683
+                scratch[lane * 4 + 3] = c.discomfort_coeff * (sp.pred * sp.pred); // :684
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double rev = scratch[0], der = scratch[1], ess = scratch[2], disc = scratch[3];
+                for (int i = 1; i < na; ++i) {                                    // python sum(): left to right
+                    rev = rev + scratch[i * 4 + 0];
+                    der = der + scratch[i * 4 + 1];
+                    ess = ess + scratch[i * 4 + 2];
+                    disc = disc + scratch[i * 4 + 3];
+                }
+                double reward = (((rev - der) - ess) - disc) - vpen;              // :686
+                scratch[24 + FP_INFO_REVENUE] = rev;
+                scratch[24 + FP_INFO_DER_COST] = der;
+                scratch[24 + FP_INFO_ESS_COST] = ess;
+                scratch[24 + FP_INFO_DISCOMFORT] = disc;
+                scratch[24 + FP_INFO_VOLTAGE_PENALTY] = vpen;
+                scratch[24 + FP_INFO_REWARD] = reward;                            // info['reward'] is pre-penalty (:697)
+                scratch[24 + FP_INFO_CUMULATIVE] = cum;                           // before adding (:703)
+                scratch[24 + FP_INFO_SOLVER_FAILED] = ok ? 0.0 : 1.0;
+                if (!ok) reward = reward - c.fail_penalty;                        // :336
+                scratch[20] = reward;
+                scratch[21] = cum + reward;                                       // :343
+            }
+            __syncwarp();
+            const double reward = scratch[20];
+            const int steps_new = steps + 1;                                      // :342
+            const bool done = (steps_new >= c.episode_limit) || !ok;              // :345-348
+            if (lane < FP_INFO_STRIDE) {
+                double iv = scratch[24 + lane];
+                if (prm.info != nullptr) prm.info[e * FP_INFO_STRIDE + lane] = iv;
+                stat_acc += iv;                     // slots 0..6 info sums, 7 failures
+            } else if (lane == 8) stat_acc += (double)vcount;
+            else if (lane == 9) stat_acc += 1.0;
+            else if (lane == 10) stat_acc += done ? 1.0 : 0.0;
+            else if (lane == 11) stat_acc += (double)__popc(lm);
+            if (lane == 0) {
+                prm.reward[e] = reward;
+                prm.done[e] = done ? 1 : 0;
+            }
+            // ------------------------------------------------------------ write back
+            // success: E_cur <- E_next; failure: E_cur stays (rolled back). E_init <- E_cur (:354).
+            const double e_cur_new = ok ? e_next : e_cur;
+            if (lane < na) {
+                rec[FP_REC_E_INIT + lane] = (uint64_t)__double_as_longlong(e_cur_new);
+                rec[FP_REC_E_CUR + lane] = (uint64_t)__double_as_longlong(e_cur_new);
+                if (ok) {
+                    double* sprow = prm.setp + e * 4 * na;
+                    sprow[0 * na + lane] = sp.pred; sprow[1 * na + lane] = sp.ch;
+                    sprow[2 * na + lane] = sp.dis; sprow[3 * na + lane] = sp.qpv;
+                }
+            }
+            if (lane == 10) rec[FP_REC_CUM] = (uint64_t)__double_as_longlong(scratch[21]);
+            if (lane == 11) rec[FP_REC_TIME] = pack2(start, steps_new);
+            if (lane == 12) rec[FP_REC_HIST] = pack2(hist_n, episode);
+            if (lane == 13) rec[FP_REC_VMASK] = vmask;
+            if (lane == 14) rec[FP_REC_COUNTS] = pack2(vcount, (done ? FP_FLAG_DONE : 0) | (ok ? 0 : FP_FLAG_FAILED));
+            if (lane == 15) rec[FP_REC_LINES] = pack2((int32_t)lm, sw.iters);
+            __syncwarp();
+        } else {
+            // ------------------------------------------------------------ reset write back
+            if (lane < na) {
+                rec[FP_REC_E_INIT + lane] = (uint64_t)__double_as_longlong(e_init);           // stays E0 (Q2)
+                rec[FP_REC_E_CUR + lane] = (uint64_t)__double_as_longlong(ok ? e_next : e_init); // :147
+                double* sprow = prm.setp + e * 4 * na;
+                sprow[0 * na + lane] = sp.pred; sprow[1 * na + lane] = sp.ch;
+                sprow[2 * na + lane] = sp.dis; sprow[3 * na + lane] = sp.qpv;
+            }
+            if (lane == 10) rec[FP_REC_CUM] = 0;
+            if (lane == 11) rec[FP_REC_TIME] = pack2(start, 1);
+            if (lane == 12) rec[FP_REC_HIST] = pack2(0, episode + 1);
+            if (lane == 13) rec[FP_REC_VMASK] = vmask;
+            if (lane == 14) rec[FP_REC_COUNTS] = pack2(vcount, ok ? 0 : FP_FLAG_RESET_FAILED);
+            if (lane == 15) rec[FP_REC_LINES] = pack2((int32_t)lm, sw.iters);
+        }
+    }
+
+    if (MODE == MODE_STEP && prm.stats_partial != nullptr) {
+        if (lane < FP_NSTATS) s_stats[warp][lane] = stat_acc;
+        __syncthreads();
+        if (threadIdx.x < FP_NSTATS) {
+            double s = 0.0;
+            for (int w = 0; w < WARPS_PER_CTA; ++w) s += s_stats[w][threadIdx.x];
+            prm.stats_partial[(int64_t)blockIdx.x * FP_NSTATS + threadIdx.x] += s;   // this CTA owns the row
+        }
+    }
+}
+
+// ------------------------------------------------------------------------ power flow only
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_power_flow(const PfParams prm) {
+    __shared__ DevTopo s_topo;
+    stage_topo(&s_topo, prm.topo);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const LaneTopo lt = load_lane_topo(s_topo, lane);
+    const int nl = prm.nl, nb = prm.nl + 1;
+    const int my_col = s_topo.col[lane];
+    const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
+    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+        double p = 0.0, q = 0.0;
+        if (lane < nl) {
+            p = __ldg(prm.p + e * nl + my_col);
+            q = __ldg(prm.q + e * nl + my_col);
+        }
+        SweepOut sw = distflow_sweep(lt, p, q, lane, prm.tol, prm.max_iter, false);
+        if (lane < nl) {
+            prm.V[e * nb + my_col + 1] = sqrt(sw.v);
+            if (prm.Pl != nullptr) prm.Pl[e * nl + my_col] = sw.P;
+            if (prm.Ql != nullptr) prm.Ql[e * nl + my_col] = sw.Q;
+            if (prm.Isq != nullptr) prm.Isq[e * nl + my_col] = sw.ell;
+        }
+        if (lane == 0) {
+            prm.V[e * nb] = 1.0;
+            if (prm.iters != nullptr) prm.iters[e] = sw.iters;
+            if (prm.fail != nullptr) prm.fail[e] = sw.ok ? 0 : 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------ observations
+// History ring hist[N][na][H][6] fp64.  Pushing call k (0-based since reset) writes slot k % H.
+template <typename OutT>
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
+    __shared__ double s_cur[WARPS_PER_CTA][32];
+    const DevCfg& c = prm.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int na = c.na, H = c.history, nl = c.nl;
+    const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
+    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+        uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
+        const uint64_t tm = rec[FP_REC_TIME], hh = rec[FP_REC_HIST];
+        const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
+        const int32_t cnt = (int32_t)(uint32_t)hh;
+        const int64_t row = (int64_t)start + ((steps > 1) ? (steps - 1) : 1);   // row currently loaded (Q1)
+        double* hist = prm.hist + e * (int64_t)(na * H * 6);
+        // current 6-vector per agent (:376-384): lanes 0 .. 6*na-1
+        const int slot = cnt % H;
+        double cur = 0.0;
+        if (lane < 6 * na) {
+            const int i = lane / 6, f = lane - 6 * i;
+            const int col = prm.agent_col[i];
+            if (f == 0) cur = __ldg(prm.P + row * nl + col);
+            else if (f == 1) cur = __ldg(prm.Q + row * nl + col);
+            else if (f == 2) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + i);
+            else if (f == 3) cur = prm.V[e * c.nb + col + 1];
+            else if (f == 4) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
+            else cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
+            if (prm.push) hist[(i * H + slot) * 6 + f] = cur;
+        }
+        s_cur[warp][lane] = cur;
+        __syncwarp();
+        // window: H entries ending with the current one; entry s (oldest first) is push
+        // number (cnt + 1 - H + s); negative -> zero padding (:393-396)
+        const int W = H * 6;
+        OutT* out = reinterpret_cast<OutT*>(prm.out) + e * (int64_t)(na * W);
+        for (int o = lane; o < na * W; o += 32) {
+            const int i = o / W, r = o - i * W;
+            const int s = r / 6, f = r - 6 * s;
+            const int k = cnt + 1 - H + s;                 // push index of this window entry
+            double x;
+            if (k < 0) x = 0.0;
+            else if (k == cnt) x = s_cur[warp][i * 6 + f];
+            else x = hist[(i * H + (k % H)) * 6 + f];
+            out[o] = (OutT)x;
+        }
+        __syncwarp();
+        if (prm.push && lane == 0) rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_state(const ObsParams prm) {
+    const DevCfg& c = prm.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int na = c.na, nl = c.nl, nb = c.nb;
+    const int W = 3 * nb + 2 * na + 1;
+    const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
+    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+        const uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
+        const uint64_t tm = rec[FP_REC_TIME];
+        const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
+        const int64_t row = (int64_t)start + ((steps > 1) ? (steps - 1) : 1);
+        OutT* out = reinterpret_cast<OutT*>(prm.out) + e * (int64_t)W;
+        for (int o = lane; o < W; o += 32) {
+            double x;
+            int r = o;
+            if (r < nb) x = (r == 0) ? 0.0 : __ldg(prm.P + row * nl + r - 1);               // :361
+            else if ((r -= nb) < nb) x = (r == 0) ? 0.0 : __ldg(prm.Q + row * nl + r - 1);  // :362
+            else if ((r -= nb) < na) x = __ldg(prm.PVP + row * FP_PVP_STRIDE + r);          // :363
+            else if ((r -= na) < nb) x = prm.V[e * nb + r];                                 // :364
+            else if ((r -= nb) < 1) x = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);// :365
+            else { r -= 1; x = __longlong_as_double((long long)rec[FP_REC_E_CUR + r]); }    // :366
+            out[o] = (OutT)x;
+        }
+    }
+}
+
+__global__ void k_stats_fold(const double* __restrict__ partial, int n_blocks, double* __restrict__ out) {
+    const int j = threadIdx.x;
+    if (j < FP_NSTATS) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * FP_NSTATS + j];
+        out[j] = s;
+    }
+}
+
+__global__ void k_pack_pvp(const double* __restrict__ pv, const double* __restrict__ price, int na,
+                           int64_t T, double* __restrict__ pvp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * FP_PVP_STRIDE) return;
+    int64_t t = i / FP_PVP_STRIDE;
+    int f = (int)(i - t * FP_PVP_STRIDE);
+    double x = 0.0;
+    if (f < na) x = pv[t * na + f];
+    else if (f == FP_PVP_PRICE) x = price[t];
+    pvp[i] = x;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------ launchers
+cudaError_t launch_env(int mode, const EnvParams& prm, int grid, cudaStream_t st) {
+    if (mode == MODE_STEP) k_env<MODE_STEP><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    else k_env<MODE_RESET><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_power_flow(const PfParams& prm, int grid, cudaStream_t st) {
+    k_power_flow<<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obs(const ObsParams& prm, int f64, int grid, cudaStream_t st) {
+    if (f64) k_obs<double><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    else k_obs<float><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_state(const ObsParams& prm, int f64, int grid, cudaStream_t st) {
+    if (f64) k_state<double><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    else k_state<float><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st) {
+    k_stats_fold<<<1, 32, 0, st>>>(partial, n_blocks, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_pvp(const double* pv, const double* price, int na, int64_t T, double* pvp,
+                            cudaStream_t st) {
+    int64_t n = T * FP_PVP_STRIDE;
+    k_pack_pvp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, price, na, T, pvp);
+    return cudaGetLastError();
+}
+
+int max_resident_grid(int mode) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t err;
+    if (mode == MODE_STEP) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env<MODE_STEP>, FP_CTA_THREADS, 0);
+    else if (mode == MODE_RESET) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env<MODE_RESET>, FP_CTA_THREADS, 0);
+    else err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_power_flow, FP_CTA_THREADS, 0);
+    if (err != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}

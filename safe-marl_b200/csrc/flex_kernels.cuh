@@ -1,0 +1,54 @@
+// flex_kernels.cuh -- parameter blocks and launcher declarations shared by the kernels
+// (flex_kernels.cu) and the C-ABI host layer (flex_api.cu).
+#pragma once
+#include "flex_common.cuh"
+
+#define FP_CTA_THREADS 256
+#define FP_PVP_STRIDE 8        // packed row: PV[0..na-1], price at slot 5, zero padding (64 B)
+#define FP_PVP_PRICE 5
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_PF = 2 };
+
+struct EnvParams {
+    DevCfg c;
+    const DevTopo* topo;
+    int64_t n;
+    // profile dataset (device): P/Q [T][nl] bus order, PVP [T][8]
+    const double* P; const double* Q; const double* PVP;
+    // per-env state
+    uint64_t* rec; double* V; double* setp;
+    double* pfl; double* qfl; double* isq;       // optional line-flow dump (nullptr = off)
+    // step inputs/outputs
+    const void* actions; int32_t act_f64;
+    double* reward; uint8_t* done; double* info;
+    const uint8_t* mask; const uint8_t* inject;
+    // reset inputs
+    const int32_t* start; const double* e0; const double* a0;
+    uint64_t seed; int64_t env_offset; int32_t random; int32_t start_range;
+    double* stats_partial;                        // [grid][FP_NSTATS]
+};
+
+struct PfParams {
+    const DevTopo* topo;
+    int64_t n; int32_t nl; int32_t max_iter; double tol;
+    const double* p; const double* q;
+    double* V; double* Pl; double* Ql; double* Isq; int32_t* iters; uint8_t* fail;
+};
+
+struct ObsParams {
+    DevCfg c;
+    int64_t n;
+    const double* P; const double* Q; const double* PVP;
+    uint64_t* rec; const double* V; double* hist;
+    int32_t agent_col[8];
+    void* out; int32_t push;
+};
+
+cudaError_t launch_env(int mode, const EnvParams& prm, int grid, cudaStream_t st);
+cudaError_t launch_power_flow(const PfParams& prm, int grid, cudaStream_t st);
+cudaError_t launch_obs(const ObsParams& prm, int f64, int grid, cudaStream_t st);
+cudaError_t launch_state(const ObsParams& prm, int f64, int grid, cudaStream_t st);
+cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st);
+cudaError_t launch_pack_pvp(const double* pv, const double* price, int na, int64_t T, double* pvp,
+                            cudaStream_t st);
+int max_resident_grid(int mode);
