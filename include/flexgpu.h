@@ -209,6 +209,10 @@ int fp_inject_failure(FpHandle* h, const uint8_t* d_mask);
 /* Kernel launches issued through this handle since creation (bench's gpu_launches). */
 int64_t fp_launch_count(const FpHandle* h);
 
+/* sizeof(FpConfig) as compiled into the library -- lets a foreign-language binding verify
+ * its struct layout before the first fp_create. */
+int32_t fp_sizeof_config(void);
+
 #ifdef __cplusplus
 }
 #endif

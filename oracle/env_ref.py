@@ -263,12 +263,13 @@ class RefFlexEnv:
         discomfort = sum(A.discomfort_coeff * power_reduction[b] ** 2 for b in power_reduction)
         vpen = sum(A.voltage_coeff * max(0, v - A.v_max, A.v_min - v) for v in voltages.values())
         reward = revenue - der_cost - ess_cost - discomfort - vpen
+        f = lambda x: float(np.asarray(x).reshape(-1)[0])        # lambda_flex has shape (1,) (:689-694)
         info = {
-            'reward': float(reward), 'revenue': float(revenue), 'der_cost': float(der_cost),
-            'ess_cost': float(ess_cost), 'discomfort_penalty': float(discomfort),
-            'voltage_penalty': float(vpen), 'cumulative_reward': self.cumulative_reward,
+            'reward': f(reward), 'revenue': f(revenue), 'der_cost': f(der_cost),
+            'ess_cost': f(ess_cost), 'discomfort_penalty': f(discomfort),
+            'voltage_penalty': f(vpen), 'cumulative_reward': self.cumulative_reward,
         }
-        return float(reward), info
+        return f(reward), info
 
     # ------------------------------------------------------------- observations
     def get_state(self):                                                            # :358-368

@@ -211,6 +211,7 @@ int fp_destroy(FpHandle* h) {
 const char* fp_last_error(const FpHandle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int64_t fp_n_envs(const FpHandle* h) { return h ? h->n : 0; }
 int64_t fp_launch_count(const FpHandle* h) { return h ? h->launches : 0; }
+int32_t fp_sizeof_config(void) { return (int32_t)sizeof(FpConfig); }
 
 int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const double* h_PV,
                      const double* h_price, int64_t T) {

@@ -68,6 +68,7 @@ _PROTOS = {
     "fp_stats_reset": (C.c_int, [_P, _P]),
     "fp_inject_failure": (C.c_int, [_P, _P]),
     "fp_launch_count": (C.c_int64, [_P]),
+    "fp_sizeof_config": (C.c_int32, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS.keys())
@@ -88,6 +89,8 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        if l.fp_sizeof_config() != C.sizeof(FpConfig):
+            raise FlexGpuError("FpConfig layout mismatch between flexgpu/_lib.py and libflexgpu.so")
         _lib = l
     return _lib
 

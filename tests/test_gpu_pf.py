@@ -1,0 +1,138 @@
+"""GPU parity: the batched DistFlow kernel (fp_power_flow, BASELINE config 2) through the C ABI
+against the oracle -- bit-exact against the C mirror (same operation order), within 1e-6 p.u.
+(observed ~1e-10) against the independent dense-Newton solver and the golden vectors, plus the
+known answers K1/K2 and the residuals of the reference's own equations (utils/pf.py:65-94)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_mirror, ieee33, pf_ref
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_PU = 1e-6          # north_star: voltages and line flows within 1e-6 p.u.
+
+
+@pytest.fixture(scope="module")
+def env(cuda, profiles):
+    from flexgpu import BatchedFlexProvisionEnv
+    e = BatchedFlexProvisionEnv(None, n_envs=8, device=cuda, profiles=profiles)
+    yield e
+    e.close()
+
+
+def _scenarios(network, n, seed, lo=0.7, hi=1.3):
+    """Base loads x U(lo, hi): the scenario generator of safety_signal/data_generation.py:31-36."""
+    rng = np.random.default_rng(seed)
+    p = network.base_p[None, 1:] * rng.uniform(lo, hi, (n, 32))
+    q = network.base_q[None, 1:] * rng.uniform(lo, hi, (n, 32))
+    return p, q
+
+
+def _np(d):
+    return {k: (v.cpu().numpy() if v is not None else None) for k, v in d.items()}
+
+
+def test_base_case_known_answer_K1(env, network):
+    """IEEE-33 base case (Baran & Wu): V_min 0.913090 at bus 18, losses 202.6771 kW / 135.1410 kvar."""
+    out = _np(env.power_flow(network.base_p[None, 1:], network.base_q[None, 1:]))
+    V = out["V"][0]
+    assert V[0] == 1.0 and int(np.argmin(V)) + 1 == 18
+    assert abs(V.min() - 0.913090) < 5e-7
+    R, X = network.r[1:], network.x[1:]
+    assert abs((R * out["Isq"][0]).sum() * 1000 - 202.6771) < 1e-3
+    assert abs((X * out["Isq"][0]).sum() * 1000 - 135.1410) < 1e-3
+    assert not out["failed"][0] and 4 <= out["iters"][0] <= 12
+
+
+def test_run_pf_operating_point_K2(env):
+    """run_pf.py:36-57: Pload 0.1 / Qload 0.005 everywhere, DER setpoints at the 5 buildings."""
+    p = np.full(32, 0.1); q = np.full(32, 0.005)
+    for b in (5, 10, 15, 20, 25):
+        p[b - 2] = 0.1 - 0.05 - 0.075 + 0.005 - 0.0           # pf.py:65-75 with Pred, Ppv, Pesc, Pesd
+    out = _np(env.power_flow(p[None], q[None]))
+    V = out["V"][0]
+    assert abs(V[17] - 0.94137528) < 1e-7 and abs(V[32] - 0.95744575) < 1e-7
+    assert abs((env.network.r[1:] * out["Isq"][0]).sum() - 0.08366532) < 1e-7
+
+
+def test_golden_vectors_newton(env):
+    g = np.load(os.path.join(GOLD, "pf_golden.npz"))
+    out = _np(env.power_flow(g["p"], g["q"]))
+    assert np.max(np.abs(out["V"] - g["V"])) < TOL_PU and np.max(np.abs(out["V"] - g["V"])) < 1e-8
+    assert np.max(np.abs(out["P"] - g["P"])) < TOL_PU
+    assert np.max(np.abs(out["Q"] - g["Q"])) < TOL_PU
+    assert np.max(np.abs(np.sqrt(out["Isq"]) - np.sqrt(g["ell"]))) < TOL_PU
+    assert not out["failed"].any()
+
+
+def test_config2_4096_envs_bit_exact_vs_mirror(env, network, fonet):
+    """BASELINE config 2 at full size; the C mirror has the kernel's op order -> identical bits."""
+    p, q = _scenarios(network, 4096, seed=3)
+    out = _np(env.power_flow(p, q))
+    ref = c_mirror.mirror_power_flow(fonet, p, q)
+    for k in ("V", "P", "Q", "Isq"):
+        assert np.array_equal(out[k], ref[k]), k
+    assert np.array_equal(out["iters"], ref["iters"]) and np.array_equal(out["failed"], ref["failed"])
+
+
+def test_vs_independent_newton_sample(env, network, tree):
+    p, q = _scenarios(network, 64, seed=11, lo=0.2, hi=1.6)
+    out = _np(env.power_flow(p, q))
+    for i in range(0, 64, 4):
+        sol = pf_ref.solve_newton(tree, np.concatenate(([0.0], p[i])), np.concatenate(([0.0], q[i])))
+        assert np.max(np.abs(out["V"][i] - np.sqrt(sol["v"]))) < 1e-8
+        assert np.max(np.abs(out["P"][i] - sol["P"][1:])) < 1e-8
+        assert np.max(np.abs(out["Isq"][i] - sol["ell"][1:])) < 1e-8
+
+
+def test_residuals_of_reference_equations_K3(env, network):
+    """Plug the kernel's outputs into utils/pf.py:65-94; every residual < 1e-8 (tol 1e-9 on v)."""
+    n = 65536
+    p, q = _scenarios(network, n, seed=5, lo=0.1, hi=1.5)
+    out = _np(env.power_flow(p, q))
+    V2 = out["V"] ** 2
+    par = network.parent[1:]                       # parent position of bus position k+1
+    R, X = network.r[1:], network.x[1:]
+    P, Q, L = out["P"], out["Q"], out["Isq"]
+    # balance: P_k = p_k + sum_children (P_c + R_c l_c)
+    child_sum_P = np.zeros_like(P); child_sum_Q = np.zeros_like(Q)
+    for k in range(32):
+        if par[k] > 0:
+            child_sum_P[:, par[k] - 1] += P[:, k] + R[k] * L[:, k]
+            child_sum_Q[:, par[k] - 1] += Q[:, k] + X[k] * L[:, k]
+    assert np.max(np.abs(P - p - child_sum_P)) < 1e-12
+    assert np.max(np.abs(Q - q - child_sum_Q)) < 1e-12
+    assert np.max(np.abs(L * V2[:, 1:] - (P ** 2 + Q ** 2))) < 1e-8          # pf.py:85-88
+    drop = V2[:, par] - 2 * (R * P + X * Q) - (R ** 2 + X ** 2) * L          # pf.py:90-94
+    assert np.max(np.abs(V2[:, 1:] - drop)) < 1e-8
+    assert not out["failed"].any()
+
+
+def test_infeasible_loading_is_reported_not_raised(env, network):
+    """Loads far beyond the feeder's capacity have no high-voltage root: per-env failure flag."""
+    p = np.stack([network.base_p[1:], network.base_p[1:] * 40.0])
+    q = np.stack([network.base_q[1:], network.base_q[1:] * 40.0])
+    out = _np(env.power_flow(p, q))
+    assert list(out["failed"]) == [False, True]
+    assert abs(out["V"][0].min() - 0.913090) < 5e-7
+
+
+def test_optional_outputs_and_ragged_sizes(env, network):
+    """n need not match the handle's n_envs nor a multiple of the CTA's 8 warps; flows optional."""
+    for n in (1, 7, 9, 257):
+        p, q = _scenarios(network, n, seed=n)
+        a = _np(env.power_flow(p, q, want_flows=False))
+        b = _np(env.power_flow(p, q, want_flows=True))
+        assert a["P"] is None and np.array_equal(a["V"], b["V"]) and a["V"].shape == (n, 33)
+    with pytest.raises(ValueError):
+        env.power_flow(np.zeros((4, 31)), np.zeros((4, 31)))
+
+
+def test_linearity_property_light_load(env, network):
+    """As loads -> 0 the DistFlow map is linear (LinDistFlow): V(2x) - 1 ~ 2 (V(x) - 1)."""
+    p, q = _scenarios(network, 16, seed=1)
+    a = _np(env.power_flow(p * 1e-4, q * 1e-4, want_flows=False))["V"]
+    b = _np(env.power_flow(p * 2e-4, q * 2e-4, want_flows=False))["V"]
+    assert np.max(np.abs((b - 1) - 2 * (a - 1))) < 1e-8

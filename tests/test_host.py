@@ -1,0 +1,73 @@
+"""CPU: host-side logic of the product package (no GPU): network parsing, configuration,
+profile generation.  Cross-checked against the oracle's independent restatement."""
+import numpy as np
+import pytest
+
+from flexgpu.config import DEFAULT_ENV_ARGS, make_fp_config, normalize_args
+from flexgpu.network import Network, create_network
+from flexgpu.profiles import Profiles, synthetic_profiles
+
+
+def test_create_network_matches_oracle_restatement(net):
+    mine = create_network(DEFAULT_ENV_ARGS)
+    assert set(mine) == set(net)                                     # utils/create_net.py:27-38 keys
+    for k in ('bus_numbers', 'buildings', 'PVs_at_buildings', 'ESSs_at_buildings'):
+        assert list(mine[k]) == list(net[k])
+    assert set(mine['line_connections']) == set(net['line_connections'])
+    for k in ('line_resistances', 'line_reactances', 'max_line_currents', 'active_power_demand',
+              'reactive_power_demand', 'bus_types'):
+        assert mine[k] == net[k]
+
+
+def test_network_positions_and_parents(network, tree):
+    assert network.n_bus == 33 and network.parent[0] == -1
+    assert np.array_equal(network.parent, tree['parent'])
+    assert np.array_equal(network.r, tree['R']) and np.array_equal(network.x, tree['X'])
+    assert network.position[19] == 18 and network.parent[18] == 1      # bus 19 hangs off bus 2
+    assert network.parent[network.position[26]] == network.position[6]
+
+
+def test_network_rejects_non_radial_or_misplaced_slack():
+    net = create_network(DEFAULT_ENV_ARGS)
+    bad = dict(net); bad['line_connections'] = net['line_connections'] + [(18, 33)]
+    for key in ('line_resistances', 'line_reactances', 'max_line_currents'):
+        bad[key] = dict(net[key]); bad[key][(18, 33)] = 0.01
+    with pytest.raises(ValueError):
+        Network(bad)
+    bad = dict(net); bad['bus_numbers'] = net['bus_numbers'][1:] + [1]
+    with pytest.raises(ValueError):
+        Network(bad)
+
+
+def test_fp_config_values(network):
+    a = normalize_args({"alg": "safemaddpg"})
+    c = make_fp_config(a, network)
+    assert c.n_bus == 33 and c.n_agents == 5 and c.raw_actions == 1
+    assert c.kappa == float.fromhex('0x1.509290e9d53d5p-2') and c.delta_t == 0.25
+    assert list(c.agent_bus) == [4, 9, 14, 19, 24] and c.parent[0] == -1 and c.parent[18] == 1
+    assert make_fp_config(normalize_args(None), network).raw_actions == 0
+    with pytest.raises(ValueError):
+        make_fp_config(normalize_args({"pv_nodes": [5, 10]}), network)      # quirk Q8 guard
+
+
+def test_namedtuple_args_are_accepted():
+    from flexgpu.config import convert
+    a = normalize_args(convert({"history": 12, "seed": 3}))
+    assert a["history"] == 12 and a["seed"] == 3 and a["episode_limit"] == 96
+
+
+def test_synthetic_profiles_shape_and_range(network):
+    p = synthetic_profiles(network, 5, T=960, seed=0)
+    assert p.P.shape == (960, 32) and p.Q.shape == (960, 32) and p.PV.shape == (960, 5) and p.price.shape == (960,)
+    assert p.P.dtype == np.float64 and p.P.flags.c_contiguous
+    assert p.PV.min() >= 0 and p.PV.max() <= 0.15 and np.all(p.PV[0:20] == 0)       # night
+    assert 0.05 <= p.price.min() and p.price.max() <= 0.30
+    ratio = p.P.mean(axis=0) / network.base_p[1:]
+    assert np.all(ratio > 0.3) and np.all(ratio < 1.05)
+    q = synthetic_profiles(network, 5, T=960, seed=0)
+    assert np.array_equal(p.P, q.P) and p.n_days() == 9
+
+
+def test_profiles_validation():
+    with pytest.raises(ValueError):
+        Profiles(np.zeros((10, 32)), np.zeros((9, 32)), np.zeros((10, 5)), np.zeros(10))
