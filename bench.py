@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostics only)")
     ap.add_argument("--with-obs", action="store_true", help="also time step+get_obs (reported as extra)")
+    ap.add_argument("--variant", default="thread", choices=["thread", "warp"], help="kernel variant (see include/flexgpu.h)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -214,7 +215,8 @@ def main():
 
     network = Network(create_network(DEFAULT_ENV_ARGS))
     prof = synthetic_profiles(network, 5, T=args.rows, seed=0)
-    env = BatchedFlexProvisionEnv(None, n_envs=E, device=dev, profiles=prof, seed=5, env_offset=rank * E)
+    env = BatchedFlexProvisionEnv({"kernel_variant": args.variant}, n_envs=E, device=dev, profiles=prof, seed=5,
+                                  env_offset=rank * E)
     env.reset(return_obs=False)
     n_act = 8
     g = torch.Generator(device=dev).manual_seed(2 + rank)
@@ -307,7 +309,7 @@ def main():
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"fused_env_step_{E}_envs_per_gpu (BASELINE config 3; config 5 sharding at N>1)",
-                       "envs_per_gpu": E, "total_envs": total_envs, "profile_rows": args.rows,
+                       "kernel_variant": args.variant, "envs_per_gpu": E, "total_envs": total_envs, "profile_rows": args.rows,
                        "actions": "fp32 uniform(0,1), resident in HBM", "auto_reset_every": EPISODE_STEPS,
                        "l2": "flushed before every timed step (256 MiB memset, untimed)" if not args.no_flush else "NOT flushed",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks",
@@ -317,7 +319,7 @@ def main():
                     "steps": Ke, "api": "BatchedFlexProvisionEnv.step_host -> fp_step_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_env<STEP>", "bytes_per_env_step": B_ALG,
+                         "traffic": None, "kernel": "k_env_t<STEP>" if args.variant == "thread" else "k_env<STEP>", "bytes_per_env_step": B_ALG,
                          "kernel_ms_median": kern_ms, "peak_source": peak_src,
                          "note": "fp64 issue-bound by design of the algorithm (6-7 sweep iterations x 32 lines "
                                  "with an IEEE divide each); see DESIGN.md"},

@@ -24,8 +24,7 @@
  *     unless it says so.  One handle per GPU per process; a handle is not thread-safe.
  *   - there is no CPU fallback: without a CUDA device fp_create fails.
  *
- * Layouts (all row-major, env-major -- one warp owns one environment, so an env's row is
- * the coalesced unit):
+ * Layouts (all row-major, env-major: an env's row is the coalesced unit):
  *   buses are addressed by POSITION in the reference's `bus_numbers` list, slack first
  *   (position 0), as flexibility_provision_env.py:489-490 assumes.  "nl" = n_bus-1 lines;
  *   line k is the line feeding bus position k+1.  "na" = number of agents/buildings.
@@ -51,6 +50,14 @@ enum {
     FP_ESTATE = -3,   /* call sequence error (e.g. step before load_profiles) */
     FP_ENOMEM = -4
 };
+
+/* kernel variants (FpConfig.variant).  Both compute the same DistFlow fixed point; they differ
+ * in the mapping and therefore in floating-point summation order (results agree to ~1e-12):
+ *   THREAD  one CUDA thread per env, sequential sweep in registers -- the throughput path;
+ *           converges on max |dl| <= pf_tol (squared current), default 1e-6.
+ *   WARP    one warp per env, lane = line, shuffle scans -- the lowest latency for tiny
+ *           batches; converges on max |dv| <= pf_tol (squared voltage), default 1e-9. */
+enum { FP_VARIANT_THREAD = 0, FP_VARIANT_WARP = 1 };
 
 /* action dtypes accepted by fp_step */
 enum { FP_F32 = 0, FP_F64 = 1 };
@@ -92,7 +99,9 @@ typedef struct FpConfig {
     int32_t episode_limit;       /* yaml episode_limit */
     int32_t raw_actions;         /* 1 = 'safemaddpg' branch of step (:268-274): setpoints unscaled */
     int32_t pf_max_iter;         /* sweep iteration cap; exceeding it == solver failure */
-    double pf_tol;               /* convergence: max |v_new - v_old| over buses (squared voltage) */
+    int32_t variant;             /* FP_VARIANT_* */
+    int32_t reserved_;
+    double pf_tol;               /* convergence threshold of the sweep, see FP_VARIANT_* */
     double v_min, v_max;
     double e_min, e_max;
     double p_ch_max, p_dis_max;

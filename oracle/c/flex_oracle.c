@@ -29,13 +29,15 @@
 #define ANC_NONE 32u
 
 typedef struct {
-    int32_t nb, nl, na, history, episode_limit, raw_actions, pf_max_iter, pad;
+    int32_t nb, nl, na, history, episode_limit, raw_actions, pf_max_iter, variant;   /* variant: 0 = thread-per-env order, 1 = warp-per-env order */
     double pf_tol, v_min, v_max, e_min, e_max, p_ch_max, p_dis_max, eta_ch, eta_dis;
     double mpr, kappa, pv_cost, ess_cost, discomfort_coeff, voltage_coeff, delta_t, fail_penalty, e_next_lb;
     /* lane tables (pre-order; lane k <-> bus position col[k]+1) */
     double R[NL], X[NL], Z2[NL], imax2[NL];
     int32_t end[NL], col[NL], agent[NL], anc[5][NL];
     int32_t agent_lane[8], agent_col[8];
+    /* thread-per-env tables: lane of the parent line (-1: the slack bus feeds this line) */
+    int32_t par[NL];
 } FoNet;
 
 /* Build lane tables from bus-order arrays: parent[nb] (-1 for slack at 0), r/x/imax[nb]. */
@@ -55,12 +57,13 @@ int fo_build(FoNet* t, int nb, int na, const int32_t* parent, const double* r, c
     for (int k = nl - 1; k >= 0; --k) { int b = bus_of[k]; if (parent[b] != 0) size[parent[b]] += size[b]; }
     for (int k = 0; k < NL; ++k) {
         t->R[k] = t->X[k] = t->Z2[k] = 0.0; t->imax2[k] = INFINITY;
-        t->end[k] = k; t->col[k] = 0; t->agent[k] = -1;
+        t->end[k] = k; t->col[k] = 0; t->agent[k] = -1; t->par[k] = -1;
         for (int j = 0; j < 5; ++j) t->anc[j][k] = ANC_NONE;
     }
     for (int k = 0; k < nl; ++k) {
         int b = bus_of[k];
         t->R[k] = r[b]; t->X[k] = x[b];
+        t->par[k] = parent[b] > 0 ? lane_of[parent[b]] : -1;
         t->Z2[k] = r[b] * r[b] + x[b] * x[b];
         t->imax2[k] = imax[b] > 0.0 ? imax[b] * imax[b] : INFINITY;
         t->end[k] = k + size[b] - 1;
@@ -89,7 +92,7 @@ static void scan32(double* s) {
 typedef struct { double P[NL], Q[NL], ell[NL], v[NL]; int iters; int ok; } Sweep;
 
 /* Lane arrays p, q (length 32, zero beyond nl). */
-static void sweep(const FoNet* t, const double* p, const double* q, double tol, int max_iter, Sweep* o) {
+static void sweep_w(const FoNet* t, const double* p, const double* q, double tol, int max_iter, Sweep* o) {
     double ell[NL], v_old[NL], SP[NL], SQ[NL], d[NL], dn[NL];
     int conv = 0, bad = 0, it = 0;
     for (int k = 0; k < NL; ++k) { ell[k] = 0.0; v_old[k] = 1.0; o->P[k] = o->Q[k] = 0.0; o->v[k] = 1.0; }
@@ -127,6 +130,98 @@ static void sweep(const FoNet* t, const double* p, const double* q, double tol, 
     }
     memcpy(o->ell, ell, sizeof(ell));
     o->iters = it; o->ok = conv && !bad;
+}
+
+
+/* ---- thread-per-env operation order (variant 0) ------------------------------------------
+ * One CUDA thread owns one env and walks the lines sequentially in DFS pre-order:
+ *   backward (k = nl-1 .. 0):  P_k = (p_k + [sum of the non-adjacent children's contributions,
+ *                              latest subtree first]) + [contribution of child k+1],
+ *                              contribution of line c = fma(R_c, l_c, P_c)      (utils/pf.py:65-83)
+ *   forward  (k = 0 .. nl-1):  v_k = v_parent - fma(Z2, l, fma(2X, Q, 2R*P))    (pf.py:90-94)
+ *                              l_k = (P^2 + Q^2) * r,  r = 1/v_k from rcp_seed() + one fp64
+ *                              Newton step (relative error < 1e-13)             (pf.py:85-88)
+ *   stop when max_k |l_new - l_old| <= tol; then one more backward and a final forward pass
+ *   give flows and voltages that satisfy the balance and voltage-drop rows to rounding. */
+/* Branch-free reciprocal seed: exponent-flip initial guess + three fp32 Newton steps (all IEEE
+ * fp32 fused multiply-adds, so the GPU's fp32 pipe and this code agree bit for bit). */
+static double rcp_seed(double v) {
+    float vf = (float)v, x, e;
+    uint32_t i;
+    memcpy(&i, &vf, 4);
+    i = 0x7EF311C7u - i;
+    memcpy(&x, &i, 4);
+    e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
+    e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
+    e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
+    return (double)x;
+}
+
+static void backward_t(const FoNet* t, const double* p, const double* q, const double* ell, double* P, double* Q) {
+    double accP[NL], accQ[NL]; int has[NL];
+    for (int k = 0; k < NL; ++k) has[k] = 0;
+    for (int k = t->nl - 1; k >= 0; --k) {
+        double tp = p[k], tq = q[k];
+        if (has[k]) { tp = tp + accP[k]; tq = tq + accQ[k]; }
+        if (k + 1 < t->nl && t->par[k + 1] == k) {
+            tp = tp + fma(t->R[k + 1], ell[k + 1], P[k + 1]);
+            tq = tq + fma(t->X[k + 1], ell[k + 1], Q[k + 1]);
+        }
+        P[k] = tp; Q[k] = tq;
+        int a = t->par[k];
+        if (a >= 0 && a != k - 1) {                   /* non-adjacent child: deposit into the parent's slot */
+            double xp = fma(t->R[k], ell[k], tp), xq = fma(t->X[k], ell[k], tq);
+            if (has[a]) { accP[a] = accP[a] + xp; accQ[a] = accQ[a] + xq; }
+            else { accP[a] = xp; accQ[a] = xq; has[a] = 1; }
+        }
+    }
+}
+
+static double line_v_t(const FoNet* t, int k, const double* v, double P, double Q, double ell) {
+    double vp = t->par[k] >= 0 ? v[t->par[k]] : 1.0;
+    double d = (t->R[k] + t->R[k]) * P;
+    d = fma(t->X[k] + t->X[k], Q, d);
+    d = fma(t->Z2[k], ell, d);
+    return vp - d;
+}
+
+static void sweep_t(const FoNet* t, const double* p, const double* q, double tol, int max_iter, Sweep* o) {
+    double ell[NL], v[NL], *P = o->P, *Q = o->Q;
+    int conv = 0, bad = 0, it = 0;
+    for (int k = 0; k < NL; ++k) { ell[k] = 0.0; v[k] = 1.0; P[k] = Q[k] = 0.0; }
+    backward_t(t, p, q, ell, P, Q);
+    while (it < max_iter) {
+        ++it;
+        conv = 1;
+        for (int k = 0; k < t->nl; ++k) {
+            double vk = line_v_t(t, k, v, P[k], Q[k], ell[k]);
+            v[k] = vk;
+            float vf = (float)vk;
+            if (!(vf > 0.0f)) bad = 1;
+            double r = rcp_seed(vk);
+            double e = fma(-vk, r, 1.0);
+            r = fma(r, e, r);
+            double s = P[k] * P[k];
+            s = fma(Q[k], Q[k], s);
+            double en = s * r;
+            if (!(fabs(en - ell[k]) <= tol)) conv = 0;
+            ell[k] = en;
+        }
+        backward_t(t, p, q, ell, P, Q);
+        if (bad || conv) break;
+    }
+    for (int k = 0; k < t->nl; ++k) {
+        double vk = line_v_t(t, k, v, P[k], Q[k], ell[k]);
+        v[k] = vk;
+        if (!((float)vk > 0.0f)) bad = 1;
+    }
+    for (int k = 0; k < NL; ++k) { o->v[k] = v[k]; o->ell[k] = ell[k]; }
+    o->iters = it; o->ok = conv && !bad;
+}
+
+static void sweep(const FoNet* t, const double* p, const double* q, double tol, int max_iter, Sweep* o) {
+    if (t->variant == 0) sweep_t(t, p, q, tol, max_iter, o);
+    else sweep_w(t, p, q, tol, max_iter, o);
 }
 
 /* Batched power flow: p/q [n][nl] bus order -> V [n][nb], Pl/Ql/Isq [n][nl] (may be NULL). */
@@ -306,7 +401,9 @@ static void env_core(const FoNet* c, const double* P, const double* Q, const dou
         s->flags[e] = ok ? 0 : 4;
         return;
     }
-    double vpen = xor_sum32(vterm) + slack_pen;
+    double vpen;
+    if (c->variant == 0) { vpen = 0.0; for (int k = 0; k < nl; ++k) vpen = vpen + vterm[k]; vpen = vpen + slack_pen; }
+    else vpen = xor_sum32(vterm) + slack_pen;
     double rev = lam * sp[0].pred, der = c->pv_cost * sp[0].qpv, ess = c->ess_cost * (sp[0].ch + sp[0].dis),
            disc = c->discomfort_coeff * (sp[0].pred * sp[0].pred);
     for (int i = 1; i < na; ++i) {

@@ -27,7 +27,7 @@ def build(force=False):
 class FoNet(C.Structure):
     _fields_ = [
         ("nb", C.c_int32), ("nl", C.c_int32), ("na", C.c_int32), ("history", C.c_int32),
-        ("episode_limit", C.c_int32), ("raw_actions", C.c_int32), ("pf_max_iter", C.c_int32), ("pad", C.c_int32),
+        ("episode_limit", C.c_int32), ("raw_actions", C.c_int32), ("pf_max_iter", C.c_int32), ("variant", C.c_int32),
         ("pf_tol", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double), ("e_min", C.c_double),
         ("e_max", C.c_double), ("p_ch_max", C.c_double), ("p_dis_max", C.c_double), ("eta_ch", C.c_double),
         ("eta_dis", C.c_double), ("mpr", C.c_double), ("kappa", C.c_double), ("pv_cost", C.c_double),
@@ -35,7 +35,7 @@ class FoNet(C.Structure):
         ("delta_t", C.c_double), ("fail_penalty", C.c_double), ("e_next_lb", C.c_double),
         ("R", C.c_double * NL), ("X", C.c_double * NL), ("Z2", C.c_double * NL), ("imax2", C.c_double * NL),
         ("end", C.c_int32 * NL), ("col", C.c_int32 * NL), ("agent", C.c_int32 * NL), ("anc", (C.c_int32 * NL) * 5),
-        ("agent_lane", C.c_int32 * 8), ("agent_col", C.c_int32 * 8),
+        ("agent_lane", C.c_int32 * 8), ("agent_col", C.c_int32 * 8), ("par", C.c_int32 * NL),
     ]
 
 
@@ -49,6 +49,7 @@ class FoState(C.Structure):
     ]
 
 
+DEFAULT_TOL = {0: 1e-8, 1: 1e-9}     # must match flexgpu.config (pf_tol per kernel variant)
 _lib = None
 
 
@@ -67,9 +68,16 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def make_net(tree, args, agent_buses, pf_tol=1e-9, pf_max_iter=32, raw_actions=False,
-             fail_penalty=200.0, e_next_lb=-1e-8):
-    """tree: oracle.ieee33.tree_arrays(net); args: dict with the reference's yaml keys."""
+VARIANT_THREAD, VARIANT_WARP = 0, 1
+
+
+def make_net(tree, args, agent_buses, pf_tol=None, pf_max_iter=32, raw_actions=False,
+             fail_penalty=200.0, e_next_lb=-1e-8, variant=VARIANT_THREAD):
+    """tree: oracle.ieee33.tree_arrays(net); args: dict with the reference's yaml keys.
+    variant selects which kernel's floating-point operation order is mirrored (the thread-per-env
+    kernel converges on max |dl| <= pf_tol, the warp-per-env kernel on max |dv| <= pf_tol)."""
+    if pf_tol is None:
+        pf_tol = DEFAULT_TOL[variant]
     l = lib()
     net = FoNet()
     nb = len(tree['parent'])
@@ -83,6 +91,7 @@ def make_net(tree, args, agent_buses, pf_tol=1e-9, pf_max_iter=32, raw_actions=F
         raise ValueError(f"fo_build failed: {rc}")
     net.history = args['history']; net.episode_limit = args['episode_limit']
     net.raw_actions = 1 if raw_actions else 0
+    net.variant = variant
     net.pf_max_iter = pf_max_iter; net.pf_tol = pf_tol
     net.v_min, net.v_max = args['v_min'], args['v_max']
     net.e_min, net.e_max = args['e_min'], args['e_max']

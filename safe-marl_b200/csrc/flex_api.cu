@@ -19,6 +19,8 @@ struct FpHandle {
     FpConfig cfg;
     DevCfg dc;
     DevTopo topo;
+    ThreadTopo tt;               // thread-per-env tables (by-value kernel parameter)
+    int variant = FP_VARIANT_THREAD, shape = SHAPE_RUNTIME;
     int64_t n = 0;
     int device = 0;
     int64_t T = 0;
@@ -36,7 +38,7 @@ struct FpHandle {
     // staging for the host-buffer entry points
     void* d_act_stage = nullptr; double* d_reward_stage = nullptr; uint8_t* d_done_stage = nullptr;
     double* d_info_stage = nullptr;
-    int grid_step = 0, grid_reset = 0, grid_pf = 0;
+    int grid_step = 0, grid_reset = 0, grid_pf = 0, grid_obs = 0;
     int64_t launches = 0;
     std::string err;
     PredictorState pred;
@@ -58,7 +60,7 @@ static int fail(FpHandle* h, int code, const std::string& msg) {
 
 // ------------------------------------------------------------------ topology preprocessing
 // Pre-order numbering (children visited in ascending bus position) + per-lane tables.
-static int build_topology(const FpConfig& c, DevTopo& t, std::string& err) {
+static int build_topology(const FpConfig& c, DevTopo& t, ThreadTopo& tt, int& shape, std::string& err) {
     const int nb = c.n_bus, nl = nb - 1;
     if (nb < 2 || nb > FP_MAX_BUS) { err = "n_bus must be in [2, 33]"; return FP_EINVAL; }
     if (c.n_agents < 1 || c.n_agents > FP_MAX_AGENTS) { err = "n_agents must be in [1, 5]"; return FP_EINVAL; }
@@ -120,6 +122,29 @@ static int build_topology(const FpConfig& c, DevTopo& t, std::string& err) {
         t.agent_lane[i] = lane_of[b];
         t.agent_col[i] = b - 1;
     }
+    // ---- thread-per-env tables: parent lanes -> carry/slot tables (same constexpr derivation
+    //      the built-in shapes use at compile time)
+    std::memset(&tt, 0, sizeof(tt));
+    int8_t par_lane[FP_NL];
+    for (int k = 0; k < FP_NL; ++k) par_lane[k] = -1;
+    for (int k = 0; k < nl; ++k) {
+        int b = bus_of[k];
+        par_lane[k] = (int8_t)((c.parent[b] > 0) ? lane_of[c.parent[b]] : -1);
+    }
+    const TreeTables tb = derive_tree_tables(par_lane, nl);
+    bool any_imax = false;
+    for (int k = 0; k < FP_NL; ++k) {
+        tt.R[k] = t.R[k]; tt.X[k] = t.X[k]; tt.R2[k] = t.R[k] + t.R[k]; tt.X2[k] = t.X[k] + t.X[k];
+        tt.Z2[k] = t.Z2[k]; tt.imax2[k] = t.imax2[k];
+        any_imax = any_imax || (k < nl && std::isfinite(t.imax2[k]));
+        tt.par_src[k] = tb.par_src[k]; tt.own_slot[k] = tb.own_slot[k]; tt.dep_slot[k] = tb.dep_slot[k];
+        tt.dep_first[k] = tb.dep_first[k]; tt.next_is_child[k] = tb.next_is_child[k];
+        tt.col[k] = (int8_t)t.col[k];
+    }
+    for (int k = 0; k < nl; ++k) tt.lane_of_col[t.col[k]] = (int8_t)k;
+    for (int i = 0; i < 8; ++i) { tt.agent_lane[i] = (int8_t)t.agent_lane[i]; tt.agent_col[i] = (int8_t)t.agent_col[i]; }
+    tt.nl = nl; tt.n_slots = tb.n_slots; tt.any_imax = any_imax ? 1 : 0;
+    shape = thread_shape_of(tt, par_lane);
     return FP_OK;
 }
 
@@ -161,8 +186,15 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     if (!h) return fail(nullptr, FP_ENOMEM, "fp_create: out of host memory");
     h->cfg = *cfg; h->n = n_envs; h->device = device;
     std::string err;
-    int rc = build_topology(*cfg, h->topo, err);
+    int rc = build_topology(*cfg, h->topo, h->tt, h->shape, err);
     if (rc != FP_OK) { delete h; return fail(nullptr, rc, "fp_create: " + err); }
+    if (cfg->variant != FP_VARIANT_THREAD && cfg->variant != FP_VARIANT_WARP) {
+        delete h; return fail(nullptr, FP_EINVAL, "fp_create: unknown kernel variant");
+    }
+    h->variant = cfg->variant;
+    if (h->variant == FP_VARIANT_THREAD && h->tt.n_slots > FP_MAX_SLOTS) {
+        delete h; return fail(nullptr, FP_EINVAL, "fp_create: more than 8 branching buses; use FP_VARIANT_WARP");
+    }
     fill_devcfg(*cfg, h->dc);
     const int nb = cfg->n_bus, na = cfg->n_agents, H = cfg->history;
 #define CREATE_TRY(expr)                                                                   \
@@ -185,10 +217,22 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     CREATE_TRY(cudaMemset(h->d_setp, 0, (size_t)n_envs * 4 * na * 8));
     CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_envs * na * H * 6 * 8));
     CREATE_TRY(cudaMemset(h->d_hist, 0, (size_t)n_envs * na * H * 6 * 8));
-    h->grid_step = grid_for(n_envs, max_resident_grid(MODE_STEP));
-    h->grid_reset = grid_for(n_envs, max_resident_grid(MODE_RESET));
-    h->grid_pf = max_resident_grid(MODE_PF);
-    h->stats_rows = max_resident_grid(MODE_STEP);
+    h->grid_obs = grid_for(n_envs, max_resident_grid(MODE_STEP));
+    if (h->variant == FP_VARIANT_THREAD) {
+        CREATE_TRY(thread_kernels_configure(FP_MAX_SLOTS));
+        const int64_t tiles = (n_envs + 31) / 32;
+        const int cap_step = thread_kernel_max_grid(MODE_STEP, h->tt.n_slots, h->shape);
+        const int cap_reset = thread_kernel_max_grid(MODE_RESET, h->tt.n_slots, h->shape);
+        h->grid_step = (int)((tiles < cap_step) ? tiles : cap_step);
+        h->grid_reset = (int)((tiles < cap_reset) ? tiles : cap_reset);
+        h->grid_pf = thread_kernel_max_grid(MODE_PF, h->tt.n_slots, h->shape);
+        h->stats_rows = cap_step;
+    } else {
+        h->grid_step = grid_for(n_envs, max_resident_grid(MODE_STEP));
+        h->grid_reset = grid_for(n_envs, max_resident_grid(MODE_RESET));
+        h->grid_pf = max_resident_grid(MODE_PF);
+        h->stats_rows = max_resident_grid(MODE_STEP);
+    }
     CREATE_TRY(cudaMalloc(&h->d_stats_partial, (size_t)h->stats_rows * FP_NSTATS * 8));
     CREATE_TRY(cudaMemset(h->d_stats_partial, 0, (size_t)h->stats_rows * FP_NSTATS * 8));
 #undef CREATE_TRY
@@ -253,6 +297,16 @@ static void fill_env_params(FpHandle* h, EnvParams& p) {
     p.start_range = h->start_range;
 }
 
+static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cudaStream_t st) {
+    const int grid = (mode == MODE_STEP) ? h->grid_step : h->grid_reset;
+    if (h->variant == FP_VARIANT_THREAD) {
+        EnvParamsT pt;
+        pt.e = p; pt.t = h->tt;
+        return launch_env_t(mode, h->shape, pt, grid, st);
+    }
+    return launch_env(mode, p, grid, st);
+}
+
 int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const double* d_a0,
              const uint8_t* d_mask, void* stream) {
     if (!h) return FP_EINVAL;
@@ -261,7 +315,7 @@ int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const doub
     EnvParams p; fill_env_params(h, p);
     p.start = d_start; p.e0 = d_e0; p.a0 = d_a0; p.mask = d_mask; p.random = 0;
     p.inject = nullptr;
-    CUDA_TRY(h, launch_env(MODE_RESET, p, h->grid_reset, (cudaStream_t)stream));
+    CUDA_TRY(h, launch_env_any(h, MODE_RESET, p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
 }
@@ -272,7 +326,7 @@ int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_
     EnvParams p; fill_env_params(h, p);
     p.mask = d_mask; p.random = 1; p.seed = seed; p.env_offset = env_offset;
     p.inject = nullptr;
-    CUDA_TRY(h, launch_env(MODE_RESET, p, h->grid_reset, (cudaStream_t)stream));
+    CUDA_TRY(h, launch_env_any(h, MODE_RESET, p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
 }
@@ -287,7 +341,7 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     p.actions = d_actions; p.act_f64 = (act_dtype == FP_F64);
     p.reward = d_reward; p.done = d_done; p.info = d_info; p.mask = d_mask;
     p.stats_partial = h->d_stats_partial;
-    CUDA_TRY(h, launch_env(MODE_STEP, p, h->grid_step, (cudaStream_t)stream));
+    CUDA_TRY(h, launch_env_any(h, MODE_STEP, p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
 }
@@ -330,7 +384,7 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_obs: bad arguments");
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
-    CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_step, (cudaStream_t)stream));
+    CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
 }
@@ -340,7 +394,7 @@ int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream) {
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_state: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_state: bad arguments");
     ObsParams p; fill_obs_params(h, p, d_out, 0);
-    CUDA_TRY(h, launch_state(p, dtype == FP_F64, h->grid_step, (cudaStream_t)stream));
+    CUDA_TRY(h, launch_state(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
 }
@@ -380,7 +434,14 @@ int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, 
     PfParams p;
     p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol;
     p.p = d_p; p.q = d_q; p.V = d_V; p.Pl = d_Pl; p.Ql = d_Ql; p.Isq = d_Isq; p.iters = d_iters; p.fail = d_fail;
-    CUDA_TRY(h, launch_power_flow(p, grid_for(n, h->grid_pf), (cudaStream_t)stream));
+    if (h->variant == FP_VARIANT_THREAD) {
+        PfParamsT pt;
+        pt.p = p; pt.t = h->tt;
+        const int64_t tiles = (n + 31) / 32;
+        CUDA_TRY(h, launch_power_flow_t(h->shape, pt, (int)((tiles < h->grid_pf) ? tiles : h->grid_pf), (cudaStream_t)stream));
+    } else {
+        CUDA_TRY(h, launch_power_flow(p, grid_for(n, h->grid_pf), (cudaStream_t)stream));
+    }
     h->launches++;
     return FP_OK;
 }

@@ -44,6 +44,73 @@ struct DevTopo {
     int32_t agent_col[8];      // dataset column of agent i's bus
 };
 
+// Topology tables of the thread-per-env kernels.  Passed BY VALUE inside the kernel parameter
+// block: after full unrolling every entry is a compile-time offset into the constant bank, so
+// impedances feed DFMA directly as constant operands and the flags become uniform predicates.
+// "Slots" are per-thread shared-memory cells for the few buses with more than one child
+// (IEEE-33: buses 2, 3, 6): the parent voltage for non-adjacent children (forward sweep) and
+// the accumulated contributions of non-adjacent children (backward sweep).
+#define FP_MAX_SLOTS 8
+#define TT_ROOT (-1)         // par_src: the slack bus feeds this line (v_parent = 1)
+#define TT_CARRY (-2)        // par_src / dep_slot: parent is lane k-1 -> value carried in a register
+struct ThreadTopo {
+    double R[FP_NL], X[FP_NL], R2[FP_NL], X2[FP_NL], Z2[FP_NL], imax2[FP_NL];
+    int8_t par_src[FP_NL];    // forward: TT_ROOT, TT_CARRY or the slot holding v_parent
+    int8_t own_slot[FP_NL];   // slot owned by this lane's bus (it has non-adjacent children), else -1
+    int8_t dep_slot[FP_NL];   // backward: TT_ROOT (nothing), TT_CARRY (to lane k-1) or slot to deposit into
+    int8_t dep_first[FP_NL];  // first deposit into that slot in a backward pass (store, not add)
+    int8_t next_is_child[FP_NL];  // parent(lane k+1) == lane k
+    int8_t col[FP_NL];        // dataset column (bus position - 1) of this lane's bus
+    int8_t lane_of_col[FP_NL];
+    int8_t agent_lane[8], agent_col[8];
+    int32_t nl, n_slots, any_imax, pad_;
+};
+
+// Slot / carry tables derived from the DFS parent-lane array.  constexpr: evaluated at compile
+// time for the built-in shapes and at run time (host) for any other radial feeder.
+struct TreeTables {
+    int8_t par_src[FP_NL], own_slot[FP_NL], dep_slot[FP_NL], dep_first[FP_NL], next_is_child[FP_NL];
+    int n_slots;
+};
+
+template <class ParArray>
+constexpr TreeTables derive_tree_tables(const ParArray& par, int nl) {
+    TreeTables t{};
+    for (int k = 0; k < FP_NL; ++k) {
+        t.par_src[k] = TT_ROOT; t.own_slot[k] = -1; t.dep_slot[k] = TT_ROOT; t.dep_first[k] = 0; t.next_is_child[k] = 0;
+    }
+    t.n_slots = 0;
+    for (int a = 0; a < nl; ++a) {                       // slots in increasing lane order of their owner
+        bool has = false;
+        for (int j = a + 2; j < nl; ++j) if (par[j] == a) has = true;
+        if (has) t.own_slot[a] = (int8_t)t.n_slots++;
+    }
+    for (int j = 0; j < nl; ++j) {
+        const int a = par[j];
+        if (a < 0) continue;
+        if (a == j - 1) { t.par_src[j] = TT_CARRY; t.dep_slot[j] = TT_CARRY; t.next_is_child[a] = 1; }
+        else {
+            t.par_src[j] = t.own_slot[a]; t.dep_slot[j] = t.own_slot[a];
+            bool later = false;                          // reverse pre-order: the highest lane deposits first
+            for (int m = j + 1; m < nl; ++m) if (par[m] == a) later = true;
+            t.dep_first[j] = later ? 0 : 1;
+        }
+    }
+    return t;
+}
+
+// IEEE 33-bus feeder (Baran & Wu), DFS pre-order with children in ascending bus position:
+// lanes 0-16 = buses 2..18, 17-24 = buses 26..33 (off bus 6), 25-27 = buses 23..25 (off bus 3),
+// 28-31 = buses 19..22 (off bus 2).
+struct Ieee33Tree {
+    static constexpr int NL = 32;
+    static constexpr int8_t PAR[FP_NL] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+                                          4, 17, 18, 19, 20, 21, 22, 23, 1, 25, 26, 0, 28, 29, 30};
+    static constexpr int8_t COL[FP_NL] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16,
+                                          24, 25, 26, 27, 28, 29, 30, 31, 21, 22, 23, 17, 18, 19, 20};
+};
+enum { SHAPE_RUNTIME = 0, SHAPE_IEEE33 = 1 };
+
 struct LaneTopo {
     double R, X, Z2;
     int32_t end;

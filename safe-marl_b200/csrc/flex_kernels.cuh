@@ -44,6 +44,18 @@ struct ObsParams {
     void* out; int32_t push;
 };
 
+// thread-per-env kernels (flex_thread_kernels.cu): same parameter blocks + the by-value topology
+struct EnvParamsT { EnvParams e; ThreadTopo t; };
+struct PfParamsT { PfParams p; ThreadTopo t; };
+enum { VARIANT_THREAD = 0, VARIANT_WARP = 1 };
+
+cudaError_t launch_env_t(int mode, int shape, const EnvParamsT& prm, int grid, cudaStream_t st);
+cudaError_t launch_power_flow_t(int shape, const PfParamsT& prm, int grid, cudaStream_t st);
+cudaError_t thread_kernels_configure(int n_slots);
+int thread_kernel_max_grid(int mode, int n_slots, int shape);
+int thread_shape_of(const ThreadTopo& t, const int8_t* par_lane);
+size_t thread_kernel_smem_bytes(int n_slots);
+
 cudaError_t launch_env(int mode, const EnvParams& prm, int grid, cudaStream_t st);
 cudaError_t launch_power_flow(const PfParams& prm, int grid, cudaStream_t st);
 cudaError_t launch_obs(const ObsParams& prm, int f64, int grid, cudaStream_t st);

@@ -16,6 +16,8 @@ FP_INFO_STRIDE = 8
 FP_NSTATS = 16
 FP_REC_STRIDE = 16
 FP_F32, FP_F64 = 0, 1
+VARIANT_THREAD, VARIANT_WARP = 0, 1
+VARIANTS = {"thread": VARIANT_THREAD, "warp": VARIANT_WARP}
 
 # record slots (include/flexgpu.h FP_REC_*)
 REC_E_INIT, REC_E_CUR, REC_CUM, REC_TIME, REC_HIST, REC_VMASK, REC_COUNTS, REC_LINES = 0, 5, 10, 11, 12, 13, 14, 15
@@ -32,6 +34,7 @@ class FpConfig(C.Structure):
     _fields_ = [
         ("n_bus", C.c_int32), ("n_agents", C.c_int32), ("history", C.c_int32),
         ("episode_limit", C.c_int32), ("raw_actions", C.c_int32), ("pf_max_iter", C.c_int32),
+        ("variant", C.c_int32), ("reserved_", C.c_int32),
         ("pf_tol", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double),
         ("e_min", C.c_double), ("e_max", C.c_double), ("p_ch_max", C.c_double),
         ("p_dis_max", C.c_double), ("eta_ch", C.c_double), ("eta_dis", C.c_double),

@@ -21,11 +21,16 @@ DEFAULT_ENV_ARGS = dict(
 
 # Solver knobs that the reference leaves to IPOPT's defaults (utils/pf.py:101-102).
 DEFAULT_SOLVER_ARGS = dict(
-    pf_tol=1e-9,        # max |dv| (squared voltage) between sweeps; see DESIGN.md "convergence"
+    kernel_variant="thread",  # "thread" (one thread per env, throughput) | "warp" (one warp per env)
+    pf_tol=None,        # None -> DEFAULT_PF_TOL[variant]; see DESIGN.md "convergence"
     pf_max_iter=32,     # exceeding it counts as solver failure (:314-337)
     fail_penalty=200.0,  # :336
     e_next_lb=-1e-8,    # E_next >= 0 (pf.py:46) relaxed by IPOPT's bound_relax_factor
 )
+
+
+# thread variant: max |dl| (squared current) between sweeps; warp variant: max |dv| (squared voltage)
+DEFAULT_PF_TOL = {"thread": 1e-6, "warp": 1e-9}
 
 
 def convert(dictionary):
@@ -70,7 +75,11 @@ def make_fp_config(args, network):
     c.episode_limit = int(args["episode_limit"])
     c.raw_actions = 1 if args.get("alg", None) == "safemaddpg" else 0
     c.pf_max_iter = int(args["pf_max_iter"])
-    c.pf_tol = float(args["pf_tol"])
+    variant = args.get("kernel_variant", "thread")
+    if variant not in _lib.VARIANTS:
+        raise ValueError("kernel_variant must be 'thread' or 'warp'")
+    c.variant = _lib.VARIANTS[variant]
+    c.pf_tol = float(DEFAULT_PF_TOL[variant] if args.get("pf_tol") is None else args["pf_tol"])
     c.v_min, c.v_max = float(args["v_min"]), float(args["v_max"])
     c.e_min, c.e_max = float(args["e_min"]), float(args["e_max"])
     c.p_ch_max, c.p_dis_max = float(args["p_ch_max"]), float(args["p_dis_max"])

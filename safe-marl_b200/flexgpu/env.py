@@ -56,6 +56,7 @@ class BatchedFlexProvisionEnv:
         self.history = self.args_dict["history"]                       # :65
         self.obs_size = 6 * self.history if self.history > 1 else 6
         self.state_size = 3 * self.n_bus + 2 * self.n_agents + 1
+        self.kernel_variant = self.args_dict["kernel_variant"]
         self.seed = int(self.args_dict["seed"] if seed is None else seed)
         self.env_offset = int(env_offset)
 
@@ -73,7 +74,7 @@ class BatchedFlexProvisionEnv:
         N, na, nb = self.n_envs, self.n_agents, self.n_bus
         dev = self.device
         self._reward = torch.empty(N, dtype=torch.float64, device=dev)
-        self._done = torch.empty(N, dtype=torch.uint8, device=dev)
+        self._done = torch.zeros(N, dtype=torch.bool, device=dev)      # one byte per env, written as uint8
         self._info = torch.empty(N, _lib.FP_INFO_STRIDE, dtype=torch.float64, device=dev)
         self._obs = {}
         self._state = {}
@@ -262,7 +263,7 @@ class BatchedFlexProvisionEnv:
         self._check(self._lib.fp_step(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
                                       _ptr(self._info) if want_info else None, _ptr(m), _stream()), "fp_step")
         info = {k: self._info[:, i] for i, k in enumerate(_lib.INFO_KEYS)} if want_info else {}
-        return self._reward, self._done.bool(), info
+        return self._reward, self._done, info
 
     def step_host(self, actions, want_info=False):
         """End-to-end variant: host (numpy, ideally pinned) in, host out, through fp_step_host."""

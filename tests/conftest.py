@@ -40,8 +40,22 @@ def tree(net):
 
 @pytest.fixture(scope="session")
 def fonet(tree, args):
+    """C mirror in the default (thread-per-env) operation order."""
     from oracle import c_mirror
     return c_mirror.make_net(tree, args, args["buildings"])
+
+
+@pytest.fixture(scope="session")
+def fonets(tree, args):
+    """C mirrors keyed by kernel variant name."""
+    from oracle import c_mirror
+    return {"thread": c_mirror.make_net(tree, args, args["buildings"], variant=c_mirror.VARIANT_THREAD),
+            "warp": c_mirror.make_net(tree, args, args["buildings"], variant=c_mirror.VARIANT_WARP)}
+
+
+@pytest.fixture(params=["thread", "warp"])
+def variant(request):
+    return request.param
 
 
 @pytest.fixture(scope="session")
