@@ -108,6 +108,12 @@ struct Ieee33Tree {
                                           4, 17, 18, 19, 20, 21, 22, 23, 1, 25, 26, 0, 28, 29, 30};
     static constexpr int8_t COL[FP_NL] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16,
                                           24, 25, 26, 27, 28, 29, 30, 31, 21, 22, 23, 17, 18, 19, 20};
+    // emission order of the unrolled sweeps (parents before children): main feeder (chain 0)
+    // interleaved with the three laterals (chain 1), each lateral after its branch bus
+    static constexpr int8_t ORDER[FP_NL] = {0, 1, 28, 2, 29, 3, 30, 4, 31, 5, 25, 6, 26, 7, 27, 8, 17,
+                                            9, 18, 10, 19, 11, 20, 12, 21, 13, 22, 14, 23, 15, 24, 16};
+    static constexpr int8_t CHAIN[FP_NL] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
 };
 enum { SHAPE_RUNTIME = 0, SHAPE_IEEE33 = 1 };
 
