@@ -199,6 +199,47 @@ int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, 
                   double* d_Pl, double* d_Ql, double* d_Isq, int32_t* d_iters, uint8_t* d_fail,
                   void* stream);
 
+/* -- device replay ring (utils/replay_buffer.py:3-30, TransReplayBuffer) ------------------- */
+
+/* A FIFO of `capacity` transitions held as struct-of-arrays fp32 fields on the device
+ * (field f: [capacity][widths[f]]).  Head/length bookkeeping lives on the host, so no call
+ * synchronises.  Producers reserve rows and write their fields in place (fp_predict does so
+ * directly from its epilogue); the learner reads a contiguous window like get_batch. */
+typedef struct FpReplay FpReplay;
+int fp_replay_create(int64_t capacity, int32_t n_fields, const int32_t* widths, int device, FpReplay** out);
+int fp_replay_destroy(FpReplay* r);
+const char* fp_replay_last_error(const FpReplay* r);   /* r may be NULL: last fp_replay_create error */
+int64_t fp_replay_len(const FpReplay* r);               /* len(self.buffer) */
+int64_t fp_replay_capacity(const FpReplay* r);
+int fp_replay_clear(FpReplay* r);                       /* clear() (:29-30) */
+/* add_experience (:23-27) for n rows at once: returns the ring position of the first row in
+ * *pos; when the ring is full the oldest rows are overwritten (offset(), :11-12). */
+int fp_replay_reserve(FpReplay* r, int64_t n, int64_t* pos);
+/* copy d_src[n][width(field)] into the rows reserved at pos (wraps at capacity) */
+int fp_replay_write(FpReplay* r, int32_t field, int64_t pos, int64_t n, const float* d_src, void* stream);
+/* get_batch / get_truncated_episodes_batch (:14-21): `batch` CONSECUTIVE rows starting at
+ * logical index `start` (0 = oldest; the caller draws start ~ U{0..len-batch} as :18 does).
+ * d_out: HOST array of n_fields DEVICE pointers, out[f] = [batch][width(f)]; NULL entries skipped. */
+int fp_replay_sample(FpReplay* r, int64_t start, int64_t batch, float* const* d_out, void* stream);
+int fp_replay_field_ptr(FpReplay* r, int32_t field, float** d_ptr);
+
+/* -- voltage predictor + safety penalty (BASELINE config 4) ------------------------------- */
+
+/* Replaces the fitted regressor of safety_signal/train_safety_signal_model.py:33-46,73 as an
+ * affine map Vhat = A x + c on RAW inputs: the caller folds the MinMax scalers into A [n_out][n_in]
+ * and c [n_out] (host, fp64).  x is interleaved [P1,Q1,...,P33,Q33] (data_generation.py:48-50).
+ * The safemaddpg row-sum quirk (safemaddpg.py:266,272) is the same map with a 2-banded A.
+ * v_min / v_max / slack_weight define the slack penalty of safemaddpg.py:205-229:
+ *   penalty = slack_weight * sum_i (max(0, v_min - Vhat_i) + max(0, Vhat_i - v_max)). */
+int fp_predictor_load(FpHandle* h, int32_t n_in, int32_t n_out, const double* h_A, const double* h_c,
+                      double v_min, double v_max, double slack_weight);
+/* Batched inference on tcgen05 tensor cores (3xTF32, fp32 accumulate): d_X [n][66] fp32 (16-byte
+ * aligned) -> d_vhat [n][33] fp32 and d_penalty [n] fp64 (either may be NULL).  If sink != NULL the
+ * results are ALSO written straight into the replay ring rows pos .. pos+n-1 (mod capacity) of
+ * fields f_vhat (width 33) / f_penalty (width 1); a negative field index skips that output. */
+int fp_predict(FpHandle* h, int64_t n, const float* d_X, float* d_vhat, double* d_penalty, FpReplay* sink,
+               int32_t f_vhat, int32_t f_penalty, int64_t pos, void* stream);
+
 /* -- episode statistics (the only cross-GPU reduction; madrl/models/model.py:247-265) ----- */
 
 /* Every fp_step adds, per stepped env, to a device vector of FP_NSTATS doubles:

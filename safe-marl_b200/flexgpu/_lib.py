@@ -72,6 +72,18 @@ _PROTOS = {
     "fp_inject_failure": (C.c_int, [_P, _P]),
     "fp_launch_count": (C.c_int64, [_P]),
     "fp_sizeof_config": (C.c_int32, []),
+    "fp_replay_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int, C.POINTER(_P)]),
+    "fp_replay_destroy": (C.c_int, [_P]),
+    "fp_replay_last_error": (C.c_char_p, [_P]),
+    "fp_replay_len": (C.c_int64, [_P]),
+    "fp_replay_capacity": (C.c_int64, [_P]),
+    "fp_replay_clear": (C.c_int, [_P]),
+    "fp_replay_reserve": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64)]),
+    "fp_replay_write": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "fp_replay_sample": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(_P), _P]),
+    "fp_replay_field_ptr": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "fp_predictor_load": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double]),
+    "fp_predict": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS.keys())

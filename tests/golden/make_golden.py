@@ -78,7 +78,24 @@ def env_golden():
         np.savez_compressed(os.path.join(HERE, f"env_golden_{tag}.npz"), **rec)
 
 
+def predictor_golden():
+    """scikit-learn's own fit + predict (the reference's pipeline, train_safety_signal_model.py:33-46,73)
+    on 1000 scenarios generated as data_generation.py:27-58 does, oracle power flow in place of IPOPT."""
+    from oracle import predictor_ref
+    X, Y = predictor_ref.generate_scenarios(1000, seed=0)
+    model, sx, sy = predictor_ref.fit_pipeline(X, Y)
+    rng = np.random.RandomState(3)
+    Xt = X[rng.choice(len(X), 48, replace=False)] * (1 + rng.uniform(-0.6, 0.6, (48, 66)))   # some far outside the fit range
+    Xt[40:] *= 3.0                                                                         # heavy loading -> under-voltage
+    Vt = predictor_ref.predict(model, sx, sy, Xt)
+    coef = np.array([e.coef_ for e in model.estimators_]); icpt = np.array([e.intercept_ for e in model.estimators_])
+    np.savez_compressed(os.path.join(HERE, "predictor_golden.npz"), coef=coef, intercept=icpt, x_scale=sx.scale_,
+                        x_min=sx.min_, y_scale=sy.scale_, y_min=sy.min_, X=Xt, V=Vt,
+                        penalty=predictor_ref.slack_penalty(Vt), V_rowsum=predictor_ref.rowsum_predict(coef, icpt, Xt))
+
+
 if __name__ == "__main__":
     pf_golden()
     env_golden()
+    predictor_golden()
     print("golden fixtures written to", HERE)

@@ -1,0 +1,138 @@
+"""GPU parity: the tcgen05 voltage predictor + safety penalty (fp_predict) and the device replay
+ring (fp_replay_*) through the C ABI.
+
+Tolerances: the kernel computes in 3xTF32 with fp32 accumulation and fp32 outputs, so Vhat is
+compared with scikit-learn's fp64 predict at 1e-6 p.u. (north_star's voltage tolerance; observed
+~2e-7) and the penalty at 1000 x 33 x that bound; ring contents are compared bit for bit with
+the dense output."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import predictor_ref, replay_ref
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "predictor_golden.npz")
+TOL_V = 1e-6
+
+
+@pytest.fixture(scope="module")
+def env(cuda, profiles):
+    from flexgpu import BatchedFlexProvisionEnv
+    e = BatchedFlexProvisionEnv(None, n_envs=8, device=cuda, profiles=profiles)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def pred(env, gold):
+    from flexgpu.predictor import VoltagePredictor
+    return VoltagePredictor.from_linear_model(env, gold["coef"], gold["intercept"], gold["x_scale"], gold["x_min"],
+                                              gold["y_scale"], gold["y_min"])
+
+
+def test_golden_vectors_sklearn_predict(pred, gold, cuda):
+    X = torch.from_numpy(gold["X"].astype(np.float32)).to(cuda)
+    vhat, pen = pred.predict(X)
+    # the kernel sees fp32 inputs: compare with sklearn evaluated on the same rounded inputs
+    want = predictor_ref.affine_predict(pred.A, pred.c, gold["X"].astype(np.float32).astype(np.float64))
+    assert np.max(np.abs(vhat.cpu().numpy() - want)) < TOL_V
+    assert np.max(np.abs(vhat.cpu().numpy() - gold["V"])) < 5e-6          # incl. the fp32 rounding of the inputs
+    wantp = predictor_ref.slack_penalty(vhat.cpu().numpy().astype(np.float64))
+    assert np.allclose(pen.cpu().numpy(), wantp, rtol=1e-12, atol=1e-9)    # fp64 penalty of the fp32 Vhat: exact arithmetic
+    assert np.max(np.abs(pen.cpu().numpy() - gold["penalty"])) < 1000 * 33 * 5e-6
+    assert int((pen == 0).sum()) >= 5 and float(pen.max()) > 1000.0
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 255, 1000, 4097])
+def test_ragged_sizes_and_random_models(env, cuda, n):
+    """Odd sizes take the non-TMA tail path; every row depends only on its own inputs."""
+    from flexgpu.predictor import VoltagePredictor
+    rng = np.random.default_rng(n)
+    A = rng.normal(0, 0.2, (33, 66)); c = rng.normal(1.0, 0.05, 33)
+    p = VoltagePredictor(env, A, c)
+    X = rng.uniform(-0.5, 0.5, (n, 66)).astype(np.float32)
+    vhat, pen = p.predict(torch.from_numpy(X).to(cuda))
+    want = predictor_ref.affine_predict(A, c, X.astype(np.float64))
+    assert vhat.shape == (n, 33) and np.max(np.abs(vhat.cpu().numpy() - want)) < 2e-6
+    assert np.allclose(pen.cpu().numpy(), predictor_ref.slack_penalty(vhat.cpu().numpy().astype(np.float64)), rtol=1e-12, atol=1e-9)
+
+
+def test_rowsum_quirk_form(env, gold, cuda):
+    from flexgpu.predictor import VoltagePredictor
+    p = VoltagePredictor.from_safemaddpg_rowsum(env, gold["coef"], gold["intercept"])
+    X32 = gold["X"].astype(np.float32)
+    vhat, _ = p.predict(torch.from_numpy(X32).to(cuda))
+    want = predictor_ref.rowsum_predict(gold["coef"], gold["intercept"], X32.astype(np.float64))
+    assert np.max(np.abs(vhat.cpu().numpy() - want)) < TOL_V * max(1.0, np.abs(want).max())
+
+
+def test_epilogue_writes_straight_into_the_replay_ring_with_wraparound(pred, cuda):
+    from flexgpu.predictor import DeviceReplayBuffer
+    buf = DeviceReplayBuffer(1000, {"obs": 7, "v_pred": 33, "safety_penalty": 1}, device=cuda)
+    ref = replay_ref.RefTransReplayBuffer(1000)
+    rng = np.random.default_rng(0)
+    for step in range(5):                                     # 5 x 300 rows into a 1000-row ring: wraps twice
+        X = torch.from_numpy(rng.uniform(0, 0.6, (300, 66)).astype(np.float32)).to(cuda)
+        obs = torch.from_numpy(rng.uniform(0, 1, (300, 7)).astype(np.float32)).to(cuda)
+        pos = buf.reserve(300)
+        buf.write("obs", pos, obs)
+        vhat, pen = pred.predict(X, sink=buf, pos=pos)
+        ref.add_rows({"obs": obs.cpu().numpy(), "v_pred": vhat.cpu().numpy(), "safety_penalty": pen.float().cpu().numpy()[:, None]})
+        assert len(buf) == len(ref) == min(1000, 300 * (step + 1))
+    got = buf.get_batch(1000, start=0)
+    for k in ("obs", "v_pred", "safety_penalty"):
+        want = np.stack([t[k] for t in ref.buffer])
+        assert np.array_equal(got[k].cpu().numpy(), want), k
+    np.random.seed(1); rs = np.random.RandomState(1)          # the reference's draw order (:17-18)
+    for _ in range(5):
+        b = buf.get_batch(64)
+        wantb, start = ref.get_batch(64, rs)
+        assert np.array_equal(b["v_pred"].cpu().numpy(), np.stack([t["v_pred"] for t in wantb]))
+    buf.clear()
+    assert len(buf) == 0
+    with pytest.raises(ValueError):
+        buf.get_batch(1)
+    buf.close()
+
+
+def test_config4_262144_envs_properties(env, pred, cuda):
+    """BASELINE config 4 at full size: linearity of the affine map, sampled rows against fp64."""
+    from flexgpu.predictor import DeviceReplayBuffer
+    n = 262144
+    g = torch.Generator(device=cuda).manual_seed(0)
+    X = torch.rand(n, 66, device=cuda, generator=g) * 0.4
+    buf = DeviceReplayBuffer(n, {"v_pred": 33, "safety_penalty": 1}, device=cuda)
+    v1, p1 = pred.predict(X, sink=buf)
+    v2, _ = pred.predict(2 * X)
+    v0, _ = pred.predict(torch.zeros(4, 66, device=cuda))
+    assert torch.allclose(v2 - v0[0], 2 * (v1 - v0[0]), rtol=0, atol=4e-6)            # affine: V(2x) - c = 2 (V(x) - c)
+    idx = torch.arange(0, n, 4099, device=cuda)
+    want = predictor_ref.affine_predict(pred.A, pred.c, X[idx].double().cpu().numpy())
+    assert np.max(np.abs(v1[idx].cpu().numpy() - want)) < 2e-6
+    got = buf.get_batch(n, start=0)
+    assert torch.equal(got["v_pred"], v1) and torch.equal(got["safety_penalty"][:, 0], p1.float())
+    buf.close()
+
+
+def test_argument_validation(env, cuda):
+    from flexgpu import FlexGpuError
+    from flexgpu.predictor import DeviceReplayBuffer, VoltagePredictor
+    with pytest.raises(FlexGpuError):
+        VoltagePredictor(env, np.zeros((10, 20)), np.zeros(10))
+    p = VoltagePredictor(env, np.zeros((33, 66)), np.ones(33))
+    with pytest.raises(ValueError):
+        p.predict(torch.zeros(4, 65, device=cuda))
+    buf = DeviceReplayBuffer(10, {"v_pred": 33}, device=cuda)
+    with pytest.raises(FlexGpuError):
+        p.predict(torch.zeros(11, 66, device=cuda), sink=buf)     # more rows than the ring holds
+    with pytest.raises(FlexGpuError):
+        buf.reserve(0)
+    buf.close()
