@@ -103,9 +103,16 @@ class VoltagePredictor:
         self.v_min = float(env.args_dict["v_min"] if v_min is None else v_min)
         self.v_max = float(env.args_dict["v_max"] if v_max is None else v_max)
         self.slack_weight = float(slack_weight)                            # safemaddpg.py:229 (1000)
+        self._load()
+
+    def _load(self):
+        """The handle holds ONE model (fp_predictor_load); several VoltagePredictor objects may share a
+        handle, so each (re)loads its weights when it is not the one currently resident."""
+        env = self.env
         env._check(env._lib.fp_predictor_load(env._h, self.n_in, self.n_out, self.A.ctypes.data_as(C.c_void_p),
                                               self.c.ctypes.data_as(C.c_void_p), self.v_min, self.v_max,
                                               self.slack_weight), "fp_predictor_load")
+        env._resident_predictor = self
 
     @classmethod
     def from_linear_model(cls, env, coef, intercept, x_scale=None, x_min=None, y_scale=None, y_min=None, **kw):
@@ -146,6 +153,8 @@ class VoltagePredictor:
         (a DeviceReplayBuffer) the kernel's epilogue also writes both into the ring rows `pos`..
         (reserved here if pos is None)."""
         env = self.env
+        if getattr(env, "_resident_predictor", None) is not self:
+            self._load()
         X = X.to(device=env.device, dtype=torch.float32).contiguous()
         n = X.shape[0]
         if X.shape[1] != self.n_in:
