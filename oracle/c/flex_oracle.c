@@ -134,15 +134,27 @@ static void sweep_w(const FoNet* t, const double* p, const double* q, double tol
 
 
 /* ---- thread-per-env operation order (variant 0) ------------------------------------------
- * One CUDA thread owns one env and walks the lines sequentially in DFS pre-order:
- *   backward (k = nl-1 .. 0):  P_k = (p_k + [sum of the non-adjacent children's contributions,
- *                              latest subtree first]) + [contribution of child k+1],
- *                              contribution of line c = fma(R_c, l_c, P_c)      (utils/pf.py:65-83)
- *   forward  (k = 0 .. nl-1):  v_k = v_parent - fma(Z2, l, fma(2X, Q, 2R*P))    (pf.py:90-94)
- *                              l_k = (P^2 + Q^2) * r,  r = 1/v_k from rcp_seed() + one fp64
- *                              Newton step (relative error < 1e-13)             (pf.py:85-88)
- *   stop when max_k |l_new - l_old| <= tol; then one more backward and a final forward pass
- *   give flows and voltages that satisfy the balance and voltage-drop rows to rounding. */
+ * One CUDA thread owns one env and walks the lines in DFS pre-order, ONE pass per iteration.
+ * The balance rows (utils/pf.py:65-83) give P_k = S_k + W_k with
+ *     S_k = sum of p over the subtree of line k                      (once per solve)
+ *     W_k = sum of R_j l_j over the lines strictly below k           (carried down the tree)
+ * Lines are grouped in chains (maximal first-child paths; a lateral's first line starts a new
+ * chain); U_c is the loss total of the subtree hanging off chain c's first line.
+ *   setup   (k = nl-1 .. 0): S_k = (p_k + [S of the non-adjacent children, latest subtree first])
+ *                                  + [S_{k+1} if line k+1 is a child of k]
+ *   pass    (k = 0 .. nl-1): chain head:  W = U_c,  v_parent = 1 or v of the branch bus
+ *                            otherwise:   W = W_{k-1} - U_c' for every chain c' leaving the bus
+ *                                         between k-1 and k (increasing c'),  v_parent = v_{k-1}
+ *                            W = fma(-R_k, l_k, W);  P = S_k + W   (same for Q with X)
+ *                            v_k = fma(-2, fma(Z2/2, l, fma(X, Q, R*P)), v_parent) (pf.py:90-94)
+ *                            l_k' = (P^2 + Q^2) * r,  r = 1/v_k from rcp_seed() + one fp64
+ *                            Newton step (relative error < 1e-13)                (pf.py:85-88)
+ *                            acc_c = fma(R_k, l_k', acc_c)
+ *           then, c = n_chains-1 .. 0: U_c = acc_c + U_c' for the chains c' attached to chain c
+ *           (increasing c'); stop when max_k |l_k' - l_k| < tol, compared on the high words of the
+ *           fp64 bit patterns (tol to 20 mantissa bits; an integer compare on the GPU)
+ *   final   one more pass with the converged l: P, Q, v that satisfy the balance and
+ *           voltage-drop rows to rounding (no current update). */
 /* Branch-free reciprocal seed: exponent-flip initial guess + three fp32 Newton steps (all IEEE
  * fp32 fused multiply-adds, so the GPU's fp32 pipe and this code agree bit for bit). */
 static double rcp_seed(double v) {
@@ -157,63 +169,108 @@ static double rcp_seed(double v) {
     return (double)x;
 }
 
-static void backward_t(const FoNet* t, const double* p, const double* q, const double* ell, double* P, double* Q) {
+/* high word of |x|'s bit pattern: the convergence measure (NaN maps above every finite value) */
+static int32_t hi_abs(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int32_t)((u >> 32) & 0x7FFFFFFFu);
+}
+
+#define MAXCH 32
+typedef struct { int n, chain_of[NL], head[NL]; uint32_t attach[NL], child[MAXCH]; } Chains;
+
+static void chains_of(const FoNet* t, Chains* c) {
+    c->n = 0;
+    for (int k = 0; k < NL; ++k) { c->chain_of[k] = 0; c->head[k] = 0; c->attach[k] = 0; }
+    for (int k = 0; k < MAXCH; ++k) c->child[k] = 0;
+    for (int k = 0; k < t->nl; ++k) {
+        if (k == 0 || t->par[k] != k - 1) {
+            int id = c->n++;
+            c->chain_of[k] = id; c->head[k] = 1;
+            if (t->par[k] >= 0) { c->attach[t->par[k]] |= 1u << id; c->child[c->chain_of[t->par[k]]] |= 1u << id; }
+        } else c->chain_of[k] = c->chain_of[k - 1];
+    }
+}
+
+static void setup_t(const FoNet* t, const double* p, const double* q, double* SP, double* SQ) {
     double accP[NL], accQ[NL]; int has[NL];
     for (int k = 0; k < NL; ++k) has[k] = 0;
     for (int k = t->nl - 1; k >= 0; --k) {
         double tp = p[k], tq = q[k];
         if (has[k]) { tp = tp + accP[k]; tq = tq + accQ[k]; }
-        if (k + 1 < t->nl && t->par[k + 1] == k) {
-            tp = tp + fma(t->R[k + 1], ell[k + 1], P[k + 1]);
-            tq = tq + fma(t->X[k + 1], ell[k + 1], Q[k + 1]);
-        }
-        P[k] = tp; Q[k] = tq;
+        if (k + 1 < t->nl && t->par[k + 1] == k) { tp = tp + SP[k + 1]; tq = tq + SQ[k + 1]; }
+        SP[k] = tp; SQ[k] = tq;
         int a = t->par[k];
         if (a >= 0 && a != k - 1) {                   /* non-adjacent child: deposit into the parent's slot */
-            double xp = fma(t->R[k], ell[k], tp), xq = fma(t->X[k], ell[k], tq);
-            if (has[a]) { accP[a] = accP[a] + xp; accQ[a] = accQ[a] + xq; }
-            else { accP[a] = xp; accQ[a] = xq; has[a] = 1; }
+            if (has[a]) { accP[a] = accP[a] + tp; accQ[a] = accQ[a] + tq; }
+            else { accP[a] = tp; accQ[a] = tq; has[a] = 1; }
         }
     }
 }
 
-static double line_v_t(const FoNet* t, int k, const double* v, double P, double Q, double ell) {
-    double vp = t->par[k] >= 0 ? v[t->par[k]] : 1.0;
-    double d = (t->R[k] + t->R[k]) * P;
-    d = fma(t->X[k] + t->X[k], Q, d);
-    d = fma(t->Z2[k], ell, d);
-    return vp - d;
+/* flows and squared voltage of line k; W carried in (wP, wQ) */
+static void line_t(const FoNet* t, const Chains* ch, int k, const double* SP, const double* SQ, double ell,
+                   const double* UP, const double* UQ, double* wP, double* wQ, double* v, double* P, double* Q) {
+    double w, wq, vp;
+    if (ch->head[k]) {
+        w = UP[ch->chain_of[k]]; wq = UQ[ch->chain_of[k]];
+        vp = t->par[k] >= 0 ? v[t->par[k]] : 1.0;
+    } else {
+        w = *wP; wq = *wQ; vp = v[k - 1];
+        for (int c = 0; c < ch->n; ++c) if ((ch->attach[k - 1] >> c) & 1u) { w = w - UP[c]; wq = wq - UQ[c]; }
+    }
+    w = fma(-t->R[k], ell, w); wq = fma(-t->X[k], ell, wq);
+    *wP = w; *wQ = wq;
+    *P = SP[k] + w; *Q = SQ[k] + wq;
+    double g = t->R[k] * *P;                         /* v_parent - 2 g: scaling by two is exact, so this is */
+    g = fma(t->X[k], *Q, g);                         /* fma(Z2, l, fma(2X, Q, 2R*P)) bit for bit            */
+    g = fma(0.5 * t->Z2[k], ell, g);
+    v[k] = fma(-2.0, g, vp);
 }
 
 static void sweep_t(const FoNet* t, const double* p, const double* q, double tol, int max_iter, Sweep* o) {
-    double ell[NL], v[NL], *P = o->P, *Q = o->Q;
+    double ell[NL], v[NL], SP[NL], SQ[NL], UP[MAXCH], UQ[MAXCH], aP[MAXCH], aQ[MAXCH];
+    Chains ch;
     int conv = 0, bad = 0, it = 0;
-    for (int k = 0; k < NL; ++k) { ell[k] = 0.0; v[k] = 1.0; P[k] = Q[k] = 0.0; }
-    backward_t(t, p, q, ell, P, Q);
+    chains_of(t, &ch);
+    for (int k = 0; k < NL; ++k) { ell[k] = 0.0; v[k] = 1.0; o->P[k] = o->Q[k] = 0.0; SP[k] = SQ[k] = 0.0; }
+    for (int c = 0; c < MAXCH; ++c) UP[c] = UQ[c] = 0.0;
+    setup_t(t, p, q, SP, SQ);
     while (it < max_iter) {
         ++it;
         conv = 1;
+        for (int c = 0; c < MAXCH; ++c) aP[c] = aQ[c] = 0.0;
+        /* a chain's lines are consecutive lanes, so one carried (W_P, W_Q) pair serves every chain */
+        double wP = 0.0, wQ = 0.0;
         for (int k = 0; k < t->nl; ++k) {
-            double vk = line_v_t(t, k, v, P[k], Q[k], ell[k]);
-            v[k] = vk;
+            double P, Q;
+            line_t(t, &ch, k, SP, SQ, ell[k], UP, UQ, &wP, &wQ, v, &P, &Q);
+            double vk = v[k];
             float vf = (float)vk;
             if (!(vf > 0.0f)) bad = 1;
             double r = rcp_seed(vk);
             double e = fma(-vk, r, 1.0);
             r = fma(r, e, r);
-            double s = P[k] * P[k];
-            s = fma(Q[k], Q[k], s);
+            double s = P * P;
+            s = fma(Q, Q, s);
             double en = s * r;
-            if (!(fabs(en - ell[k]) <= tol)) conv = 0;
+            if (!(hi_abs(en - ell[k]) < hi_abs(tol))) conv = 0;
             ell[k] = en;
+            int c = ch.chain_of[k];
+            aP[c] = fma(t->R[k], en, aP[c]); aQ[c] = fma(t->X[k], en, aQ[c]);
         }
-        backward_t(t, p, q, ell, P, Q);
+        for (int c = ch.n - 1; c >= 0; --c) {
+            UP[c] = aP[c]; UQ[c] = aQ[c];
+            for (int d = c + 1; d < ch.n; ++d) if ((ch.child[c] >> d) & 1u) { UP[c] = UP[c] + UP[d]; UQ[c] = UQ[c] + UQ[d]; }
+        }
         if (bad || conv) break;
     }
-    for (int k = 0; k < t->nl; ++k) {
-        double vk = line_v_t(t, k, v, P[k], Q[k], ell[k]);
-        v[k] = vk;
-        if (!((float)vk > 0.0f)) bad = 1;
+    {
+        double wP = 0.0, wQ = 0.0;
+        for (int k = 0; k < t->nl; ++k) {
+            line_t(t, &ch, k, SP, SQ, ell[k], UP, UQ, &wP, &wQ, v, &o->P[k], &o->Q[k]);
+            if (!((float)v[k] > 0.0f)) bad = 1;
+        }
     }
     for (int k = 0; k < NL; ++k) { o->v[k] = v[k]; o->ell[k] = ell[k]; }
     o->iters = it; o->ok = conv && !bad;

@@ -3,7 +3,7 @@
 # explicitly (fma()) so the fp64 operation order is the one the CPU mirror oracle reproduces.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="$HERE/../flexgpu/libflexgpu.so"
+OUT="${FLEXGPU_OUT:-$HERE/../flexgpu/libflexgpu.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 SRCS=("$HERE/flex_api.cu" "$HERE/flex_kernels.cu" "$HERE/flex_thread_kernels.cu")
 [ -f "$HERE/predictor.cu" ] && SRCS+=("$HERE/predictor.cu")

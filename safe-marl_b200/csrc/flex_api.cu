@@ -134,13 +134,15 @@ static int build_topology(const FpConfig& c, DevTopo& t, ThreadTopo& tt, int& sh
     const TreeTables tb = derive_tree_tables(par_lane, nl);
     bool any_imax = false;
     for (int k = 0; k < FP_NL; ++k) {
-        tt.R[k] = t.R[k]; tt.X[k] = t.X[k]; tt.R2[k] = t.R[k] + t.R[k]; tt.X2[k] = t.X[k] + t.X[k];
-        tt.Z2[k] = t.Z2[k]; tt.imax2[k] = t.imax2[k];
+        tt.R[k] = t.R[k]; tt.X[k] = t.X[k]; tt.Z2h[k] = 0.5 * t.Z2[k]; tt.imax2[k] = t.imax2[k];
         any_imax = any_imax || (k < nl && std::isfinite(t.imax2[k]));
         tt.par_src[k] = tb.par_src[k]; tt.own_slot[k] = tb.own_slot[k]; tt.dep_slot[k] = tb.dep_slot[k];
         tt.dep_first[k] = tb.dep_first[k]; tt.next_is_child[k] = tb.next_is_child[k];
+        tt.chain_of[k] = tb.chain_of[k]; tt.attach_mask[k] = tb.attach_mask[k];
         tt.col[k] = (int8_t)t.col[k];
     }
+    for (int c = 0; c < FP_MAX_CHAINS; ++c) tt.child_mask[c] = tb.child_mask[c];
+    tt.n_chains = tb.n_chains;
     for (int k = 0; k < nl; ++k) tt.lane_of_col[t.col[k]] = (int8_t)k;
     for (int i = 0; i < 8; ++i) { tt.agent_lane[i] = (int8_t)t.agent_lane[i]; tt.agent_col[i] = (int8_t)t.agent_col[i]; }
     tt.nl = nl; tt.n_slots = tb.n_slots; tt.any_imax = any_imax ? 1 : 0;
@@ -192,8 +194,8 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
         delete h; return fail(nullptr, FP_EINVAL, "fp_create: unknown kernel variant");
     }
     h->variant = cfg->variant;
-    if (h->variant == FP_VARIANT_THREAD && h->tt.n_slots > FP_MAX_SLOTS) {
-        delete h; return fail(nullptr, FP_EINVAL, "fp_create: more than 8 branching buses; use FP_VARIANT_WARP");
+    if (h->variant == FP_VARIANT_THREAD && (h->tt.n_slots > FP_MAX_SLOTS || h->tt.n_chains > FP_MAX_CHAINS)) {
+        delete h; return fail(nullptr, FP_EINVAL, "fp_create: more than 8 branching buses or 16 laterals; use FP_VARIANT_WARP");
     }
     fill_devcfg(*cfg, h->dc);
     const int nb = cfg->n_bus, na = cfg->n_agents, H = cfg->history;

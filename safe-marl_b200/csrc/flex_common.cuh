@@ -53,24 +53,29 @@ struct DevTopo {
 #define FP_MAX_SLOTS 8
 #define TT_ROOT (-1)         // par_src: the slack bus feeds this line (v_parent = 1)
 #define TT_CARRY (-2)        // par_src / dep_slot: parent is lane k-1 -> value carried in a register
+#define FP_MAX_CHAINS 16
 struct ThreadTopo {
-    double R[FP_NL], X[FP_NL], R2[FP_NL], X2[FP_NL], Z2[FP_NL], imax2[FP_NL];
+    double R[FP_NL], X[FP_NL], Z2h[FP_NL], imax2[FP_NL];      // Z2h = |z|^2 / 2 (exact scaling)
     int8_t par_src[FP_NL];    // forward: TT_ROOT, TT_CARRY or the slot holding v_parent
     int8_t own_slot[FP_NL];   // slot owned by this lane's bus (it has non-adjacent children), else -1
     int8_t dep_slot[FP_NL];   // backward: TT_ROOT (nothing), TT_CARRY (to lane k-1) or slot to deposit into
     int8_t dep_first[FP_NL];  // first deposit into that slot in a backward pass (store, not add)
     int8_t next_is_child[FP_NL];  // parent(lane k+1) == lane k
+    int8_t chain_of[FP_NL];   // chain (maximal first-child path) this lane belongs to; chain 0 starts at lane 0
     int8_t col[FP_NL];        // dataset column (bus position - 1) of this lane's bus
     int8_t lane_of_col[FP_NL];
     int8_t agent_lane[8], agent_col[8];
-    int32_t nl, n_slots, any_imax, pad_;
+    uint16_t attach_mask[FP_NL];          // chains whose head line leaves this lane's bus (non-adjacent children)
+    uint16_t child_mask[FP_MAX_CHAINS];   // chains attached to any lane of this chain
+    int32_t nl, n_slots, any_imax, n_chains;
 };
 
 // Slot / carry tables derived from the DFS parent-lane array.  constexpr: evaluated at compile
 // time for the built-in shapes and at run time (host) for any other radial feeder.
 struct TreeTables {
-    int8_t par_src[FP_NL], own_slot[FP_NL], dep_slot[FP_NL], dep_first[FP_NL], next_is_child[FP_NL];
-    int n_slots;
+    int8_t par_src[FP_NL], own_slot[FP_NL], dep_slot[FP_NL], dep_first[FP_NL], next_is_child[FP_NL], chain_of[FP_NL];
+    uint16_t attach_mask[FP_NL], child_mask[FP_NL];
+    int n_slots, n_chains;
 };
 
 template <class ParArray>
@@ -78,8 +83,23 @@ constexpr TreeTables derive_tree_tables(const ParArray& par, int nl) {
     TreeTables t{};
     for (int k = 0; k < FP_NL; ++k) {
         t.par_src[k] = TT_ROOT; t.own_slot[k] = -1; t.dep_slot[k] = TT_ROOT; t.dep_first[k] = 0; t.next_is_child[k] = 0;
+        t.chain_of[k] = 0; t.attach_mask[k] = 0; t.child_mask[k] = 0;
     }
-    t.n_slots = 0;
+    t.n_slots = 0; t.n_chains = 0;
+    // chains: a lane whose parent is not lane k-1 (a lateral's first line, or a line leaving the slack
+    // bus) starts a new chain; pre-order numbering gives nested chains larger ids than their hosts
+    for (int k = 0; k < nl; ++k) {
+        if (k == 0 || par[k] != k - 1) {
+            const int c = t.n_chains++;
+            t.chain_of[k] = (int8_t)c;
+            if (par[k] >= 0 && c < 16) {
+                t.attach_mask[par[k]] = (uint16_t)(t.attach_mask[par[k]] | (1u << c));
+                t.child_mask[t.chain_of[par[k]]] = (uint16_t)(t.child_mask[t.chain_of[par[k]]] | (1u << c));
+            }
+        } else {
+            t.chain_of[k] = t.chain_of[k - 1];
+        }
+    }
     for (int a = 0; a < nl; ++a) {                       // slots in increasing lane order of their owner
         bool has = false;
         for (int j = a + 2; j < nl; ++j) if (par[j] == a) has = true;

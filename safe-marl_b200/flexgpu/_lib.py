@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflexgpu.so")
+# FLEXGPU_LIB: tuning builds of the same library (tools/); the product path is the in-tree default
+LIB_PATH = os.environ.get("FLEXGPU_LIB") or os.path.join(_HERE, "libflexgpu.so")
 
 FP_MAX_BUS = 33
 FP_MAX_AGENTS = 5
