@@ -6,6 +6,7 @@
 // boundary; every pointer is a plain host or device pointer.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -14,6 +15,10 @@
 
 #include "flex_kernels.cuh"
 #include "predictor.cuh"
+
+#define FP_HOST_CHUNKS 4      // fp_step_host can pipeline the batch in up to this many chunks (copy engines || SMs)
+#define FP_HOST_STREAMS 2
+#define FP_HOST_CHUNKS_DEFAULT 2
 
 struct FpHandle {
     FpConfig cfg;
@@ -39,6 +44,9 @@ struct FpHandle {
     void* d_act_stage = nullptr; double* d_reward_stage = nullptr; uint8_t* d_done_stage = nullptr;
     double* d_info_stage = nullptr;
     int grid_step = 0, grid_reset = 0, grid_pf = 0, grid_obs = 0;
+    cudaStream_t host_streams[FP_HOST_STREAMS] = {nullptr, nullptr};
+    cudaEvent_t host_ev_in = nullptr, host_ev_out[FP_HOST_STREAMS] = {nullptr, nullptr};
+    int host_chunks = 0;         // 0 = not decided yet (FLEXGPU_HOST_CHUNKS or the default)
     int64_t launches = 0;
     std::string err;
     PredictorState pred;
@@ -228,7 +236,7 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
         h->grid_step = (int)((tiles < cap_step) ? tiles : cap_step);
         h->grid_reset = (int)((tiles < cap_reset) ? tiles : cap_reset);
         h->grid_pf = thread_kernel_max_grid(MODE_PF, h->tt.n_slots, h->shape);
-        h->stats_rows = cap_step;
+        h->stats_rows = cap_step * (1 + FP_HOST_CHUNKS);     // + one block of rows per chunk of the pipelined host path
     } else {
         h->grid_step = grid_for(n_envs, max_resident_grid(MODE_STEP));
         h->grid_reset = grid_for(n_envs, max_resident_grid(MODE_RESET));
@@ -250,6 +258,11 @@ int fp_destroy(FpHandle* h) {
     cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
     cudaFree(h->d_act_stage); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
+    for (int i = 0; i < FP_HOST_STREAMS; ++i) {
+        if (h->host_streams[i]) cudaStreamDestroy(h->host_streams[i]);
+        if (h->host_ev_out[i]) cudaEventDestroy(h->host_ev_out[i]);
+    }
+    if (h->host_ev_in) cudaEventDestroy(h->host_ev_in);
     delete h;
     return FP_OK;
 }
@@ -348,9 +361,14 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     return FP_OK;
 }
 
+// Host-buffer step.  The batch is cut into FP_HOST_CHUNKS runs of 32-env tiles that flow through two
+// internal streams: the host->device copy of chunk c+1, the kernel of chunk c and the device->host
+// copies of chunk c-1 overlap (both copy engines and the SMs busy at once).  Chunks touch disjoint
+// envs and disjoint statistics rows, so results are identical to one full-batch launch.
 int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_reward, uint8_t* h_done,
                  double* h_info, void* stream) {
     if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_host: call fp_load_profiles first");
     if (!h_actions || !h_reward || !h_done) return fail(h, FP_EINVAL, "fp_step_host: null buffer");
     if (act_dtype != FP_F32 && act_dtype != FP_F64) return fail(h, FP_EINVAL, "fp_step_host: bad action dtype");
     cudaStream_t st = (cudaStream_t)stream;
@@ -361,14 +379,61 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
         CUDA_TRY(h, cudaMalloc(&h->d_done_stage, n));
         CUDA_TRY(h, cudaMalloc(&h->d_info_stage, n * FP_INFO_STRIDE * 8));
     }
-    const size_t abytes = n * na * 4 * (act_dtype == FP_F64 ? 8 : 4);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_act_stage, h_actions, abytes, cudaMemcpyHostToDevice, st));
-    int rc = fp_step(h, h->d_act_stage, act_dtype, h->d_reward_stage, h->d_done_stage,
-                     h_info ? h->d_info_stage : nullptr, nullptr, stream);
-    if (rc != FP_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h_reward, h->d_reward_stage, n * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h_done, h->d_done_stage, n, cudaMemcpyDeviceToHost, st));
-    if (h_info) CUDA_TRY(h, cudaMemcpyAsync(h_info, h->d_info_stage, n * FP_INFO_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+    const size_t abpe = na * 4 * (act_dtype == FP_F64 ? 8 : 4);          // action bytes per env
+    const int64_t tiles = ((int64_t)n + 31) / 32;
+    if (h->host_chunks == 0) {
+        const char* ev = std::getenv("FLEXGPU_HOST_CHUNKS");
+        int k = ev ? std::atoi(ev) : FP_HOST_CHUNKS_DEFAULT;
+        h->host_chunks = (k < 1) ? 1 : ((k > FP_HOST_CHUNKS) ? FP_HOST_CHUNKS : k);
+    }
+    const int n_chunks = h->host_chunks;
+    if (h->variant != FP_VARIANT_THREAD || n_chunks == 1 || tiles < 4 * n_chunks) {  // small batch / warp variant: one shot
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_act_stage, h_actions, n * abpe, cudaMemcpyHostToDevice, st));
+        int rc = fp_step(h, h->d_act_stage, act_dtype, h->d_reward_stage, h->d_done_stage,
+                         h_info ? h->d_info_stage : nullptr, nullptr, stream);
+        if (rc != FP_OK) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(h_reward, h->d_reward_stage, n * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaMemcpyAsync(h_done, h->d_done_stage, n, cudaMemcpyDeviceToHost, st));
+        if (h_info) CUDA_TRY(h, cudaMemcpyAsync(h_info, h->d_info_stage, n * FP_INFO_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        return FP_OK;
+    }
+    if (!h->host_ev_in) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        for (int i = 0; i < FP_HOST_STREAMS; ++i) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_streams[i], cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->host_ev_out[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->host_ev_in, cudaEventDisableTiming));
+    }
+    // everything already queued on the caller's stream happens before the chunks
+    CUDA_TRY(h, cudaEventRecord(h->host_ev_in, st));
+    for (int i = 0; i < FP_HOST_STREAMS; ++i) CUDA_TRY(h, cudaStreamWaitEvent(h->host_streams[i], h->host_ev_in, 0));
+    const int cap = h->stats_rows / (1 + FP_HOST_CHUNKS);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t t0 = tiles * c / n_chunks, t1 = tiles * (c + 1) / n_chunks;
+        const size_t e0 = (size_t)t0 * 32, e1 = ((size_t)t1 * 32 < n) ? (size_t)t1 * 32 : n, ne = e1 - e0;
+        cudaStream_t cs = h->host_streams[c % FP_HOST_STREAMS];
+        CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_act_stage + e0 * abpe, (const char*)h_actions + e0 * abpe, ne * abpe,
+                                    cudaMemcpyHostToDevice, cs));
+        EnvParams p; fill_env_params(h, p);
+        p.actions = h->d_act_stage; p.act_f64 = (act_dtype == FP_F64);
+        p.reward = h->d_reward_stage; p.done = h->d_done_stage; p.info = h_info ? h->d_info_stage : nullptr;
+        p.stats_partial = h->d_stats_partial + (size_t)(1 + c) * cap * FP_NSTATS;
+        p.tile_begin = t0; p.tile_end = t1;
+        EnvParamsT pt; pt.e = p; pt.t = h->tt;
+        const int grid = (int)((t1 - t0 < cap) ? (t1 - t0) : cap);
+        CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, cs));
+        h->launches++;
+        CUDA_TRY(h, cudaMemcpyAsync(h_reward + e0, h->d_reward_stage + e0, ne * 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(h, cudaMemcpyAsync(h_done + e0, h->d_done_stage + e0, ne, cudaMemcpyDeviceToHost, cs));
+        if (h_info) CUDA_TRY(h, cudaMemcpyAsync(h_info + e0 * FP_INFO_STRIDE, h->d_info_stage + e0 * FP_INFO_STRIDE,
+                                                ne * FP_INFO_STRIDE * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int i = 0; i < FP_HOST_STREAMS; ++i) {
+        CUDA_TRY(h, cudaEventRecord(h->host_ev_out[i], h->host_streams[i]));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->host_ev_out[i], 0));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(st));
     return FP_OK;
 }

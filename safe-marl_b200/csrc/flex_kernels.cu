@@ -384,12 +384,15 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_state(const ObsParams prm) {
     }
 }
 
+// One warp per statistic: lane l adds rows l, l + 32, ... in order, then a fixed butterfly joins
+// the 32 lane sums -- deterministic, and 32 independent load streams instead of one serial chain.
 __global__ void k_stats_fold(const double* __restrict__ partial, int n_blocks, double* __restrict__ out) {
-    const int j = threadIdx.x;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (j < FP_NSTATS) {
         double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * FP_NSTATS + j];
-        out[j] = s;
+        for (int b = lane; b < n_blocks; b += 32) s += partial[(int64_t)b * FP_NSTATS + j];
+        s = warp_sum_xor(s);
+        if (lane == 0) out[j] = s;
     }
 }
 
@@ -432,7 +435,7 @@ cudaError_t launch_state(const ObsParams& prm, int f64, int grid, cudaStream_t s
 }
 
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st) {
-    k_stats_fold<<<1, 32, 0, st>>>(partial, n_blocks, out);
+    k_stats_fold<<<1, 32 * FP_NSTATS, 0, st>>>(partial, n_blocks, out);
     return cudaGetLastError();
 }
 

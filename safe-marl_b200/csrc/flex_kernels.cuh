@@ -26,6 +26,7 @@ struct EnvParams {
     const int32_t* start; const double* e0; const double* a0;
     uint64_t seed; int64_t env_offset; int32_t random; int32_t start_range;
     double* stats_partial;                        // [grid][FP_NSTATS]
+    int64_t tile_begin, tile_end;                 // thread kernels: 32-env tiles [tile_begin, tile_end) of this launch (0, 0 = all)
 };
 
 struct PfParams {

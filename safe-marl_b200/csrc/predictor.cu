@@ -25,6 +25,7 @@
 //      coalesced rows into the replay ring at (pos + env) mod capacity (and/or a dense output).
 // By shape (K = 66, N = 33: ~11 flop/B) the op is HBM-bound; the tensor pipe is nearly idle by
 // construction and the point of tcgen05 here is to take the contraction off the fp32 pipe.
+#include <cmath>
 #include <cstring>
 
 #include "flex_kernels.cuh"
@@ -45,8 +46,9 @@ constexpr uint32_t STAGE_BYTES = PRED_M * N_IN * 4;          // 33 792
 constexpr uint32_t OFF_AHI = 0, OFF_ALO = OFF_AHI + A_BYTES, OFF_BHI = OFF_ALO + A_BYTES, OFF_BLO = OFF_BHI + B_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_BLO + B_BYTES;            // two stages
 constexpr uint32_t OFF_OUT = OFF_STAGE + 2 * STAGE_BYTES;    // [128][33] fp32
-constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;
-constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // 3 mbarriers
+constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;     // 16 896 B: keeps OFF_PEN 8-byte aligned
+constexpr uint32_t OFF_PEN = OFF_BIAS + PRED_N * 4;          // [2][128] fp64 penalty partials (column halves)
+constexpr uint32_t OFF_BAR = OFF_PEN + 2 * PRED_M * 8;       // 3 mbarriers
 constexpr uint32_t OFF_TMEM = OFF_BAR + 3 * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 constexpr uint32_t TMEM_COLS = 64;                           // power of two >= 48
@@ -57,6 +59,7 @@ struct PredParams {
     float* vhat; double* penalty;                            // dense outputs (may be null)
     float* ring_vhat; float* ring_pen; int64_t ring_cap, ring_pos;   // replay sink (may be null)
     double v_min, v_max, w;
+    float lo_f, hi_f;                                        // smallest float >= v_min, largest float <= v_max
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +109,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -114,7 +120,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(PRED_M, 1) k_predict(const PredParams prm) {
+constexpr int PRED_THREADS = 2 * PRED_M;     // two threads per env row: K halves in the split, column halves in the epilogue
+
+__global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* A_hi = reinterpret_cast<float*>(smem + OFF_AHI);
     float* A_lo = reinterpret_cast<float*>(smem + OFF_ALO);
@@ -123,7 +131,9 @@ __global__ void __launch_bounds__(PRED_M, 1) k_predict(const PredParams prm) {
     float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const uint32_t bar_full0 = smem_u32(smem + OFF_BAR), bar_mma = bar_full0 + 16;
+    double* pen_part = reinterpret_cast<double*>(smem + OFF_PEN);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (PRED_M - 1), half = tid >> 7;               // env row of the tile, which half of the work
     const int64_t n_tiles = (prm.n + PRED_M - 1) / PRED_M;
 
     // ---- one-time setup: barriers, TMEM, weights, zero K padding
@@ -135,14 +145,14 @@ __global__ void __launch_bounds__(PRED_M, 1) k_predict(const PredParams prm) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < (int)(2 * B_BYTES / 4); i += PRED_M) Bsm[i] = prm.B[i];
+    for (int i = tid; i < (int)(2 * B_BYTES / 4); i += PRED_THREADS) Bsm[i] = prm.B[i];
     if (tid < PRED_N) bias[tid] = prm.bias[tid];
-    {   // columns 66..71 of every row stay zero for the lifetime of the CTA
-        float* hz = A_hi + ((N_IN >> 2) * PRED_M + tid) * 4;            // chunk 16: k = 64..67
-        float* lz = A_lo + ((N_IN >> 2) * PRED_M + tid) * 4;
+    if (half == 0) {   // columns 66..71 of every row stay zero for the lifetime of the CTA
+        float* hz = A_hi + ((N_IN >> 2) * PRED_M + row) * 4;            // chunk 16: k = 64..67
+        float* lz = A_lo + ((N_IN >> 2) * PRED_M + row) * 4;
         hz[2] = hz[3] = 0.0f; lz[2] = lz[3] = 0.0f;
-        float4* h4 = reinterpret_cast<float4*>(A_hi + ((PRED_KC - 1) * PRED_M + tid) * 4);   // chunk 17: k = 68..71
-        float4* l4 = reinterpret_cast<float4*>(A_lo + ((PRED_KC - 1) * PRED_M + tid) * 4);
+        float4* h4 = reinterpret_cast<float4*>(A_hi + ((PRED_KC - 1) * PRED_M + row) * 4);   // chunk 17: k = 68..71
+        float4* l4 = reinterpret_cast<float4*>(A_lo + ((PRED_KC - 1) * PRED_M + row) * 4);
         *h4 = make_float4(0.f, 0.f, 0.f, 0.f); *l4 = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     fence_proxy_async();
@@ -174,21 +184,25 @@ __global__ void __launch_bounds__(PRED_M, 1) k_predict(const PredParams prm) {
             ph_full[s] ^= 1u;
         } else {                                                        // odd-sized last tile: plain loads
             const float* src = prm.X + tile * (int64_t)(PRED_M * N_IN);
-            for (int i = tid; i < rows * N_IN; i += PRED_M) stage[i] = src[i];
+            for (int i = tid; i < rows * N_IN; i += PRED_THREADS) stage[i] = src[i];
             __syncthreads();
         }
 
-        // ---- 3xTF32 split into the UMMA layout (thread = row)
-        if (tid < rows) {
-            const float2* src = reinterpret_cast<const float2*>(stage + tid * N_IN);
+        // ---- 3xTF32 split into the UMMA layout (two threads per row: pairs 0..16 / 17..32)
+        if (row < rows) {
+            const float2* src = reinterpret_cast<const float2*>(stage + row * N_IN);
+            const int j0 = half ? 17 : 0, j1 = half ? N_IN / 2 : 17;
 #pragma unroll
-            for (int j = 0; j < N_IN / 2; ++j) {
-                const float2 x = src[j];
-                const float hx = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                const float hy = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                const int k = 2 * j, off = ((k >> 2) * PRED_M + tid) * 4 + (k & 3);
-                *reinterpret_cast<float2*>(A_hi + off) = make_float2(hx, hy);
-                *reinterpret_cast<float2*>(A_lo + off) = make_float2(x.x - hx, x.y - hy);
+            for (int jj = 0; jj < 17; ++jj) {
+                const int j = j0 + jj;
+                if (j < j1) {
+                    const float2 x = src[j];
+                    const float hx = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    const float hy = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    const int k = 2 * j, off = ((k >> 2) * PRED_M + row) * 4 + (k & 3);
+                    *reinterpret_cast<float2*>(A_hi + off) = make_float2(hx, hy);
+                    *reinterpret_cast<float2*>(A_lo + off) = make_float2(x.x - hx, x.y - hy);
+                }
             }
         }
         fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
@@ -214,40 +228,75 @@ __global__ void __launch_bounds__(PRED_M, 1) k_predict(const PredParams prm) {
         ph_mma ^= 1u;
         tc_fence_after();
 
-        // ---- epilogue: this thread's env = TMEM lane 32*warp + lane
-        uint32_t acc[PRED_N];
+        // ---- epilogue: TMEM lane = env row; warps 0-3 take columns 0..16, warps 4-7 columns 17..32
+        // (a warp may only touch the TMEM lane quarter 32 * (warp % 4))
         {
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-            uint32_t r0[16], r1[16], r2[16];
-            tmem_ld16(taddr, r0); tmem_ld16(taddr + 16, r1); tmem_ld16(taddr + 32, r2);
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (half ? 17u : 0u);
+            uint32_t r0[16], r1 = 0u;
+            tmem_ld16(taddr, r0);
+            if (half == 0) tmem_ld1(taddr + 16, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { acc[i] = r0[i]; acc[16 + i] = r1[i]; acc[32 + i] = r2[i]; }
-        }
-        const int64_t e = tile * PRED_M + tid;
-        if (tid < rows) {
             double pen = 0.0;
+            if (row < rows) {
+                const int c0 = half ? 17 : 0;
 #pragma unroll
-            for (int i = 0; i < N_OUT; ++i) {
-                const float V = __uint_as_float(acc[i]) + bias[i];
-                out[tid * N_OUT + i] = V;
-                const double under = prm.v_min - (double)V, over = (double)V - prm.v_max;
-                pen = pen + ((under > 0.0 ? under : 0.0) + (over > 0.0 ? over : 0.0));
+                for (int i = 0; i < 17; ++i) {
+                    if (i < 16 || half == 0) {
+                        const float V = __uint_as_float(i < 16 ? r0[i] : r1) + bias[c0 + i];
+                        out[row * N_OUT + c0 + i] = V;
+                        // in-limit voltages (the common case) contribute exactly zero: the fp64 terms are
+                        // only evaluated outside the conservative fp32 bounds lo_f >= v_min, hi_f <= v_max
+                        if (V < prm.lo_f || V > prm.hi_f) {
+                            const double under = prm.v_min - (double)V, over = (double)V - prm.v_max;
+                            pen = pen + ((under > 0.0 ? under : 0.0) + (over > 0.0 ? over : 0.0));
+                        }
+                    }
+                }
             }
-            pen = prm.w * pen;
-            if (prm.penalty != nullptr) prm.penalty[e] = pen;
-            if (prm.ring_pen != nullptr) prm.ring_pen[(prm.ring_pos + e) % prm.ring_cap] = (float)pen;
+            pen_part[half * PRED_M + row] = pen;
         }
         tc_fence_before();
         __syncthreads();
+        const int64_t e = tile * PRED_M + row;
+        if (half == 0 && row < rows) {
+            const double pen = prm.w * (pen_part[row] + pen_part[PRED_M + row]);
+            if (prm.penalty != nullptr) prm.penalty[e] = pen;
+            if (prm.ring_pen != nullptr) {               // pos < cap and n <= cap: one conditional subtraction wraps
+                const int64_t rr = prm.ring_pos + e;
+                prm.ring_pen[rr >= prm.ring_cap ? rr - prm.ring_cap : rr] = (float)pen;
+            }
+        }
 
         // ---- coalesced row stores: dense output and/or replay ring (wraps at capacity)
+        // (the tile's rows are contiguous in the dense output; in the ring they are contiguous up to
+        //  one wrap, so element i of the tile lands at i + base, minus the ring size past the end)
         const int64_t e0 = tile * PRED_M;
-        for (int i = tid; i < rows * N_OUT; i += PRED_M) {
-            const int r = i / N_OUT, c = i - r * N_OUT;
-            const float v = out[i];
-            if (prm.vhat != nullptr) prm.vhat[(e0 + r) * N_OUT + c] = v;
-            if (prm.ring_vhat != nullptr) prm.ring_vhat[((prm.ring_pos + e0 + r) % prm.ring_cap) * N_OUT + c] = v;
+        const int64_t ring_elems = prm.ring_cap * N_OUT, ring_base = (prm.ring_pos + e0) * N_OUT;
+        const int n_el = rows * N_OUT;
+        float* dense = prm.vhat != nullptr ? prm.vhat + e0 * N_OUT : nullptr;
+        // 16-byte stores where the destination allows it: a full tile is 1056 float4 (e0 * 33 * 4 bytes is
+        // a multiple of 16); the ring segment qualifies when it does not wrap and starts 16-byte aligned
+        const bool ring_vec = prm.ring_vhat != nullptr && ((ring_base & 3) == 0) && (ring_base + n_el <= ring_elems);
+        if ((n_el & 3) == 0 && (dense == nullptr || ((reinterpret_cast<uintptr_t>(dense) & 15) == 0)) &&
+            (prm.ring_vhat == nullptr || (ring_vec && ((reinterpret_cast<uintptr_t>(prm.ring_vhat) & 15) == 0)))) {
+            const float4* o4 = reinterpret_cast<const float4*>(out);
+            float4* d4 = reinterpret_cast<float4*>(dense);
+            float4* r4 = prm.ring_vhat != nullptr ? reinterpret_cast<float4*>(prm.ring_vhat + ring_base) : nullptr;
+            for (int i = tid; i < (n_el >> 2); i += PRED_THREADS) {
+                const float4 v = o4[i];
+                if (d4 != nullptr) d4[i] = v;
+                if (r4 != nullptr) r4[i] = v;
+            }
+        } else {
+            for (int i = tid; i < n_el; i += PRED_THREADS) {
+                const float v = out[i];
+                if (dense != nullptr) dense[i] = v;
+                if (prm.ring_vhat != nullptr) {
+                    int64_t o = ring_base + i;
+                    o = o >= ring_elems ? o - ring_elems : o;
+                    prm.ring_vhat[o] = v;
+                }
+            }
         }
         // the next iteration's transform does not touch `out`; its epilogue is two barriers away
     }
@@ -258,21 +307,26 @@ __global__ void __launch_bounds__(PRED_M, 1) k_predict(const PredParams prm) {
 }
 
 // ---------------------------------------------------------------------------- replay ring
+// n consecutive ring rows starting at `pos` are contiguous in memory up to one wrap, so both
+// copies are flat, fully coalesced and free of integer division: element i <-> ring element
+// pos * width + i, minus the ring size past the end.
 __global__ void k_replay_write(float* __restrict__ dst, int64_t cap, int width, int64_t pos, int64_t n,
                                const float* __restrict__ src) {
-    const int64_t total = n * width;
+    const int64_t total = n * width, ring = cap * width, base = pos * width;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / width; const int c = (int)(i - r * width);
-        dst[((pos + r) % cap) * width + c] = src[i];
+        int64_t o = base + i;
+        o = o >= ring ? o - ring : o;
+        dst[o] = src[i];
     }
 }
 
 __global__ void k_replay_gather(const float* __restrict__ field, int64_t cap, int width, int64_t first, int64_t batch,
                                 float* __restrict__ out) {
-    const int64_t total = batch * width;
+    const int64_t total = batch * width, ring = cap * width, base = first * width;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / width; const int c = (int)(i - r * width);
-        out[i] = field[((first + r) % cap) * width + c];
+        int64_t o = base + i;
+        o = o >= ring ? o - ring : o;
+        out[i] = field[o];
     }
 }
 
@@ -341,6 +395,8 @@ int fp_predict(FpHandle* h, int64_t n, const float* d_X, float* d_vhat, double* 
     std::memset(&prm, 0, sizeof(prm));
     prm.X = d_X; prm.n = n; prm.B = p->d_B; prm.bias = p->d_bias; prm.vhat = d_vhat; prm.penalty = d_penalty;
     prm.v_min = p->v_min; prm.v_max = p->v_max; prm.w = p->slack_weight;
+    prm.lo_f = (float)p->v_min; if ((double)prm.lo_f < p->v_min) prm.lo_f = std::nextafterf(prm.lo_f, INFINITY);
+    prm.hi_f = (float)p->v_max; if ((double)prm.hi_f > p->v_max) prm.hi_f = std::nextafterf(prm.hi_f, -INFINITY);
     prm.ring_cap = 1; prm.ring_pos = 0;
     if (sink) {
         const int nf = (int)sink->widths.size();
@@ -361,7 +417,7 @@ int fp_predict(FpHandle* h, int64_t n, const float* d_X, float* d_vhat, double* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + PRED_M - 1) / PRED_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    k_predict<<<grid, PRED_M, SMEM_BYTES, (cudaStream_t)stream>>>(prm);
+    k_predict<<<grid, PRED_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(prm);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fp_internal_fail(h, FP_ECUDA, cudaGetErrorString(e));
     fp_internal_count_launch(h, 1);
