@@ -51,13 +51,16 @@ enum {
     FP_ENOMEM = -4
 };
 
-/* kernel variants (FpConfig.variant).  Both compute the same DistFlow fixed point; they differ
- * in the mapping and therefore in floating-point summation order (results agree to ~1e-12):
- *   THREAD  one CUDA thread per env, sequential sweep in registers -- the throughput path;
- *           converges on max |dl| <= pf_tol (squared current), default 1e-6.
+/* kernel variants (FpConfig.variant).  All compute the same DistFlow fixed point; THREAD/PAIR and
+ * WARP differ in floating-point summation order (results agree to ~1e-12):
+ *   THREAD  one CUDA thread per env, one-pass sweep with the currents in registers -- the
+ *           throughput path; converges on max |dl| < pf_tol (squared current, compared on the
+ *           high words of the fp64 patterns), default 1e-6.
  *   WARP    one warp per env, lane = line, shuffle scans -- the lowest latency for tiny
- *           batches; converges on max |dv| <= pf_tol (squared voltage), default 1e-9. */
-enum { FP_VARIANT_THREAD = 0, FP_VARIANT_WARP = 1 };
+ *           batches; converges on max |dv| <= pf_tol (squared voltage), default 1e-9.
+ *   PAIR    two lanes per env (main feeder | laterals), IEEE 33-bus shape only; bit-identical to
+ *           THREAD, twice the resident warps; measured slightly slower on B200. */
+enum { FP_VARIANT_THREAD = 0, FP_VARIANT_WARP = 1, FP_VARIANT_PAIR = 2 };
 
 /* action dtypes accepted by fp_step */
 enum { FP_F32 = 0, FP_F64 = 1 };

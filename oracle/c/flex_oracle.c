@@ -158,15 +158,28 @@ static void sweep_w(const FoNet* t, const double* p, const double* q, double tol
 /* Branch-free reciprocal seed: exponent-flip initial guess + three fp32 Newton steps (all IEEE
  * fp32 fused multiply-adds, so the GPU's fp32 pipe and this code agree bit for bit). */
 static double rcp_seed(double v) {
-    float vf = (float)v, x, e;
-    uint32_t i;
-    memcpy(&i, &vf, 4);
+    /* fp64 -> fp32 by truncation and fp32 -> fp64 exactly, both as integer bit manipulation (the
+     * kernels avoid the conversion instructions); valid for positive normal v in the fp32 range */
+    uint64_t u; uint32_t i; float vf, x, e;
+    memcpy(&u, &v, 8);
+    i = (((uint32_t)(u >> 32) - 0x38000000u) << 3) | ((uint32_t)u >> 29);
+    memcpy(&vf, &i, 4);
     i = 0x7EF311C7u - i;
     memcpy(&x, &i, 4);
     e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
     e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
     e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
-    return (double)x;
+    memcpy(&i, &x, 4);
+    u = ((uint64_t)((i >> 3) + 0x38000000u) << 32) | (uint64_t)(uint32_t)(i << 29);
+    memcpy(&v, &u, 8);
+    return v;
+}
+
+/* v <= 0 (also -0 and the smallest denormals), +-inf or NaN */
+static int sqv_bad(double v) {
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    return (uint32_t)((uint32_t)(u >> 32) - 1u) >= 0x7FEFFFFFu;
 }
 
 /* high word of |x|'s bit pattern: the convergence measure (NaN maps above every finite value) */
@@ -246,8 +259,7 @@ static void sweep_t(const FoNet* t, const double* p, const double* q, double tol
             double P, Q;
             line_t(t, &ch, k, SP, SQ, ell[k], UP, UQ, &wP, &wQ, v, &P, &Q);
             double vk = v[k];
-            float vf = (float)vk;
-            if (!(vf > 0.0f)) bad = 1;
+            if (sqv_bad(vk)) bad = 1;
             double r = rcp_seed(vk);
             double e = fma(-vk, r, 1.0);
             r = fma(r, e, r);
@@ -269,7 +281,7 @@ static void sweep_t(const FoNet* t, const double* p, const double* q, double tol
         double wP = 0.0, wQ = 0.0;
         for (int k = 0; k < t->nl; ++k) {
             line_t(t, &ch, k, SP, SQ, ell[k], UP, UQ, &wP, &wQ, v, &o->P[k], &o->Q[k]);
-            if (!((float)v[k] > 0.0f)) bad = 1;
+            if (sqv_bad(v[k])) bad = 1;
         }
     }
     for (int k = 0; k < NL; ++k) { o->v[k] = v[k]; o->ell[k] = ell[k]; }

@@ -25,6 +25,8 @@ struct FpHandle {
     DevCfg dc;
     DevTopo topo;
     ThreadTopo tt;               // thread-per-env tables (by-value kernel parameter)
+    PairTopo pt;                 // pair-per-env tables (IEEE 33-bus shape only)
+    int pair = 0;                // 1: the thread variant runs the pair-per-env kernels
     int variant = FP_VARIANT_THREAD, shape = SHAPE_RUNTIME;
     int64_t n = 0;
     int device = 0;
@@ -37,7 +39,7 @@ struct FpHandle {
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
-    int stats_rows = 0;
+    int stats_rows = 0, stats_cap = 0;     // rows of one launch's statistics block
     const uint8_t* d_inject = nullptr;
     int keep_flows = 0;
     // staging for the host-buffer entry points
@@ -198,7 +200,7 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     std::string err;
     int rc = build_topology(*cfg, h->topo, h->tt, h->shape, err);
     if (rc != FP_OK) { delete h; return fail(nullptr, rc, "fp_create: " + err); }
-    if (cfg->variant != FP_VARIANT_THREAD && cfg->variant != FP_VARIANT_WARP) {
+    if (cfg->variant != FP_VARIANT_THREAD && cfg->variant != FP_VARIANT_WARP && cfg->variant != FP_VARIANT_PAIR) {
         delete h; return fail(nullptr, FP_EINVAL, "fp_create: unknown kernel variant");
     }
     h->variant = cfg->variant;
@@ -228,7 +230,26 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_envs * na * H * 6 * 8));
     CREATE_TRY(cudaMemset(h->d_hist, 0, (size_t)n_envs * na * H * 6 * 8));
     h->grid_obs = grid_for(n_envs, max_resident_grid(MODE_STEP));
-    if (h->variant == FP_VARIANT_THREAD) {
+    // FP_VARIANT_PAIR: two lanes per env (flex_pair_kernels.cu), IEEE 33-bus shape only -- same results bit
+    // for bit; measured ~10 % slower than one thread per env on B200 (profiles/), kept as a selectable variant
+    h->pair = 0;
+    if (cfg->variant == FP_VARIANT_PAIR) {
+        if (h->shape != SHAPE_IEEE33) {
+            delete h; return fail(nullptr, FP_EINVAL, "fp_create: FP_VARIANT_PAIR needs the IEEE 33-bus feeder shape");
+        }
+        h->pair = 1; h->variant = FP_VARIANT_THREAD;              // shares the thread variant's host paths and mirror order
+    }
+    if (h->pair) {
+        pair_topo_from(h->tt, h->pt);
+        CREATE_TRY(pair_kernels_configure());
+        const int64_t ctas = (n_envs + 31) / 32;                  // two 16-env tiles (warps) per CTA
+        const int cap_step = pair_kernel_max_grid(MODE_STEP), cap_reset = pair_kernel_max_grid(MODE_RESET);
+        h->grid_step = (int)((ctas < cap_step) ? ctas : cap_step);
+        h->grid_reset = (int)((ctas < cap_reset) ? ctas : cap_reset);
+        h->grid_pf = pair_kernel_max_grid(MODE_PF);
+        h->stats_cap = 2 * cap_step;                               // one statistics row per warp
+        h->stats_rows = h->stats_cap * (1 + FP_HOST_CHUNKS);
+    } else if (h->variant == FP_VARIANT_THREAD) {
         CREATE_TRY(thread_kernels_configure(FP_MAX_SLOTS));
         const int64_t tiles = (n_envs + 31) / 32;
         const int cap_step = thread_kernel_max_grid(MODE_STEP, h->tt.n_slots, h->shape);
@@ -236,12 +257,13 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
         h->grid_step = (int)((tiles < cap_step) ? tiles : cap_step);
         h->grid_reset = (int)((tiles < cap_reset) ? tiles : cap_reset);
         h->grid_pf = thread_kernel_max_grid(MODE_PF, h->tt.n_slots, h->shape);
+        h->stats_cap = cap_step;
         h->stats_rows = cap_step * (1 + FP_HOST_CHUNKS);     // + one block of rows per chunk of the pipelined host path
     } else {
         h->grid_step = grid_for(n_envs, max_resident_grid(MODE_STEP));
         h->grid_reset = grid_for(n_envs, max_resident_grid(MODE_RESET));
         h->grid_pf = max_resident_grid(MODE_PF);
-        h->stats_rows = max_resident_grid(MODE_STEP);
+        h->stats_rows = max_resident_grid(MODE_STEP); h->stats_cap = h->stats_rows;
     }
     CREATE_TRY(cudaMalloc(&h->d_stats_partial, (size_t)h->stats_rows * FP_NSTATS * 8));
     CREATE_TRY(cudaMemset(h->d_stats_partial, 0, (size_t)h->stats_rows * FP_NSTATS * 8));
@@ -314,6 +336,11 @@ static void fill_env_params(FpHandle* h, EnvParams& p) {
 
 static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cudaStream_t st) {
     const int grid = (mode == MODE_STEP) ? h->grid_step : h->grid_reset;
+    if (h->pair) {
+        EnvParamsP pp;
+        pp.e = p; pp.t = h->pt;
+        return launch_env_p(mode, pp, grid, st);
+    }
     if (h->variant == FP_VARIANT_THREAD) {
         EnvParamsT pt;
         pt.e = p; pt.t = h->tt;
@@ -409,7 +436,8 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
     // everything already queued on the caller's stream happens before the chunks
     CUDA_TRY(h, cudaEventRecord(h->host_ev_in, st));
     for (int i = 0; i < FP_HOST_STREAMS; ++i) CUDA_TRY(h, cudaStreamWaitEvent(h->host_streams[i], h->host_ev_in, 0));
-    const int cap = h->stats_rows / (1 + FP_HOST_CHUNKS);
+    const int cap = h->stats_cap;                                       // statistics rows of one launch
+    const int cap_grid = h->pair ? cap / 2 : cap;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t t0 = tiles * c / n_chunks, t1 = tiles * (c + 1) / n_chunks;
         const size_t e0 = (size_t)t0 * 32, e1 = ((size_t)t1 * 32 < n) ? (size_t)t1 * 32 : n, ne = e1 - e0;
@@ -421,9 +449,14 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
         p.reward = h->d_reward_stage; p.done = h->d_done_stage; p.info = h_info ? h->d_info_stage : nullptr;
         p.stats_partial = h->d_stats_partial + (size_t)(1 + c) * cap * FP_NSTATS;
         p.tile_begin = t0; p.tile_end = t1;
-        EnvParamsT pt; pt.e = p; pt.t = h->tt;
-        const int grid = (int)((t1 - t0 < cap) ? (t1 - t0) : cap);
-        CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, cs));
+        const int grid = (int)((t1 - t0 < cap_grid) ? (t1 - t0) : cap_grid);
+        if (h->pair) {
+            EnvParamsP pp; pp.e = p; pp.t = h->pt;
+            CUDA_TRY(h, launch_env_p(MODE_STEP, pp, grid, cs));
+        } else {
+            EnvParamsT pt; pt.e = p; pt.t = h->tt;
+            CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, cs));
+        }
         h->launches++;
         CUDA_TRY(h, cudaMemcpyAsync(h_reward + e0, h->d_reward_stage + e0, ne * 8, cudaMemcpyDeviceToHost, cs));
         CUDA_TRY(h, cudaMemcpyAsync(h_done + e0, h->d_done_stage + e0, ne, cudaMemcpyDeviceToHost, cs));
@@ -501,7 +534,12 @@ int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, 
     PfParams p;
     p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol;
     p.p = d_p; p.q = d_q; p.V = d_V; p.Pl = d_Pl; p.Ql = d_Ql; p.Isq = d_Isq; p.iters = d_iters; p.fail = d_fail;
-    if (h->variant == FP_VARIANT_THREAD) {
+    if (h->pair) {
+        PfParamsP pp;
+        pp.p = p; pp.t = h->pt;
+        const int64_t ctas = (n + 31) / 32;
+        CUDA_TRY(h, launch_power_flow_p(pp, (int)((ctas < h->grid_pf) ? ctas : h->grid_pf), (cudaStream_t)stream));
+    } else if (h->variant == FP_VARIANT_THREAD) {
         PfParamsT pt;
         pt.p = p; pt.t = h->tt;
         const int64_t tiles = (n + 31) / 32;

@@ -229,6 +229,23 @@ __device__ __forceinline__ SweepOut distflow_sweep(const LaneTopo& t, double p, 
     return o;
 }
 
+// ------------------------------------------------------------------ reciprocal seed (thread / pair kernels)
+// fp64 <-> fp32 by integer bit manipulation instead of F2F: the conversions are quarter-rate,
+// ~18-cycle, scoreboard-tracked instructions on the XU pipe, and a warp has six scoreboards for
+// everything of variable latency -- two conversions per line were what kept lines from
+// overlapping.  Valid for positive normal values inside the fp32 range (squared voltages are
+// ~1); anything else is caught by sqv_bad() or fails to converge and is reported as a failed solve.
+//   d2f_trunc  truncates (a seed does not care), f2d_exact is exact
+__device__ __forceinline__ float d2f_trunc(double v) {
+    return __int_as_float(__funnelshift_l((unsigned)__double2loint(v), (unsigned)(__double2hiint(v) - 0x38000000), 3));
+}
+__device__ __forceinline__ double f2d_exact(float x) {
+    const unsigned b = __float_as_uint(x);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+// v <= 0 (also -0 and the smallest denormals), +-inf or NaN: one unsigned compare on the high word
+__device__ __forceinline__ bool sqv_bad(double v) { return (unsigned)(__double2hiint(v) - 1) >= 0x7FEFFFFFu; }
+
 // ------------------------------------------------------------------ Philox4x32-10
 struct U4 { uint32_t x, y, z, w; };
 

@@ -21,7 +21,7 @@ DEFAULT_ENV_ARGS = dict(
 
 # Solver knobs that the reference leaves to IPOPT's defaults (utils/pf.py:101-102).
 DEFAULT_SOLVER_ARGS = dict(
-    kernel_variant="thread",  # "thread" (one thread per env, throughput) | "warp" (one warp per env)
+    kernel_variant="thread",  # "thread" (one thread per env, throughput) | "warp" (one warp per env) | "pair" (two lanes per env)
     pf_tol=None,        # None -> DEFAULT_PF_TOL[variant]; see DESIGN.md "convergence"
     pf_max_iter=32,     # exceeding it counts as solver failure (:314-337)
     fail_penalty=200.0,  # :336
@@ -30,7 +30,7 @@ DEFAULT_SOLVER_ARGS = dict(
 
 
 # thread variant: max |dl| (squared current) between sweeps; warp variant: max |dv| (squared voltage)
-DEFAULT_PF_TOL = {"thread": 1e-6, "warp": 1e-9}
+DEFAULT_PF_TOL = {"thread": 1e-6, "warp": 1e-9, "pair": 1e-6}
 
 
 def convert(dictionary):
@@ -77,7 +77,7 @@ def make_fp_config(args, network):
     c.pf_max_iter = int(args["pf_max_iter"])
     variant = args.get("kernel_variant", "thread")
     if variant not in _lib.VARIANTS:
-        raise ValueError("kernel_variant must be 'thread' or 'warp'")
+        raise ValueError("kernel_variant must be 'thread', 'warp' or 'pair'")
     c.variant = _lib.VARIANTS[variant]
     c.pf_tol = float(DEFAULT_PF_TOL[variant] if args.get("pf_tol") is None else args["pf_tol"])
     c.v_min, c.v_max = float(args["v_min"]), float(args["v_max"])

@@ -26,13 +26,30 @@ __global__ void k_dfma(double* out, int iters, double a, double b, long long* cy
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
-// float <-> double conversion chain + fp32 fma (the reciprocal-seed path)
+// float <-> double conversion chain (the reciprocal-seed path): asm volatile keeps every conversion
 __global__ void k_cvt(double* out, int iters, long long* cycles) {
     double x = 1.0 + threadIdx.x * 1e-3;
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { float f = (float)x; f = __fmaf_rn(f, 0.999f, 0.001f); x = (double)f; }
+        for (int r = 0; r < 16; ++r) {
+            float f;
+            asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(x));
+            asm volatile("cvt.f64.f32 %0, %1;" : "=d"(x) : "f"(f));
+        }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+// dependent fp32 FMA chain
+__global__ void k_ffma(double* out, int iters, long long* cycles) {
+    float x = 1.0f + threadIdx.x * 1e-3f;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) asm volatile("fma.rn.f32 %0, %0, 0f3F7FBE77, 0f3A83126F;" : "+f"(x));
     }
     const long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = x;
@@ -85,7 +102,10 @@ int main() {
     long long cyc;
     k_cvt<<<148, 32>>>(d_out, 1000, d_cyc); cudaDeviceSynchronize();
     cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
-    printf("D2F + FFMA + F2D chain: %.2f clk per round\n", (double)cyc / 16000.0);
+    printf("F2F.F32.F64 + F2F.F64.F32 dependent pair: %.2f clk per pair\n", (double)cyc / 16000.0);
+    k_ffma<<<148, 32>>>(d_out, 1000, d_cyc); cudaDeviceSynchronize();
+    cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+    printf("FFMA dependent chain: %.2f clk per op\n", (double)cyc / 16000.0);
     k_lds<<<148, 32>>>(d_out, 1000, d_cyc); cudaDeviceSynchronize();
     cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
     printf("LDS.64 dependent chain: %.2f clk per load\n", (double)cyc / 16000.0);
