@@ -111,6 +111,8 @@ def make_mirror(n, prof, seed):
 def cpu_port_rate(prof, n_envs, budget_s, seed=5):
     """The C port (OpenMP, all cores) on a bounded sample: `n` envs stepped until budget_s."""
     import numpy as np
+    from oracle import c_mirror
+    cores = c_mirror.use_all_cores()
     n = min(n_envs, 65536)
     mb = make_mirror(n, prof, seed)
     rng = np.random.default_rng(0)
@@ -122,7 +124,6 @@ def cpu_port_rate(prof, n_envs, budget_s, seed=5):
         el = time.perf_counter() - t0
         if el >= budget_s or k >= 90:
             break
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     return n * k / el, cores, f"{n} envs x {k} steps of the C port (oracle/c/flex_oracle.c, OpenMP) in {el:.2f} s"
 
 
@@ -152,6 +153,8 @@ def run_reference(args):
     network = Network(create_network(DEFAULT_ENV_ARGS))
     prof = synthetic_profiles(network, 5, T=args.rows, seed=0)
     import numpy as np
+    from oracle import c_mirror
+    cores = c_mirror.use_all_cores()                             # torchrun exports OMP_NUM_THREADS=1
     n = min(args.envs_per_gpu, 65536)
     mb = make_mirror(n, prof, 5)
     rng = np.random.default_rng(0)
@@ -163,7 +166,6 @@ def run_reference(args):
     for k in range(steps):
         mb.step(acts[k % 4])
     el = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0))
     value = n * steps / el
     py = python_restatement_rate(prof, 5.0)
     line = {

@@ -540,5 +540,15 @@ void fo_env_step(const FoNet* c, const double* P, const double* Q, const double*
     }
 }
 
+/* OpenMP worker threads the batched entry points will use (bench.py reports it as `cores`). */
+#ifdef _OPENMP
+#include <omp.h>
+int fo_threads(void) { return omp_get_max_threads(); }
+void fo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+#else
+int fo_threads(void) { return 1; }
+void fo_set_threads(int n) { (void)n; }
+#endif
+
 int fo_sizeof_net(void) { return (int)sizeof(FoNet); }
 int fo_sizeof_state(void) { return (int)sizeof(FoState); }

@@ -68,6 +68,15 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def use_all_cores():
+    """Give the OpenMP loops every core this process may run on (torchrun exports OMP_NUM_THREADS=1);
+    returns the number of worker threads in force."""
+    l = lib()
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    l.fo_set_threads(C.c_int(n))
+    return int(l.fo_threads())
+
+
 VARIANT_THREAD, VARIANT_WARP = 0, 1
 
 
