@@ -147,34 +147,16 @@ static void sweep_w(const FoNet* t, const double* p, const double* q, double tol
  *                                         between k-1 and k (increasing c'),  v_parent = v_{k-1}
  *                            W = fma(-R_k, l_k, W);  P = S_k + W   (same for Q with X)
  *                            v_k = fma(-2, fma(Z2/2, l, fma(X, Q, R*P)), v_parent) (pf.py:90-94)
- *                            l_k' = (P^2 + Q^2) * r,  r = 1/v_k from rcp_seed() + one fp64
- *                            Newton step (relative error < 1e-13)                (pf.py:85-88)
+ *                            e = fma(-v_k, l_k, P^2 + Q^2)   residual of the current row (pf.py:85-88)
+ *                            l_k' = fma(e, 1 + d + d^2, l_k),  d = 1 - v_k: a division-free
+ *                            relaxation whose fixed point is the row itself (1 + d + d^2 =
+ *                            (1 - d^3)/v, so it converges like the exact quotient)
  *                            acc_c = fma(R_k, l_k', acc_c)
  *           then, c = n_chains-1 .. 0: U_c = acc_c + U_c' for the chains c' attached to chain c
- *           (increasing c'); stop when max_k |l_k' - l_k| < tol, compared on the high words of the
+ *           (increasing c'); stop when max_k |e_k| < tol, compared on the high words of the
  *           fp64 bit patterns (tol to 20 mantissa bits; an integer compare on the GPU)
  *   final   one more pass with the converged l: P, Q, v that satisfy the balance and
  *           voltage-drop rows to rounding (no current update). */
-/* Branch-free reciprocal seed: exponent-flip initial guess + three fp32 Newton steps (all IEEE
- * fp32 fused multiply-adds, so the GPU's fp32 pipe and this code agree bit for bit). */
-static double rcp_seed(double v) {
-    /* fp64 -> fp32 by truncation and fp32 -> fp64 exactly, both as integer bit manipulation (the
-     * kernels avoid the conversion instructions); valid for positive normal v in the fp32 range */
-    uint64_t u; uint32_t i; float vf, x, e;
-    memcpy(&u, &v, 8);
-    i = (((uint32_t)(u >> 32) - 0x38000000u) << 3) | ((uint32_t)u >> 29);
-    memcpy(&vf, &i, 4);
-    i = 0x7EF311C7u - i;
-    memcpy(&x, &i, 4);
-    e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
-    e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
-    e = fmaf(-vf, x, 1.0f); x = fmaf(x, e, x);
-    memcpy(&i, &x, 4);
-    u = ((uint64_t)((i >> 3) + 0x38000000u) << 32) | (uint64_t)(uint32_t)(i << 29);
-    memcpy(&v, &u, 8);
-    return v;
-}
-
 /* v <= 0 (also -0 and the smallest denormals), +-inf or NaN */
 static int sqv_bad(double v) {
     uint64_t u;
@@ -260,13 +242,13 @@ static void sweep_t(const FoNet* t, const double* p, const double* q, double tol
             line_t(t, &ch, k, SP, SQ, ell[k], UP, UQ, &wP, &wQ, v, &P, &Q);
             double vk = v[k];
             if (sqv_bad(vk)) bad = 1;
-            double r = rcp_seed(vk);
-            double e = fma(-vk, r, 1.0);
-            r = fma(r, e, r);
             double s = P * P;
             s = fma(Q, Q, s);
-            double en = s * r;
-            if (!(hi_abs(en - ell[k]) < hi_abs(tol))) conv = 0;
+            double e = fma(-vk, ell[k], s);          /* residual of the current row at the old current */
+            double d = 1.0 - vk, rt = 2.0 - vk;
+            rt = fma(d, rt, 1.0);                    /* 1 + d + d^2 = (1 - d^3) / v */
+            double en = fma(e, rt, ell[k]);
+            if (!(hi_abs(e) < hi_abs(tol))) conv = 0;
             ell[k] = en;
             int c = ch.chain_of[k];
             aP[c] = fma(t->R[k], en, aP[c]); aQ[c] = fma(t->X[k], en, aQ[c]);

@@ -149,7 +149,6 @@ template <int S0, int B>
 __device__ __forceinline__ void p_pass_batch(unsigned m, bool role, const double2* row2, const double* ltp, PState& st, PCarry& cy,
                                              int32_t& dmax, bool& bad) {
     double v[B], s[B], R[B], X[B];
-    float vf[B], x[B];
     static_for<B>([&](auto j) {
         constexpr int J = decltype(j)::value, S = S0 + J;
         if constexpr (S < NS) {
@@ -157,42 +156,24 @@ __device__ __forceinline__ void p_pass_batch(unsigned m, bool role, const double
             p_line<S>(m, role, row2, ltp, st.ell[S], st, cy, P, Q, v[J], R[J], X[J]);
             const double t = P * P;
             s[J] = fma(Q, Q, t);
-        }
-    });
-    static_for<B>([&](auto j) {
-        constexpr int J = decltype(j)::value, S = S0 + J;
-        if constexpr (S < NS) {
-            vf[J] = d2f_trunc(v[J]);
             bad = bad || sqv_bad(v[J]);
-            x[J] = __uint_as_float(0x7EF311C7u - __float_as_uint(vf[J]));
         }
     });
-#pragma unroll
-    for (int step = 0; step < 3; ++step) {
-        float e[B];
-        static_for<B>([&](auto j) {
-            constexpr int J = decltype(j)::value, S = S0 + J;
-            if constexpr (S < NS) e[J] = __fmaf_rn(-vf[J], x[J], 1.0f);
-        });
-        static_for<B>([&](auto j) {
-            constexpr int J = decltype(j)::value, S = S0 + J;
-            if constexpr (S < NS) x[J] = __fmaf_rn(x[J], e[J], x[J]);
-        });
-    }
-    double r[B], e2[B];
+    // division-free relaxed update of the current row (same arithmetic as t_pass_batch)
+    double e[B], d[B], rt[B];
     static_for<B>([&](auto j) {
         constexpr int J = decltype(j)::value, S = S0 + J;
-        if constexpr (S < NS) { r[J] = f2d_exact(x[J]); e2[J] = fma(-v[J], r[J], 1.0); }
+        if constexpr (S < NS) { e[J] = fma(-v[J], st.ell[S], s[J]); d[J] = 1.0 - v[J]; rt[J] = 2.0 - v[J]; }
     });
     static_for<B>([&](auto j) {
         constexpr int J = decltype(j)::value, S = S0 + J;
-        if constexpr (S < NS) r[J] = fma(r[J], e2[J], r[J]);
+        if constexpr (S < NS) rt[J] = fma(d[J], rt[J], 1.0);
     });
     static_for<B>([&](auto j) {
         constexpr int J = decltype(j)::value, S = S0 + J;
         if constexpr (S < NS) {
-            const double en = s[J] * r[J];
-            const int32_t dh = __double2hiint(en - st.ell[S]) & 0x7FFFFFFF;
+            const double en = fma(e[J], rt[J], st.ell[S]);
+            const int32_t dh = __double2hiint(e[J]) & 0x7FFFFFFF;
             dmax = dh > dmax ? dh : dmax;
             st.ell[S] = en;
             if constexpr (S == 5) { cy.un0 = cy.acc; cy.un0q = cy.accq; cy.acc = role ? 0.0 : cy.acc; cy.accq = role ? 0.0 : cy.accq; }
