@@ -34,7 +34,7 @@ struct FpHandle {
     int32_t start_range = 0;
     // device buffers
     DevTopo* d_topo = nullptr;
-    double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr;
+    double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr, *d_PQD = nullptr;
     uint64_t* d_rec = nullptr;
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
@@ -276,7 +276,7 @@ int fp_destroy(FpHandle* h) {
     if (!h) return FP_OK;
     cudaSetDevice(h->device);
     predictor_free(&h->pred);
-    cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP);
+    cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
     cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
     cudaFree(h->d_act_stage); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
@@ -303,8 +303,8 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
     const int64_t need = (int64_t)h->cfg.episode_limit + h->cfg.history + 1;
     if (T < need) return fail(h, FP_EINVAL, "fp_load_profiles: fewer rows than one episode slice");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP);
-    h->d_P = h->d_Q = h->d_PVP = nullptr;
+    cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
+    h->d_P = h->d_Q = h->d_PVP = h->d_PQD = nullptr;
     double *d_pv = nullptr, *d_price = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->d_P, (size_t)T * nl * 8));
     CUDA_TRY(h, cudaMalloc(&h->d_Q, (size_t)T * nl * 8));
@@ -317,6 +317,11 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
     CUDA_TRY(h, cudaMemcpy(d_price, h_price, (size_t)T * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(h, launch_pack_pvp(d_pv, d_price, na, T, h->d_PVP, 0));
     h->launches++;
+    if (h->variant == FP_VARIANT_THREAD && !h->pair) {   // (p, q) pairs in DFS lane order for the thread kernels
+        CUDA_TRY(h, cudaMalloc(&h->d_PQD, (size_t)T * nl * 16));
+        CUDA_TRY(h, launch_pack_pq(h->d_P, h->d_Q, h->tt, T, h->d_PQD, 0));
+        h->launches++;
+    }
     CUDA_TRY(h, cudaDeviceSynchronize());
     cudaFree(d_pv); cudaFree(d_price);
     h->T = T;
@@ -327,7 +332,7 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
 static void fill_env_params(FpHandle* h, EnvParams& p) {
     std::memset(&p, 0, sizeof(p));
     p.c = h->dc; p.topo = h->d_topo; p.n = h->n;
-    p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP;
+    p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP; p.PQD = h->d_PQD;
     p.rec = h->d_rec; p.V = h->d_V; p.setp = h->d_setp;
     if (h->keep_flows) { p.pfl = h->d_pfl; p.qfl = h->d_qfl; p.isq = h->d_isq; }
     p.inject = h->d_inject;

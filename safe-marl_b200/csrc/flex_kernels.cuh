@@ -15,6 +15,9 @@ struct EnvParams {
     int64_t n;
     // profile dataset (device): P/Q [T][nl] bus order, PVP [T][8]
     const double* P; const double* Q; const double* PVP;
+    // thread kernels: the same load rows as (p, q) pairs in DFS lane order, [T][nl][2] -- one
+    // contiguous 16*nl-byte row per (env, step), fetched with a single bulk copy
+    const double* PQD;
     // per-env state
     uint64_t* rec; double* V; double* setp;
     double* pfl; double* qfl; double* isq;       // optional line-flow dump (nullptr = off)
@@ -69,6 +72,7 @@ void pair_topo_from(const ThreadTopo& t, PairTopo& p);
 cudaError_t launch_env_t(int mode, int shape, const EnvParamsT& prm, int grid, cudaStream_t st);
 cudaError_t launch_power_flow_t(int shape, const PfParamsT& prm, int grid, cudaStream_t st);
 cudaError_t thread_kernels_configure(int n_slots);
+cudaError_t launch_pack_pq(const double* P, const double* Q, const ThreadTopo& t, int64_t T, double* pqd, cudaStream_t st);
 int thread_kernel_max_grid(int mode, int n_slots, int shape);
 int thread_shape_of(const ThreadTopo& t, const int8_t* par_lane);
 size_t thread_kernel_smem_bytes(int n_slots);
