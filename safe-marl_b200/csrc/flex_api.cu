@@ -10,13 +10,14 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <cstdint>
 #include <string>
 #include <vector>
 
 #include "flex_kernels.cuh"
 #include "predictor.cuh"
 
-#define FP_HOST_CHUNKS 4      // fp_step_host can pipeline the batch in up to this many chunks (copy engines || SMs)
+#define FP_HOST_CHUNKS 16     // fp_step_host can pipeline the batch in up to this many chunks (copy engines || SMs)
 #define FP_HOST_STREAMS 2
 #define FP_HOST_CHUNKS_DEFAULT 2
 
@@ -339,6 +340,12 @@ static void fill_env_params(FpHandle* h, EnvParams& p) {
     p.start_range = h->start_range;
 }
 
+// whole-tile bulk stores (thread kernels) need 16-byte aligned output arrays
+static int bulk_io_ok(const EnvParams& p) {
+    auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15u) == 0; };
+    return (al16(p.rec) && al16(p.setp) && al16(p.V) && al16(p.reward) && al16(p.done) && (p.info == nullptr || al16(p.info))) ? 1 : 0;
+}
+
 static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cudaStream_t st) {
     const int grid = (mode == MODE_STEP) ? h->grid_step : h->grid_reset;
     if (h->pair) {
@@ -349,6 +356,7 @@ static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cud
     if (h->variant == FP_VARIANT_THREAD) {
         EnvParamsT pt;
         pt.e = p; pt.t = h->tt;
+        if (mode == MODE_STEP) pt.e.bulk_io = bulk_io_ok(p);
         return launch_env_t(mode, h->shape, pt, grid, st);
     }
     return launch_env(mode, p, grid, st);
@@ -460,6 +468,7 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
             CUDA_TRY(h, launch_env_p(MODE_STEP, pp, grid, cs));
         } else {
             EnvParamsT pt; pt.e = p; pt.t = h->tt;
+            pt.e.bulk_io = bulk_io_ok(p);
             CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, cs));
         }
         h->launches++;

@@ -34,10 +34,10 @@ __device__ __forceinline__ void ess_energy_clip(const DevCfg& c, double& ch, dou
     dis = clipd(dis, 0.0, c.p_dis_max);
 }
 
-// :262-293 (step) / :113-130 (reset): raw action -> applied setpoints.
-__device__ __forceinline__ Setpoint apply_actions(const DevCfg& c, bool scale, double a0, double a1,
-                                                  double a2, double a3, double pload, double ppv,
-                                                  double e_clip) {
+// :262-293 (step) / :113-130 (reset): raw action -> applied setpoints, everything that does not
+// need the building's load: `pred` returns the clipped reduction FRACTION (:676-677).
+__device__ __forceinline__ Setpoint apply_actions_frac(const DevCfg& c, bool scale, double a0, double a1,
+                                                       double a2, double a3, double ppv, double e_clip) {
     double pct, ch, dis, qpv;
     if (scale) {
         pct = c.mpr * a0;                                   // :278
@@ -56,8 +56,15 @@ __device__ __forceinline__ Setpoint apply_actions(const DevCfg& c, bool scale, d
     }
     ess_energy_clip(c, ch, dis, e_clip);                    // :289-290
     Setpoint s;
-    s.pred = pload * pct;                                   // :293
+    s.pred = pct;
     s.ch = ch; s.dis = dis; s.qpv = qpv;
     return s;
 }
 
+__device__ __forceinline__ Setpoint apply_actions(const DevCfg& c, bool scale, double a0, double a1,
+                                                  double a2, double a3, double pload, double ppv,
+                                                  double e_clip) {
+    Setpoint s = apply_actions_frac(c, scale, a0, a1, a2, a3, ppv, e_clip);
+    s.pred = pload * s.pred;                                // :293
+    return s;
+}

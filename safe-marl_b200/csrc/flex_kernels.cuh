@@ -30,6 +30,7 @@ struct EnvParams {
     uint64_t seed; int64_t env_offset; int32_t random; int32_t start_range;
     double* stats_partial;                        // [grid][FP_NSTATS]
     int64_t tile_begin, tile_end;                 // thread kernels: 32-env tiles [tile_begin, tile_end) of this launch (0, 0 = all)
+    int32_t bulk_io;                              // thread kernels: every per-env output array is 16-byte aligned (bulk stores allowed)
 };
 
 struct PfParams {
