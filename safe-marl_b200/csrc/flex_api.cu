@@ -18,8 +18,9 @@
 #include "predictor.cuh"
 
 #define FP_HOST_CHUNKS 16     // fp_step_host can pipeline the batch in up to this many chunks (copy engines || SMs)
-#define FP_HOST_STREAMS 2
-#define FP_HOST_CHUNKS_DEFAULT 2
+#define FP_HOST_STREAMS 3
+#define FP_HOST_CHUNKS_DEFAULT 4
+#define FP_HOST_GRAPHS 8
 
 struct FpHandle {
     FpConfig cfg;
@@ -47,9 +48,15 @@ struct FpHandle {
     void* d_act_stage = nullptr; double* d_reward_stage = nullptr; uint8_t* d_done_stage = nullptr;
     double* d_info_stage = nullptr;
     int grid_step = 0, grid_reset = 0, grid_pf = 0, grid_obs = 0;
-    cudaStream_t host_streams[FP_HOST_STREAMS] = {nullptr, nullptr};
-    cudaEvent_t host_ev_in = nullptr, host_ev_out[FP_HOST_STREAMS] = {nullptr, nullptr};
+    cudaStream_t host_streams[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t host_ev_in = nullptr, host_ev_out[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
     int host_chunks = 0;         // 0 = not decided yet (FLEXGPU_HOST_CHUNKS or the default)
+    // the chunk pipeline of fp_step_host as instantiated CUDA graphs, one per set of (pinned) host
+    // buffers: one launch per step instead of five API calls per chunk
+    cudaStream_t host_origin = nullptr;
+    struct HostGraph { cudaGraphExec_t exec = nullptr; std::vector<char> key; };
+    HostGraph host_graphs[FP_HOST_GRAPHS];
+    int host_graph_next = 0;
     int64_t launches = 0;
     std::string err;
     PredictorState pred;
@@ -286,6 +293,8 @@ int fp_destroy(FpHandle* h) {
         if (h->host_ev_out[i]) cudaEventDestroy(h->host_ev_out[i]);
     }
     if (h->host_ev_in) cudaEventDestroy(h->host_ev_in);
+    for (auto& g : h->host_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->host_origin) cudaStreamDestroy(h->host_origin);
     delete h;
     return FP_OK;
 }
@@ -401,10 +410,63 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     return FP_OK;
 }
 
-// Host-buffer step.  The batch is cut into FP_HOST_CHUNKS runs of 32-env tiles that flow through two
-// internal streams: the host->device copy of chunk c+1, the kernel of chunk c and the device->host
-// copies of chunk c-1 overlap (both copy engines and the SMs busy at once).  Chunks touch disjoint
-// envs and disjoint statistics rows, so results are identical to one full-batch launch.
+// The chunk pipeline of fp_step_host, enqueued behind everything already on `st` (no synchronisation).
+static int enqueue_host_chunks(FpHandle* h, const void* h_actions, int act_dtype, double* h_reward, uint8_t* h_done,
+                               double* h_info, int n_chunks, cudaStream_t st) {
+    const size_t n = (size_t)h->n, na = (size_t)h->dc.na;
+    const size_t abpe = na * 4 * (act_dtype == FP_F64 ? 8 : 4);          // action bytes per env
+    const int64_t tiles = ((int64_t)n + 31) / 32;
+    // everything already queued on the caller's stream happens before the chunks
+    cudaStream_t s_in = h->host_streams[0], s_k = h->host_streams[1], s_out = h->host_streams[2];
+    CUDA_TRY(h, cudaEventRecord(h->host_ev_in, st));
+    for (int i = 0; i < FP_HOST_STREAMS; ++i) CUDA_TRY(h, cudaStreamWaitEvent(h->host_streams[i], h->host_ev_in, 0));
+    const int cap = h->stats_cap;                                       // statistics rows of one launch
+    const int cap_grid = h->pair ? cap / 2 : cap;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t t0 = tiles * c / n_chunks, t1 = tiles * (c + 1) / n_chunks;
+        const size_t e0 = (size_t)t0 * 32, e1 = ((size_t)t1 * 32 < n) ? (size_t)t1 * 32 : n, ne = e1 - e0;
+        // host -> device copies run back to back on their own stream (the link never idles) ...
+        CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_act_stage + e0 * abpe, (const char*)h_actions + e0 * abpe, ne * abpe,
+                                    cudaMemcpyHostToDevice, s_in));
+        CUDA_TRY(h, cudaEventRecord(h->host_ev_out[0], s_in));
+        // ... the kernel of a chunk follows its copy ...
+        CUDA_TRY(h, cudaStreamWaitEvent(s_k, h->host_ev_out[0], 0));
+        EnvParams p; fill_env_params(h, p);
+        p.actions = h->d_act_stage; p.act_f64 = (act_dtype == FP_F64);
+        p.reward = h->d_reward_stage; p.done = h->d_done_stage; p.info = h_info ? h->d_info_stage : nullptr;
+        p.stats_partial = h->d_stats_partial + (size_t)(1 + c) * cap * FP_NSTATS;
+        p.tile_begin = t0; p.tile_end = t1;
+        const int grid = (int)((t1 - t0 < cap_grid) ? (t1 - t0) : cap_grid);
+        if (h->pair) {
+            EnvParamsP pp; pp.e = p; pp.t = h->pt;
+            CUDA_TRY(h, launch_env_p(MODE_STEP, pp, grid, s_k));
+        } else {
+            EnvParamsT pt; pt.e = p; pt.t = h->tt;
+            pt.e.bulk_io = bulk_io_ok(p);
+            CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, s_k));
+        }
+        h->launches++;
+        CUDA_TRY(h, cudaEventRecord(h->host_ev_out[1], s_k));
+        // ... and its results leave on the other copy engine while the next chunk computes
+        CUDA_TRY(h, cudaStreamWaitEvent(s_out, h->host_ev_out[1], 0));
+        CUDA_TRY(h, cudaMemcpyAsync(h_reward + e0, h->d_reward_stage + e0, ne * 8, cudaMemcpyDeviceToHost, s_out));
+        CUDA_TRY(h, cudaMemcpyAsync(h_done + e0, h->d_done_stage + e0, ne, cudaMemcpyDeviceToHost, s_out));
+        if (h_info) CUDA_TRY(h, cudaMemcpyAsync(h_info + e0 * FP_INFO_STRIDE, h->d_info_stage + e0 * FP_INFO_STRIDE,
+                                                ne * FP_INFO_STRIDE * 8, cudaMemcpyDeviceToHost, s_out));
+    }
+    for (int i = 0; i < FP_HOST_STREAMS; ++i) {
+        CUDA_TRY(h, cudaEventRecord(h->host_ev_out[i], h->host_streams[i]));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->host_ev_out[i], 0));
+    }
+    return FP_OK;
+}
+
+// Host-buffer step.  The batch is cut into chunks of 32-env tiles that flow through three internal
+// streams (copy in / kernels / copy out): the host->device copies run back to back, the kernel of
+// chunk c overlaps the copy of chunk c+1 and the device->host copies of chunk c-1 (both copy
+// engines and the SMs busy at once).  Chunks touch disjoint envs and disjoint statistics rows, so
+// results are identical to one full-batch launch.  With pinned host buffers the whole pipeline is
+// one instantiated CUDA graph per buffer set.
 int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_reward, uint8_t* h_done,
                  double* h_info, void* stream) {
     if (!h) return FP_EINVAL;
@@ -446,41 +508,47 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
         }
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->host_ev_in, cudaEventDisableTiming));
     }
-    // everything already queued on the caller's stream happens before the chunks
-    CUDA_TRY(h, cudaEventRecord(h->host_ev_in, st));
-    for (int i = 0; i < FP_HOST_STREAMS; ++i) CUDA_TRY(h, cudaStreamWaitEvent(h->host_streams[i], h->host_ev_in, 0));
-    const int cap = h->stats_cap;                                       // statistics rows of one launch
-    const int cap_grid = h->pair ? cap / 2 : cap;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int64_t t0 = tiles * c / n_chunks, t1 = tiles * (c + 1) / n_chunks;
-        const size_t e0 = (size_t)t0 * 32, e1 = ((size_t)t1 * 32 < n) ? (size_t)t1 * 32 : n, ne = e1 - e0;
-        cudaStream_t cs = h->host_streams[c % FP_HOST_STREAMS];
-        CUDA_TRY(h, cudaMemcpyAsync((char*)h->d_act_stage + e0 * abpe, (const char*)h_actions + e0 * abpe, ne * abpe,
-                                    cudaMemcpyHostToDevice, cs));
-        EnvParams p; fill_env_params(h, p);
-        p.actions = h->d_act_stage; p.act_f64 = (act_dtype == FP_F64);
-        p.reward = h->d_reward_stage; p.done = h->d_done_stage; p.info = h_info ? h->d_info_stage : nullptr;
-        p.stats_partial = h->d_stats_partial + (size_t)(1 + c) * cap * FP_NSTATS;
-        p.tile_begin = t0; p.tile_end = t1;
-        const int grid = (int)((t1 - t0 < cap_grid) ? (t1 - t0) : cap_grid);
-        if (h->pair) {
-            EnvParamsP pp; pp.e = p; pp.t = h->pt;
-            CUDA_TRY(h, launch_env_p(MODE_STEP, pp, grid, cs));
-        } else {
-            EnvParamsT pt; pt.e = p; pt.t = h->tt;
-            pt.e.bulk_io = bulk_io_ok(p);
-            CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, cs));
-        }
-        h->launches++;
-        CUDA_TRY(h, cudaMemcpyAsync(h_reward + e0, h->d_reward_stage + e0, ne * 8, cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(h, cudaMemcpyAsync(h_done + e0, h->d_done_stage + e0, ne, cudaMemcpyDeviceToHost, cs));
-        if (h_info) CUDA_TRY(h, cudaMemcpyAsync(h_info + e0 * FP_INFO_STRIDE, h->d_info_stage + e0 * FP_INFO_STRIDE,
-                                                ne * FP_INFO_STRIDE * 8, cudaMemcpyDeviceToHost, cs));
+    // Pinned buffers: the whole chunk pipeline is one instantiated graph per buffer set.
+    auto pinned = [](const void* x) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, x) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool use_graph = pinned(h_actions) && pinned(h_reward) && pinned(h_done) && (!h_info || pinned(h_info)) &&
+                           !std::getenv("FLEXGPU_NO_HOST_GRAPH");
+    if (!use_graph) {
+        int rc = enqueue_host_chunks(h, h_actions, act_dtype, h_reward, h_done, h_info, n_chunks, st);
+        if (rc != FP_OK) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        return FP_OK;
     }
-    for (int i = 0; i < FP_HOST_STREAMS; ++i) {
-        CUDA_TRY(h, cudaEventRecord(h->host_ev_out[i], h->host_streams[i]));
-        CUDA_TRY(h, cudaStreamWaitEvent(st, h->host_ev_out[i], 0));
+    struct Key { EnvParams p; const void* a; void* r; void* d; void* i; int dtype, chunks; } key;
+    std::memset(&key, 0, sizeof(key));
+    fill_env_params(h, key.p);
+    key.a = h_actions; key.r = h_reward; key.d = h_done; key.i = h_info; key.dtype = act_dtype; key.chunks = n_chunks;
+    FpHandle::HostGraph* g = nullptr;
+    for (auto& c : h->host_graphs)
+        if (c.exec && c.key.size() == sizeof(key) && std::memcmp(c.key.data(), &key, sizeof(key)) == 0) { g = &c; break; }
+    if (!g) {
+        g = &h->host_graphs[h->host_graph_next];
+        h->host_graph_next = (h->host_graph_next + 1) % FP_HOST_GRAPHS;
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        if (!h->host_origin) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->host_origin, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->host_origin, cudaStreamCaptureModeThreadLocal));
+        const int64_t launches0 = h->launches;
+        int rc = enqueue_host_chunks(h, h_actions, act_dtype, h_reward, h_done, h_info, n_chunks, h->host_origin);
+        h->launches = launches0;                                         // counted per graph launch below
+        cudaError_t ce = cudaStreamEndCapture(h->host_origin, &graph);
+        if (rc != FP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        CUDA_TRY(h, ce);
+        ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CUDA_TRY(h, ce);
+        g->key.assign(reinterpret_cast<const char*>(&key), reinterpret_cast<const char*>(&key) + sizeof(key));
     }
+    CUDA_TRY(h, cudaGraphLaunch(g->exec, st));
+    h->launches += n_chunks;
     CUDA_TRY(h, cudaStreamSynchronize(st));
     return FP_OK;
 }
