@@ -1,8 +1,10 @@
 /*
  * flex_oracle.c -- CPU mirror of the flex_provision hot path.  TEST INFRASTRUCTURE ONLY.
  *
- * PARITY UNPINNED: the reference (kosmylo/Safe-MARL) has no tests or golden vectors for
- * this path and its power flow runs inside IPOPT, which is not available here.  This file
+ * PARITY: the reference (kosmylo/Safe-MARL) has no tests or golden vectors for this path and
+ * its power flow runs inside IPOPT, which is not available here; the fixtures this mirror is
+ * checked against (tests/golden/ref_*.npz) are outputs of the reference's own Python code with
+ * only the IPOPT root finder substituted (see oracle/__init__.py).  This file
  * restates the algorithm in plain C, in fp64, with the SAME floating-point operation order
  * as the CUDA kernels (explicit fma(), -ffp-contract=off), so that integer outputs
  * (voltage-violation masks and counts, flags, iteration counts) can be compared bit for

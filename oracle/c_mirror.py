@@ -1,6 +1,6 @@
 """ctypes wrapper of oracle/c/flex_oracle.c -- the bit-exact CPU mirror (TEST INFRASTRUCTURE).
 
-PARITY UNPINNED (see oracle/__init__.py).  `MirrorBatch` holds N environments as plain numpy
+PARITY: see oracle/__init__.py (pinned on the reference's Python code, IPOPT excepted).  `MirrorBatch` holds N environments as plain numpy
 arrays and advances them with the C restatement of reset/step; `mirror_power_flow` is the
 batched power flow.  Used by the GPU parity tests (bit-exact masks, ulp-level floats) and as
 bench.py's CPU baseline.

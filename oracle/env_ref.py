@@ -1,7 +1,10 @@
 """Single-env fp64 restatement of the reference's FlexibilityProvisionEnv (oracle side).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED (no reference
-goldens; the power flow behind it is oracle/pf_ref.py, not IPOPT).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY: pinned on the
+reference's own env code -- tests/golden/ref_env_*.npz are episodes produced by
+the reference's FlexibilityProvisionEnv itself (tests/golden/make_ref_golden.py)
+and this restatement reproduces them to 1e-16 (tests/test_oracle_env.py); the
+power flow behind both is Newton (oracle/pf_ref.py), not IPOPT.
 
 Behavioural restatement of
 madrl/environments/flex_provision/flexibility_provision_env.py -- every method

@@ -1,6 +1,6 @@
 """IEEE 33-bus feeder data + the reference's per-unit conversion (oracle side).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: the reference's
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY: data unpinned -- the reference's
 Lines_33.xlsx / Nodes_33.xlsx are Git-LFS pointers, so the feeder is restated
 from the public Baran & Wu (1989) 33-bus case.  The `Imax` column is not part of
 that case; `IMAX_A` below is a documented synthetic rating.

@@ -1,6 +1,7 @@
 """fp64 CPU power flow: two independent solvers of the reference's DistFlow system.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED (IPOPT absent).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY: pinned on the reference's own model code through
+oracle/pyomo_shim.py (tests/golden/ref_pf.npz); IPOPT itself is absent.
 
 The reference states the power flow as a square nonlinear system inside a Pyomo
 model (utils/pf.py:65-98) and lets IPOPT find a root; the objective

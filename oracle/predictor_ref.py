@@ -1,6 +1,6 @@
 """fp64 restatement of the safety-signal voltage predictor and the safety penalty (oracle side).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: the reference's training data
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY: fit unpinned -- the reference's training data
 (data/net_power_inputs.csv, data/bus_voltages_outputs.csv) are Git-LFS pointers and its fitted
 model is not shipped; what is pinned here is the *pipeline* -- scikit-learn's own MinMaxScaler /
 LinearRegression run in this container on scenarios generated the way the reference generates

@@ -141,3 +141,15 @@ def test_linearity_property_light_load(env, network):
     a = _np(env.power_flow(p * 1e-4, q * 1e-4, want_flows=False))["V"]
     b = _np(env.power_flow(p * 2e-4, q * 2e-4, want_flows=False))["V"]
     assert np.max(np.abs((b - 1) - 2 * (a - 1))) < 1e-8
+
+
+def test_reference_power_flow_solver_outputs(env):
+    """Scenarios solved through the reference's own power_flow_solver_simplified (model, constraint
+    rules and extraction are the reference's code; tests/golden/make_ref_golden.py): north_star
+    tolerance 1e-6 p.u. on voltages, line flows and currents (observed < 1e-8)."""
+    g = np.load(os.path.join(GOLD, "ref_pf.npz"))
+    out = _np(env.power_flow(g["p"][:, 1:], g["q"][:, 1:]))
+    assert not out["failed"].any()
+    for got, want in ((out["V"], g["V"]), (out["P"], g["P"]), (out["Q"], g["Q"]), (np.sqrt(out["Isq"]), g["I"])):
+        err = np.max(np.abs(got - want))
+        assert err < TOL_PU and err < 1e-8

@@ -154,10 +154,26 @@ def test_solver_failure_semantics(profiles):
 
 
 @pytest.mark.parametrize("tag", ["normal", "train"])
-def test_golden_episode_env_ref_and_mirror(tag, fonet):
-    """The stored episode (generated with the Newton power flow) is reproduced by the Python
-    restatement exactly and by the C mirror within the sweep tolerance; integer outputs equal."""
-    g = np.load(os.path.join(GOLD, f"env_golden_{tag}.npz"))
+def test_restatement_equals_reference_code(tag):
+    """PIN: the episode produced by the reference's own FlexibilityProvisionEnv (imported from the
+    reference checkout, Pyomo/IPOPT replaced by oracle/pyomo_shim.py; tests/golden/make_ref_golden.py)
+    equals the episode produced by the Python restatement oracle/env_ref.py from the same seeds and
+    profiles -- reset draws, setpoints, ESS energies, voltages, rewards, info, state and observations."""
+    ref = np.load(os.path.join(GOLD, f"ref_env_{tag}.npz"))
+    own = np.load(os.path.join(GOLD, f"env_golden_{tag}.npz"))
+    assert ref['max_residual'].max() < 1e-12                  # the reference's constraint rules hold on every solve
+    for k in ('e0', 'a0', 'P', 'Q', 'price', 'actions', 'E0', 'E', 'done', 'obs_steps'):
+        assert np.array_equal(ref[k], own[k]), k
+    for k in ('PV', 'V0', 'obs0', 'state0', 'reward', 'info', 'V', 'setp', 'state', 'obs'):
+        assert ref[k].shape == own[k].shape and np.max(np.abs(ref[k] - own[k])) < 1e-13, k
+
+
+@pytest.mark.parametrize("src", ["env_golden", "ref_env"])
+@pytest.mark.parametrize("tag", ["normal", "train"])
+def test_golden_episode_env_ref_and_mirror(tag, src, fonet):
+    """The stored episodes (`env_golden`: restatement + Newton; `ref_env`: the reference's own env
+    code) are reproduced by the C mirror within the sweep tolerance; integer outputs equal."""
+    g = np.load(os.path.join(GOLD, f"{src}_{tag}.npz"))
     prof = dict(P=g['P'], Q=g['Q'], PV=g['PV'], price=g['price'])
     mb = c_mirror.MirrorBatch(fonet, prof, 1)
     mb.reset([0], g['e0'][None], g['a0'][None])

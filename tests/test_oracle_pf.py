@@ -117,3 +117,40 @@ def test_mirror_zero_and_negative_load(fonet):
     # reverse power flow (generation) raises voltages above 1
     m = c_mirror.mirror_power_flow(fonet, -0.05 * np.ones((1, 32)), np.zeros((1, 32)))
     assert m['V'][0, 1:].min() > 1.0 and not m['failed'][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# Fixtures produced by the REFERENCE'S OWN code (tests/golden/make_ref_golden.py: utils/create_net.py
+# and utils/pf.py imported from the reference checkout; Pyomo/IPOPT replaced by oracle/pyomo_shim.py,
+# which solves with Newton and then evaluates every constraint rule of the reference on the solution).
+def test_reference_create_network_equals_oracle(net):
+    g = np.load(os.path.join(GOLD, "ref_network.npz"))
+    lines = [tuple(int(x) for x in l) for l in g['lines']]
+    assert list(g['bus_numbers']) == list(net['bus_numbers']) and sorted(lines) == sorted(net['line_connections'])
+    assert np.array_equal(g['R'], [net['line_resistances'][l] for l in lines])       # create_net.py:22
+    assert np.array_equal(g['X'], [net['line_reactances'][l] for l in lines])
+    assert np.array_equal(g['imax'], [net['max_line_currents'][l] for l in lines])   # create_net.py:24
+    assert np.array_equal(g['p'], [net['active_power_demand'][n] for n in net['bus_numbers']])   # create_net.py:17
+    assert np.array_equal(g['q'], [net['reactive_power_demand'][n] for n in net['bus_numbers']])
+    assert np.array_equal(g['bus_types'], [net['bus_types'][n] for n in net['bus_numbers']])
+    assert list(g['buildings']) == list(net['buildings'])
+
+
+def test_reference_power_flow_solver_outputs(fonet, tree):
+    """run_pf.py's operating point through the reference's power_flow_solver and 32 scenarios through
+    power_flow_solver_simplified: the sweep oracle, the Newton oracle and the C mirror agree with what
+    the reference's extraction code (pf.py:108-113) returned."""
+    g = np.load(os.path.join(GOLD, "ref_pf.npz"))
+    assert g['max_residual'].max() < 1e-12 and g['runpf_max_residual'][0] < 1e-12   # the reference's own rules hold
+    # K2 (run_pf.py:36-57)
+    assert abs(g['runpf_V'][17] - 0.94137528) < 1e-8 and abs(g['runpf_V'][32] - 0.95744575) < 1e-8
+    assert np.max(np.abs(g['runpf_E_next'] - 0.013625)) < 1e-17                     # pf.py:96-98
+    m = c_mirror.mirror_power_flow(fonet, g['p'][:, 1:], g['q'][:, 1:])
+    assert not m['failed'].any()
+    assert np.max(np.abs(m['V'] - g['V'])) < 1e-9
+    assert np.max(np.abs(m['P'] - g['P'])) < 1e-8 and np.max(np.abs(m['Q'] - g['Q'])) < 1e-8
+    assert np.max(np.abs(np.sqrt(m['Isq']) - g['I'])) < 1e-8
+    for e in (0, 7, 31):
+        b = pf_ref.solve_sweep(tree, g['p'][e], g['q'][e])
+        assert np.max(np.abs(np.sqrt(b['v']) - g['V'][e])) < 1e-11
+        assert np.max(np.abs(np.sqrt(b['ell'][1:]) - g['I'][e])) < 1e-10
