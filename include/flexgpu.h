@@ -63,7 +63,11 @@ enum {
 enum { FP_VARIANT_THREAD = 0, FP_VARIANT_WARP = 1, FP_VARIANT_PAIR = 2 };
 
 /* action dtypes accepted by fp_step */
-enum { FP_F32 = 0, FP_F64 = 1 };
+/* Action dtypes of fp_step / fp_step_host.  FP_F32_POLICY: raw fp32 policy outputs; the kernel
+ * applies translate_action (utils/util.py:121-129) itself, in fp32 and in the reference's operation
+ * order -- clamp to [action_low, action_high], then 0.5 * (x + 1) * (high - low) + low (quirk Q5) --
+ * before widening to fp64, so the rollout loop needs no separate elementwise pass. */
+enum { FP_F32 = 0, FP_F64 = 1, FP_F32_POLICY = 2 };
 
 /* info row slots (FP_INFO_STRIDE doubles per env); keys of calculate_reward's dict
  * (flexibility_provision_env.py:696-704) plus the solver_failed flag (:337). */
@@ -120,6 +124,8 @@ typedef struct FpConfig {
     double x[FP_MAX_BUS];
     double imax[FP_MAX_BUS];     /* p.u. rating of that line (max_line_currents) */
     int32_t agent_bus[FP_MAX_AGENTS];  /* bus POSITION of each building */
+    int32_t reserved2_[3];
+    double action_low, action_high;    /* yaml action_low / action_high: the range translate_action maps into (FP_F32_POLICY) */
 } FpConfig;
 
 typedef struct FpHandle FpHandle;

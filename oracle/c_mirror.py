@@ -80,6 +80,19 @@ def use_all_cores():
 VARIANT_THREAD, VARIANT_WARP = 0, 1
 
 
+def translate_action_f32(x, low=0.0, high=1.0):
+    """numpy fp32 restatement of translate_action's continuous branch (utils/util.py:124-128), in
+    torch's operation order: clamp, + 1, * 0.5, * (high - low), + low, every step rounded to fp32.
+    Pinned on the reference's own function by tests/golden/ref_translate_action.npz."""
+    f = np.float32
+    x = np.asarray(x, dtype=f)
+    c = np.where(x < f(low), f(low), np.where(x > f(high), f(high), x)).astype(f)
+    t = (c + f(1.0)).astype(f)
+    t = (f(0.5) * t).astype(f)
+    t = (t * f(high - low)).astype(f)
+    return (t + f(low)).astype(f)
+
+
 def make_net(tree, args, agent_buses, pf_tol=None, pf_max_iter=32, raw_actions=False,
              fail_penalty=200.0, e_next_lb=-1e-8, variant=VARIANT_THREAD):
     """tree: oracle.ieee33.tree_arrays(net); args: dict with the reference's yaml keys.

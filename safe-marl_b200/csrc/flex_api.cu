@@ -45,7 +45,7 @@ struct FpHandle {
     const uint8_t* d_inject = nullptr;
     int keep_flows = 0;
     // staging for the host-buffer entry points
-    void* d_act_stage = nullptr; double* d_reward_stage = nullptr; uint8_t* d_done_stage = nullptr;
+    void* d_act_stage = nullptr; float* d_act_xlat = nullptr; double* d_reward_stage = nullptr; uint8_t* d_done_stage = nullptr;
     double* d_info_stage = nullptr;
     int grid_step = 0, grid_reset = 0, grid_pf = 0, grid_obs = 0;
     cudaStream_t host_streams[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
@@ -287,7 +287,7 @@ int fp_destroy(FpHandle* h) {
     cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
     cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
-    cudaFree(h->d_act_stage); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
+    cudaFree(h->d_act_stage); cudaFree(h->d_act_xlat); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
     for (int i = 0; i < FP_HOST_STREAMS; ++i) {
         if (h->host_streams[i]) cudaStreamDestroy(h->host_streams[i]);
         if (h->host_ev_out[i]) cudaEventDestroy(h->host_ev_out[i]);
@@ -355,6 +355,14 @@ static int bulk_io_ok(const EnvParams& p) {
     return (al16(p.rec) && al16(p.setp) && al16(p.V) && al16(p.reward) && al16(p.done) && (p.info == nullptr || al16(p.info))) ? 1 : 0;
 }
 
+// translate_action's constants exactly as torch forms them (utils/util.py:124-128): the clamp bounds
+// and `low` become fp32 scalars, `high - low` is a Python (double) difference turned into an fp32 scalar
+static void set_translate(const FpHandle* h, EnvParams& p) {
+    p.act_translate = 1;
+    p.act_lo = (float)h->cfg.action_low; p.act_hi = (float)h->cfg.action_high;
+    p.act_span = (float)(h->cfg.action_high - h->cfg.action_low);
+}
+
 static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cudaStream_t st) {
     const int grid = (mode == MODE_STEP) ? h->grid_step : h->grid_reset;
     if (h->pair) {
@@ -400,9 +408,21 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     if (!h) return FP_EINVAL;
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step: call fp_load_profiles first");
     if (!d_actions || !d_reward || !d_done) return fail(h, FP_EINVAL, "fp_step: null input/output");
-    if (act_dtype != FP_F32 && act_dtype != FP_F64) return fail(h, FP_EINVAL, "fp_step: bad action dtype");
+    if (act_dtype != FP_F32 && act_dtype != FP_F64 && act_dtype != FP_F32_POLICY) return fail(h, FP_EINVAL, "fp_step: bad action dtype");
     EnvParams p; fill_env_params(h, p);
     p.actions = d_actions; p.act_f64 = (act_dtype == FP_F64);
+    if (act_dtype == FP_F32_POLICY) {
+        if (h->variant == FP_VARIANT_THREAD && !h->pair) set_translate(h, p);      // fused into the step kernel
+        else {                                                                     // other variants: elementwise pre-pass
+            const size_t cnt = (size_t)h->n * h->dc.na * 4;
+            if (!h->d_act_xlat) CUDA_TRY(h, cudaMalloc(&h->d_act_xlat, cnt * 4));
+            EnvParams t; set_translate(h, t);
+            CUDA_TRY(h, launch_translate_actions((const float*)d_actions, h->d_act_xlat, (int64_t)cnt, t.act_lo, t.act_hi, t.act_span,
+                                                 (cudaStream_t)stream));
+            h->launches++;
+            p.actions = h->d_act_xlat;
+        }
+    }
     p.reward = d_reward; p.done = d_done; p.info = d_info; p.mask = d_mask;
     p.stats_partial = h->d_stats_partial;
     CUDA_TRY(h, launch_env_any(h, MODE_STEP, p, (cudaStream_t)stream));
@@ -433,6 +453,7 @@ static int enqueue_host_chunks(FpHandle* h, const void* h_actions, int act_dtype
         CUDA_TRY(h, cudaStreamWaitEvent(s_k, h->host_ev_out[0], 0));
         EnvParams p; fill_env_params(h, p);
         p.actions = h->d_act_stage; p.act_f64 = (act_dtype == FP_F64);
+        if (act_dtype == FP_F32_POLICY) set_translate(h, p);
         p.reward = h->d_reward_stage; p.done = h->d_done_stage; p.info = h_info ? h->d_info_stage : nullptr;
         p.stats_partial = h->d_stats_partial + (size_t)(1 + c) * cap * FP_NSTATS;
         p.tile_begin = t0; p.tile_end = t1;
@@ -472,7 +493,7 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
     if (!h) return FP_EINVAL;
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_host: call fp_load_profiles first");
     if (!h_actions || !h_reward || !h_done) return fail(h, FP_EINVAL, "fp_step_host: null buffer");
-    if (act_dtype != FP_F32 && act_dtype != FP_F64) return fail(h, FP_EINVAL, "fp_step_host: bad action dtype");
+    if (act_dtype != FP_F32 && act_dtype != FP_F64 && act_dtype != FP_F32_POLICY) return fail(h, FP_EINVAL, "fp_step_host: bad action dtype");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->n, na = (size_t)h->dc.na;
     if (!h->d_act_stage) {
@@ -489,7 +510,7 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
         h->host_chunks = (k < 1) ? 1 : ((k > FP_HOST_CHUNKS) ? FP_HOST_CHUNKS : k);
     }
     const int n_chunks = h->host_chunks;
-    if (h->variant != FP_VARIANT_THREAD || n_chunks == 1 || tiles < 4 * n_chunks) {  // small batch / warp variant: one shot
+    if (h->variant != FP_VARIANT_THREAD || (h->pair && act_dtype == FP_F32_POLICY) || n_chunks == 1 || tiles < 4 * n_chunks) {  // small batch / warp variant: one shot
         CUDA_TRY(h, cudaMemcpyAsync(h->d_act_stage, h_actions, n * abpe, cudaMemcpyHostToDevice, st));
         int rc = fp_step(h, h->d_act_stage, act_dtype, h->d_reward_stage, h->d_done_stage,
                          h_info ? h->d_info_stage : nullptr, nullptr, stream);

@@ -396,6 +396,13 @@ __global__ void k_stats_fold(const double* __restrict__ partial, int n_blocks, d
     }
 }
 
+// translate_action as a pre-pass (warp / pair variants; the thread kernels fuse it)
+__global__ void k_translate_actions(const float* __restrict__ in, float* __restrict__ out, int64_t n, float lo, float hi,
+                                    float span) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = translate_action_f32(in[i], lo, hi, span);
+}
+
 __global__ void k_pack_pvp(const double* __restrict__ pv, const double* __restrict__ price, int na,
                            int64_t T, double* __restrict__ pvp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,6 +450,11 @@ cudaError_t launch_pack_pvp(const double* pv, const double* price, int na, int64
                             cudaStream_t st) {
     int64_t n = T * FP_PVP_STRIDE;
     k_pack_pvp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, price, na, T, pvp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_translate_actions(const float* in, float* out, int64_t n, float lo, float hi, float span, cudaStream_t st) {
+    k_translate_actions<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, lo, hi, span);
     return cudaGetLastError();
 }
 

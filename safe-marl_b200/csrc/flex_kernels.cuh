@@ -23,6 +23,8 @@ struct EnvParams {
     double* pfl; double* qfl; double* isq;       // optional line-flow dump (nullptr = off)
     // step inputs/outputs
     const void* actions; int32_t act_f64;
+    // fp32 policy outputs: translate_action (utils/util.py:121-129) in fp32 before widening
+    int32_t act_translate; float act_lo, act_hi, act_span;
     double* reward; uint8_t* done; double* info;
     const uint8_t* mask; const uint8_t* inject;
     // reset inputs
@@ -86,3 +88,14 @@ cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, 
 cudaError_t launch_pack_pvp(const double* pv, const double* price, int na, int64_t T, double* pvp,
                             cudaStream_t st);
 int max_resident_grid(int mode);
+
+// translate_action (utils/util.py:124-128) on one fp32 action, in the reference's (torch fp32)
+// operation order: clamp, + 1, * 0.5, * (high - low), + low.  NaN propagates like th.clamp.
+__device__ __forceinline__ float translate_action_f32(float x, float lo, float hi, float span) {
+    x = (x < lo) ? lo : ((x > hi) ? hi : x);
+    float t = __fadd_rn(x, 1.0f);
+    t = __fmul_rn(0.5f, t);
+    t = __fmul_rn(t, span);
+    return __fadd_rn(t, lo);
+}
+cudaError_t launch_translate_actions(const float* in, float* out, int64_t n, float lo, float hi, float span, cudaStream_t st);

@@ -10,6 +10,7 @@ from .config import DEFAULT_ENV_ARGS, load_env_yaml, normalize_args
 from .network import Network, create_network
 from .profiles import Profiles, load_csv_profiles, synthetic_profiles
 from ._lib import FlexGpuError, INFO_KEYS, STAT_KEYS
+from .util import prep_obs, translate_action
 
 
 def __getattr__(name):

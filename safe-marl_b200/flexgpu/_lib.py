@@ -16,7 +16,7 @@ FP_MAX_AGENTS = 5
 FP_INFO_STRIDE = 8
 FP_NSTATS = 16
 FP_REC_STRIDE = 16
-FP_F32, FP_F64 = 0, 1
+FP_F32, FP_F64, FP_F32_POLICY = 0, 1, 2
 VARIANT_THREAD, VARIANT_WARP, VARIANT_PAIR = 0, 1, 2
 VARIANTS = {"thread": VARIANT_THREAD, "warp": VARIANT_WARP, "pair": VARIANT_PAIR}
 
@@ -44,7 +44,8 @@ class FpConfig(C.Structure):
         ("delta_t", C.c_double), ("fail_penalty", C.c_double), ("e_next_lb", C.c_double),
         ("parent", C.c_int32 * FP_MAX_BUS), ("r", C.c_double * FP_MAX_BUS),
         ("x", C.c_double * FP_MAX_BUS), ("imax", C.c_double * FP_MAX_BUS),
-        ("agent_bus", C.c_int32 * FP_MAX_AGENTS),
+        ("agent_bus", C.c_int32 * FP_MAX_AGENTS), ("reserved2_", C.c_int32 * 3),
+        ("action_low", C.c_double), ("action_high", C.c_double),
     ]
 
 

@@ -98,4 +98,5 @@ def make_fp_config(args, network):
         c.imax[i] = float(network.imax[i])
     for i, b in enumerate(args["buildings"]):
         c.agent_bus[i] = network.position[b]
+    c.action_low, c.action_high = float(args.get("action_low", 0.0)), float(args.get("action_high", 1.0))
     return c

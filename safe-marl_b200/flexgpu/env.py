@@ -249,26 +249,34 @@ class BatchedFlexProvisionEnv:
             return self.get_obs(), self.get_state()                     # :155
         return None
 
-    def step(self, actions, mask=None, want_info=True):
-        """Replaces step() (:241-356).  actions: [N, na, 4] (or [N, na*4]) fp32 or fp64 tensor."""
+    def step(self, actions, mask=None, want_info=True, translate=False):
+        """Replaces step() (:241-356).  actions: [N, na, 4] (or [N, na*4]) fp32 or fp64 tensor.
+        translate=True: `actions` are the policy's raw fp32 outputs and translate_action
+        (utils/util.py:121-129: clamp to [action_low, action_high], then 0.5 (x + 1)(high - low) + low,
+        all in fp32 -- quirk Q5) is applied inside the step kernel, as model.py:218-220 does on the host."""
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.ascontiguousarray(actions))
-        if actions.dtype not in (torch.float32, torch.float64):
+        if translate:
+            actions = actions.to(torch.float32)
+        elif actions.dtype not in (torch.float32, torch.float64):
             actions = actions.to(torch.float64)
         actions = actions.to(self.device).contiguous()
         if actions.numel() != self.n_envs * self.n_agents * self.n_actions:
             raise ValueError("actions must have n_envs * n_agents * 4 elements")         # :260
         m = self._dev(mask, torch.uint8)
-        dt = _lib.FP_F64 if actions.dtype == torch.float64 else _lib.FP_F32
+        dt = _lib.FP_F32_POLICY if translate else (_lib.FP_F64 if actions.dtype == torch.float64 else _lib.FP_F32)
         self._check(self._lib.fp_step(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
                                       _ptr(self._info) if want_info else None, _ptr(m), _stream()), "fp_step")
         info = {k: self._info[:, i] for i, k in enumerate(_lib.INFO_KEYS)} if want_info else {}
         return self._reward, self._done, info
 
-    def step_host(self, actions, want_info=False):
-        """End-to-end variant: host (numpy, ideally pinned) in, host out, through fp_step_host."""
+    def step_host(self, actions, want_info=False, translate=False):
+        """End-to-end variant: host (numpy, ideally pinned) in, host out, through fp_step_host.
+        translate: see step()."""
         a = np.ascontiguousarray(actions)
-        if a.dtype not in (np.float32, np.float64):
+        if translate:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+        elif a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float64)
         if a.size != self.n_envs * self.n_agents * self.n_actions:
             raise ValueError("actions must have n_envs * n_agents * 4 elements")
@@ -279,7 +287,7 @@ class BatchedFlexProvisionEnv:
                 done=torch.empty(N, dtype=torch.uint8).pin_memory(),
                 info=torch.empty(N, _lib.FP_INFO_STRIDE, dtype=torch.float64).pin_memory())
         hb = self._host
-        dt = _lib.FP_F64 if a.dtype == np.float64 else _lib.FP_F32
+        dt = _lib.FP_F32_POLICY if translate else (_lib.FP_F64 if a.dtype == np.float64 else _lib.FP_F32)
         self._check(self._lib.fp_step_host(
             self._h, a.ctypes.data_as(C.c_void_p), dt, C.c_void_p(hb["reward"].data_ptr()),
             C.c_void_p(hb["done"].data_ptr()), C.c_void_p(hb["info"].data_ptr()) if want_info else None,

@@ -71,3 +71,26 @@ def test_synthetic_profiles_shape_and_range(network):
 def test_profiles_validation():
     with pytest.raises(ValueError):
         Profiles(np.zeros((10, 32)), np.zeros((9, 32)), np.zeros((10, 5)), np.zeros(10))
+
+
+def test_translate_action_matches_reference_function():
+    """utils/util.py::translate_action itself produced the fixture (tests/golden/make_ref_golden.py):
+    the numpy restatement used by the mirror and flexgpu.util.translate_action reproduce it bit for bit."""
+    import os
+    from collections import namedtuple
+    import numpy as np
+    import torch
+    from oracle import c_mirror
+    from flexgpu import translate_action, prep_obs
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_translate_action.npz"))
+    lo, hi = float(g["low"][0]), float(g["high"][0])
+    assert np.array_equal(c_mirror.translate_action_f32(g["x"], lo, hi).reshape(g["y"].shape), g["y"])
+    A = namedtuple("A", "continuous action_low action_high")(True, lo, hi)
+    for i in (0, 1, 63):
+        raw, cp = translate_action(A, torch.from_numpy(g["x"][i]), None)
+        assert cp.dtype == torch.float32 and np.array_equal(cp.numpy(), g["y"][i])
+    assert g["y"].min() >= 0.5 and g["y"].max() <= 1.0                                   # quirk Q5
+    obs = [np.arange(144, dtype=np.float64) + i for i in range(5)]
+    t = prep_obs(obs)
+    assert t.dtype == torch.float32 and tuple(t.shape) == (5, 144)
+    assert prep_obs(torch.zeros(7, 5, 144, dtype=torch.float64)).shape == (7, 5, 144)
