@@ -304,18 +304,25 @@ static double clipd(double x, double lo, double hi) { double t = x > lo ? x : lo
 
 typedef struct { double pred, ch, dis, qpv; } Setp;
 
+/* x / d with r = RN(1/d): q0 = x r, rem = x - q0 d (exact), q = q0 + rem r -- the correctly rounded
+ * quotient (Markstein), which is what the kernels evaluate instead of a division subroutine */
+static double div_const(double x, double d, double r) {
+    double q0 = x * r, rem = fma(-q0, d, x);
+    return fma(rem, r, q0);
+}
+
 static void ess_clip(const FoNet* c, double* ch_, double* dis_, double e_now) {
     double ch = clipd(*ch_, 0.0, c->p_ch_max), dis = clipd(*dis_, 0.0, c->p_dis_max);
-    const double inv_eta_dis = 1.0 / c->eta_dis;
+    const double inv_eta_dis = 1.0 / c->eta_dis, inv_eta_ch = 1.0 / c->eta_ch;
     double e_next = (e_now + c->eta_ch * ch) - inv_eta_dis * dis;
     if (e_next > c->e_max) {
-        double excess = e_next - c->e_max, tt = excess / c->eta_ch;
+        double excess = e_next - c->e_max, tt = div_const(excess, c->eta_ch, inv_eta_ch);
         if (ch > tt) ch = ch - tt;
         else { dis = dis + (excess - ch * c->eta_ch) * c->eta_dis; ch = 0.0; }
     } else if (e_next < c->e_min) {
         double lack = c->e_min - e_next, tt = lack * c->eta_dis;
         if (dis > tt) dis = dis - tt;
-        else { ch = ch + (lack - dis / c->eta_dis) / c->eta_ch; dis = 0.0; }
+        else { ch = ch + div_const(lack - div_const(dis, c->eta_dis, inv_eta_dis), c->eta_ch, inv_eta_ch); dis = 0.0; }
     }
     *ch_ = clipd(ch, 0.0, c->p_ch_max); *dis_ = clipd(dis, 0.0, c->p_dis_max);
 }

@@ -175,6 +175,7 @@ static void fill_devcfg(const FpConfig& c, DevCfg& d) {
     d.obs_w = 6 * c.history;
     d.pf_tol = c.pf_tol; d.v_min = c.v_min; d.v_max = c.v_max; d.e_min = c.e_min; d.e_max = c.e_max;
     d.p_ch_max = c.p_ch_max; d.p_dis_max = c.p_dis_max; d.eta_ch = c.eta_ch; d.eta_dis = c.eta_dis;
+    d.inv_eta_ch = 1.0 / c.eta_ch;
     d.inv_eta_dis = 1.0 / c.eta_dis;                   // python evaluates (1 / eta_dis) first (:634, pf.py:97)
     d.mpr = c.max_power_reduction; d.kappa = c.kappa; d.pv_cost = c.pv_cost; d.ess_cost = c.ess_cost;
     d.discomfort_coeff = c.discomfort_coeff; d.voltage_coeff = c.voltage_coeff; d.delta_t = c.delta_t;

@@ -25,7 +25,7 @@
 // Scalar configuration, passed by value as a kernel parameter (uniform constant-bank reads).
 struct DevCfg {
     int32_t nb, nl, na, history, episode_limit, raw_actions, pf_max_iter, obs_w;
-    double pf_tol, v_min, v_max, e_min, e_max, p_ch_max, p_dis_max, eta_ch, eta_dis, inv_eta_dis;
+    double pf_tol, v_min, v_max, e_min, e_max, p_ch_max, p_dis_max, eta_ch, eta_dis, inv_eta_dis, inv_eta_ch;
     double mpr, kappa, pv_cost, ess_cost, discomfort_coeff, voltage_coeff, delta_t, fail_penalty;
     double e_next_lb, slack_pen;
     int32_t slack_viol, pad_;

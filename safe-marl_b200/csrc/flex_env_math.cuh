@@ -6,30 +6,38 @@
 // Setpoints of one agent (executed by the agent's lane).
 struct Setpoint { double pred, ch, dis, qpv; };
 
-// flexibility_provision_env.py:628-661 (no delta_t here -- quirk Q3)
+// x / d for a constant divisor with r = RN(1 / d): one multiplication and two fused
+// multiply-adds give the CORRECTLY ROUNDED quotient (Markstein: q0 = x r, rem = x - q0 d exactly,
+// q = q0 + rem r), i.e. the bits of the reference's Python `x / d`, without the division
+// subroutine and its branches (checked against true division on 4e8 values; mirrored in
+// oracle/c/flex_oracle.c).
+__device__ __forceinline__ double div_const(double x, double d, double r) {
+    const double q0 = x * r;
+    const double rem = fma(-q0, d, x);
+    return fma(rem, r, q0);
+}
+
+// flexibility_provision_env.py:628-661 (no delta_t here -- quirk Q3).  Branch-free: both
+// candidate corrections are evaluated and selected, so the 32 envs of a warp never diverge.
 __device__ __forceinline__ void ess_energy_clip(const DevCfg& c, double& ch, double& dis, double e_now) {
     ch = clipd(ch, 0.0, c.p_ch_max);
     dis = clipd(dis, 0.0, c.p_dis_max);
-    double e_next = (e_now + c.eta_ch * ch) - c.inv_eta_dis * dis;
-    if (e_next > c.e_max) {
-        double excess = e_next - c.e_max;
-        double t = excess / c.eta_ch;
-        if (ch > t) {
-            ch = ch - t;
-        } else {
-            dis = dis + (excess - ch * c.eta_ch) * c.eta_dis;
-            ch = 0.0;
-        }
-    } else if (e_next < c.e_min) {
-        double lack = c.e_min - e_next;
-        double t = lack * c.eta_dis;
-        if (dis > t) {
-            dis = dis - t;
-        } else {
-            ch = ch + (lack - dis / c.eta_dis) / c.eta_ch;
-            dis = 0.0;
-        }
-    }
+    const double e_next = (e_now + c.eta_ch * ch) - c.inv_eta_dis * dis;
+    const bool over = e_next > c.e_max, under = !over && (e_next < c.e_min);
+    // e_next > e_max (:637-646)
+    const double excess = e_next - c.e_max;
+    const double t = div_const(excess, c.eta_ch, c.inv_eta_ch);
+    const bool o1 = ch > t;
+    const double ch_o = o1 ? (ch - t) : 0.0;
+    const double dis_o = o1 ? dis : (dis + (excess - ch * c.eta_ch) * c.eta_dis);
+    // e_next < e_min (:647-656)
+    const double lack = c.e_min - e_next;
+    const double t2 = lack * c.eta_dis;
+    const bool u1 = dis > t2;
+    const double dis_u = u1 ? (dis - t2) : 0.0;
+    const double ch_u = u1 ? ch : (ch + div_const(lack - div_const(dis, c.eta_dis, c.inv_eta_dis), c.eta_ch, c.inv_eta_ch));
+    ch = over ? ch_o : (under ? ch_u : ch);
+    dis = over ? dis_o : (under ? dis_u : dis);
     ch = clipd(ch, 0.0, c.p_ch_max);
     dis = clipd(dis, 0.0, c.p_dis_max);
 }
@@ -50,9 +58,10 @@ __device__ __forceinline__ Setpoint apply_actions_frac(const DevCfg& c, bool sca
         pct = a0; ch = a1; dis = a2; qpv = a3;
     }
     pct = clipd(pct, 0.0, c.mpr);                           // :676-677
-    if (ch > 0.0 && dis > 0.0) {                            // :663-674
-        if (ch > dis) { ch = ch - dis; dis = 0.0; }
-        else          { dis = dis - ch; ch = 0.0; }
+    {                                                       // :663-674, branch-free
+        const bool both = (ch > 0.0) && (dis > 0.0), gt = ch > dis;
+        const double ch2 = gt ? (ch - dis) : 0.0, dis2 = gt ? 0.0 : (dis - ch);
+        ch = both ? ch2 : ch; dis = both ? dis2 : dis;
     }
     ess_energy_clip(c, ch, dis, e_clip);                    // :289-290
     Setpoint s;
