@@ -144,6 +144,22 @@ def python_restatement_rate(prof, budget_s=5.0):
     return k / (time.perf_counter() - t0)
 
 
+def ncu_traffic(envs_per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_env_t<STEP> launch from the committed
+    `ncu --set full` capture (profiles/r1_step_kernel_traffic.json), if it was taken at this launch size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_step_kernel_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch"]) if int(d["envs"]) == int(envs_per_gpu) else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def workload_name(envs_per_gpu):
+    return (f"fused_env_step_{envs_per_gpu}_envs_per_gpu (one GPU's shard of BASELINE config 5 = 2^20 envs over 8 GPUs; "
+            f"N=8 is config 5)")
+
+
 def run_reference(args):
     """--impl reference: the CPU arm (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -172,8 +188,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"fused_env_step_{n}_envs_per_step (BASELINE config 3, bounded CPU sample)",
-                   "envs": n, "profile_rows": args.rows},
+        "config": {"workload": workload_name(args.envs_per_gpu), "envs_per_gpu": args.envs_per_gpu,
+                   "total_envs": args.envs_per_gpu * args.gpus, "profile_rows": args.rows,
+                   "actions": "fp32 uniform(0,1), host memory",
+                   "sample": f"each step = {n} envs of that workload (bounded CPU sample), rank 0 only"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} envs x {steps} steps, C port of the step (oracle/c/flex_oracle.c, OpenMP); "
                                    f"the reference itself (Pyomo+IPOPT per step) is not installable; "
@@ -334,7 +352,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"fused_env_step_{E}_envs_per_gpu (one GPU's shard of BASELINE config 5 = 2^20 envs over 8 GPUs; N=8 is config 5)",
+            "config": {"workload": workload_name(E),
                        "kernel_variant": args.variant, "envs_per_gpu": E, "total_envs": total_envs, "profile_rows": args.rows,
                        "actions": "fp32 uniform(0,1), resident in HBM", "auto_reset_every": EPISODE_STEPS,
                        "l2": "flushed before every timed step (256 MiB memset, untimed)" if not args.no_flush else "NOT flushed",
@@ -345,11 +363,12 @@ def main():
                     "steps": Ke, "api": "BatchedFlexProvisionEnv.step_host -> fp_step_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": {"thread": "k_env_t<STEP>", "pair": "k_env_p<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
+                         "traffic": ncu_traffic(E), "kernel": {"thread": "k_env_t<STEP>", "pair": "k_env_p<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
                          "kernel_ms_median": kern_ms, "peak_source": peak_src,
-                         "note": "not HBM-bound: ~4500 fp64 lane-ops per env-step (7 one-pass sweeps + final pass over 32 "
-                                 "lines) cap the kernel at ~3.8e9 env-steps/s on the fp64 pipe (59 lane-ops/clk/SM "
-                                 "measured), i.e. 73 % of this HBM roofline at best; see DESIGN.md section 3"},
+                         "note": "not HBM-bound: 17 fp64 ops x 32 lines x 6-7 one-pass sweeps + the final pass + the setpoint "
+                                 "arithmetic = ~4400 fp64 lane-ops per env-step, which cap the kernel at ~3.9e9 env-steps/s "
+                                 "on the fp64 pipe (59 lane-ops/clk/SM measured), i.e. 75 % of this HBM roofline at best; "
+                                 "see DESIGN.md section 3"},
             "stats": {k: float(v) for k, v in stats.items()},
         }
         if obs_extra is not None:
