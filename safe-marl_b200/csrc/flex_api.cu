@@ -165,6 +165,7 @@ static int build_topology(const FpConfig& c, DevTopo& t, ThreadTopo& tt, int& sh
     for (int i = 0; i < 8; ++i) { tt.agent_lane[i] = (int8_t)t.agent_lane[i]; tt.agent_col[i] = (int8_t)t.agent_col[i]; }
     tt.nl = nl; tt.n_slots = tb.n_slots; tt.any_imax = any_imax ? 1 : 0;
     shape = thread_shape_of(tt, par_lane);
+    if (c.n_agents != FP_MAX_AGENTS) shape = SHAPE_RUNTIME;      // the built-in shape unrolls the reference's five buildings
     return FP_OK;
 }
 
