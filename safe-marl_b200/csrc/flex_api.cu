@@ -265,6 +265,10 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
         const int cap_step = thread_kernel_max_grid(MODE_STEP, h->tt.n_slots, h->shape);
         const int cap_reset = thread_kernel_max_grid(MODE_RESET, h->tt.n_slots, h->shape);
         h->grid_step = (int)((tiles < cap_step) ? tiles : cap_step);
+        if (const char* gs = std::getenv("FLEXGPU_GRID_STEP")) {      // tuning knob: persistent CTAs of the step kernel
+            const int g = std::atoi(gs);
+            if (g > 0 && g <= cap_step) h->grid_step = (int)((tiles < g) ? tiles : g);
+        }
         h->grid_reset = (int)((tiles < cap_reset) ? tiles : cap_reset);
         h->grid_pf = thread_kernel_max_grid(MODE_PF, h->tt.n_slots, h->shape);
         h->stats_cap = cap_step;
