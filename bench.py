@@ -213,7 +213,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config3", action="store_true", help="skip the extra 65 536-env (config 3) measurement at N=1")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostics only)")
-    ap.add_argument("--with-obs", action="store_true", help="also time step+get_obs (reported as extra)")
+    ap.add_argument("--no-obs", action="store_true", help="skip the extra step+get_obs measurement (rollout-loop cost)")
     ap.add_argument("--variant", default="thread", choices=["thread", "warp", "pair"], help="kernel variant (see include/flexgpu.h)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -306,7 +306,7 @@ def main():
     e2e_s = time.perf_counter() - t0
 
     obs_extra = None
-    if args.with_obs:
+    if not args.no_obs:
         env.reset(return_obs=False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(); e0.record(stream)

@@ -182,6 +182,15 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
  * of what the next pushing call would return minus the append. */
 int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream);
 
+/* Handle-owned fp32 observation window [N][na][history*6] (allocated on first call).  Passing this
+ * pointer as d_out of fp_get_obs(h, d_out, FP_F32, push = 1, ...) selects the in-place path of the
+ * rollout loop (one pushing get_obs per step, madrl/models/model.py:223): the window the previous call
+ * returned is shifted by one 6-vector per agent and the current one appended -- a third of the
+ * traffic of re-materialising it from the history ring.  The contents are valid until the next pushing
+ * call and must not be modified by the caller; any other pushing fp_get_obs makes the next in-place
+ * call rebuild the window from the ring first. */
+int fp_obs_window(FpHandle* h, float** d_window);
+
 /* Replaces get_state() (:358-368): out[N][2*n_bus + na + n_bus + 1 + na]. */
 int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream);
 

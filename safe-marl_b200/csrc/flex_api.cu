@@ -39,6 +39,7 @@ struct FpHandle {
     double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr, *d_PQD = nullptr;
     uint64_t* d_rec = nullptr;
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
+    float* d_obsw = nullptr; bool obsw_valid = false;   // fp32 observation window kept in place (fp_obs_window)
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
     int stats_rows = 0, stats_cap = 0;     // rows of one launch's statistics block
@@ -239,7 +240,11 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     CREATE_TRY(cudaMemset(h->d_setp, 0, (size_t)n_envs * 4 * na * 8));
     CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_envs * na * H * 6 * 8));
     CREATE_TRY(cudaMemset(h->d_hist, 0, (size_t)n_envs * na * H * 6 * 8));
-    h->grid_obs = grid_for(n_envs, max_resident_grid(MODE_STEP));
+    {   // observation / state kernels are streaming kernels: a full SM worth of warps (8 CTAs of 256 threads)
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        h->grid_obs = grid_for(n_envs, 8 * (sms > 0 ? sms : 1));
+    }
     // FP_VARIANT_PAIR: two lanes per env (flex_pair_kernels.cu), IEEE 33-bus shape only -- same results bit
     // for bit; measured ~10 % slower than one thread per env on B200 (profiles/), kept as a selectable variant
     h->pair = 0;
@@ -291,7 +296,7 @@ int fp_destroy(FpHandle* h) {
     cudaSetDevice(h->device);
     predictor_free(&h->pred);
     cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
-    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist);
+    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsw);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
     cudaFree(h->d_act_stage); cudaFree(h->d_act_xlat); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
     for (int i = 0; i < FP_HOST_STREAMS; ++i) {
@@ -613,8 +618,30 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_obs: bad arguments");
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
+    if (push && dtype == FP_F32 && h->d_obsw && d_out == (void*)h->d_obsw && h->obsw_valid) {
+        // the caller reads the handle-owned window: shift it in place (k_obs_shift)
+        CUDA_TRY(h, launch_obs_shift(p, h->d_obsw, h->grid_obs, (cudaStream_t)stream));
+        h->launches++;
+        return FP_OK;
+    }
     CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
+    // a pushing call that filled the window itself (re)validates it; any other pushing call leaves it behind
+    if (push) h->obsw_valid = (dtype == FP_F32 && h->d_obsw && d_out == (void*)h->d_obsw &&
+                               obs_shift_supported(h->dc.na, h->dc.history));
+    return FP_OK;
+}
+
+int fp_obs_window(FpHandle* h, float** d_window) {
+    if (!h || !d_window) return FP_EINVAL;
+    if (!h->d_obsw) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        const size_t bytes = (size_t)h->n * h->dc.na * h->dc.history * 6 * 4;
+        CUDA_TRY(h, cudaMalloc(&h->d_obsw, bytes));
+        CUDA_TRY(h, cudaMemset(h->d_obsw, 0, bytes));
+        h->obsw_valid = false;
+    }
+    *d_window = h->d_obsw;
     return FP_OK;
 }
 

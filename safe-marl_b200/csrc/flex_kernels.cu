@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_env(const EnvParams prm) {
 
         // ---------------------------------------------------------------- gather the profile row
         // Quirk Q1: the row in force is max(steps-1, 1); the row loaded after the solve is `steps`.
-        const int64_t row = (int64_t)start + ((MODE == MODE_STEP && steps > 1) ? (steps - 1) : 1);
+        const int64_t row = (int64_t)start + ((MODE == MODE_STEP && steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);
         double pl = 0.0, ql = 0.0;
         if (lane < nl) {
             pl = __ldg(prm.P + row * nl + my_col);
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
         const uint64_t tm = rec[FP_REC_TIME], hh = rec[FP_REC_HIST];
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
         const int32_t cnt = (int32_t)(uint32_t)hh;
-        const int64_t row = (int64_t)start + ((steps > 1) ? (steps - 1) : 1);   // row currently loaded (Q1)
+        const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);   // row currently loaded (Q1)
         double* hist = prm.hist + e * (int64_t)(na * H * 6);
         // current 6-vector per agent (:376-384): lanes 0 .. 6*na-1
         const int slot = cnt % H;
@@ -357,6 +357,77 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
     }
 }
 
+// In-place variant for the rollout loop (one pushing fp32 get_obs per step, model.py:223): the
+// window the previous call returned IS the state -- obsw[N][na][H*6] fp32, handle-owned -- and a push
+// shifts every agent's row by one 6-vector and appends the current one: 2880 B read + 2880 B written
+// per env with coalesced 8-byte accesses (a 6-float shift keeps float2 alignment), instead of
+// re-materialising the window from the fp64 ring with scattered reads.  The ring is still pushed
+// (it stays the source of truth for fp64 / non-pushing / out-of-place reads).  cnt == 0 (first push
+// after a reset) ignores the old window: zero padding in front (:393-396).
+constexpr int OBS_SHIFT_IT = 12;                   // 32 * 12 float2 >= na * H * 3 for na <= 5, H <= 25
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_shift(const ObsParams prm, float* __restrict__ obsw) {
+    __shared__ float s_cur[WARPS_PER_CTA][32];
+    const DevCfg& c = prm.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int na = c.na, H = c.history, nl = c.nl;
+    const int W2 = H * 3, tot = na * W2;           // float2 units per agent row / per env
+    const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
+    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+        float2* w = reinterpret_cast<float2*>(obsw) + e * (int64_t)tot;
+        // 1. the old window, shifted by one entry (independent of everything below: issued first)
+        float2 v[OBS_SHIFT_IT];
+        {
+            int i = 0, j = lane;
+            while (j >= W2) { j -= W2; ++i; }
+#pragma unroll
+            for (int it = 0; it < OBS_SHIFT_IT; ++it) {
+                const int idx = lane + 32 * it;
+                v[it] = (idx < tot && j < W2 - 3) ? w[idx + 3] : make_float2(0.f, 0.f);
+                j += 32;
+                while (j >= W2) { j -= W2; ++i; }
+            }
+        }
+        // 2. the current 6-vector per agent (:376-384): lanes 0 .. 6*na-1; ring push
+        uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
+        const uint64_t tm = rec[FP_REC_TIME], hh = rec[FP_REC_HIST];
+        const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
+        const int32_t cnt = (int32_t)(uint32_t)hh;
+        const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);   // row currently loaded (Q1)
+        double cur = 0.0;
+        if (lane < 6 * na) {
+            const int i = lane / 6, f = lane - 6 * i;
+            const int col = prm.agent_col[i];
+            if (f == 0) cur = __ldg(prm.P + row * nl + col);
+            else if (f == 1) cur = __ldg(prm.Q + row * nl + col);
+            else if (f == 2) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + i);
+            else if (f == 3) cur = prm.V[e * c.nb + col + 1];
+            else if (f == 4) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
+            else cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
+            prm.hist[e * (int64_t)(na * H * 6) + (i * H + cnt % H) * 6 + f] = cur;
+        }
+        s_cur[warp][lane] = (float)cur;
+        __syncwarp();                              // every load of the old window has landed
+        // 3. the new window, in place
+        {
+            int i = 0, j = lane;
+            while (j >= W2) { j -= W2; ++i; }
+#pragma unroll
+            for (int it = 0; it < OBS_SHIFT_IT; ++it) {
+                const int idx = lane + 32 * it;
+                if (idx < tot) {
+                    float2 x = (cnt > 0) ? v[it] : make_float2(0.f, 0.f);
+                    if (j >= W2 - 3) { const int k = i * 6 + 2 * (j - (W2 - 3)); x = make_float2(s_cur[warp][k], s_cur[warp][k + 1]); }
+                    w[idx] = x;
+                }
+                j += 32;
+                while (j >= W2) { j -= W2; ++i; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(FP_CTA_THREADS) k_state(const ObsParams prm) {
     const DevCfg& c = prm.c;
@@ -368,7 +439,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_state(const ObsParams prm) {
         const uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
         const uint64_t tm = rec[FP_REC_TIME];
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
-        const int64_t row = (int64_t)start + ((steps > 1) ? (steps - 1) : 1);
+        const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);
         OutT* out = reinterpret_cast<OutT*>(prm.out) + e * (int64_t)W;
         for (int o = lane; o < W; o += 32) {
             double x;
@@ -432,6 +503,13 @@ cudaError_t launch_power_flow(const PfParams& prm, int grid, cudaStream_t st) {
 cudaError_t launch_obs(const ObsParams& prm, int f64, int grid, cudaStream_t st) {
     if (f64) k_obs<double><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
     else k_obs<float><<<grid, FP_CTA_THREADS, 0, st>>>(prm);
+    return cudaGetLastError();
+}
+
+int obs_shift_supported(int na, int history) { return na * history * 3 <= 32 * OBS_SHIFT_IT; }
+
+cudaError_t launch_obs_shift(const ObsParams& prm, float* obsw, int grid, cudaStream_t st) {
+    k_obs_shift<<<grid, FP_CTA_THREADS, 0, st>>>(prm, obsw);
     return cudaGetLastError();
 }
 

@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 8) k_env_p(const EnvParamsP pr
             }
         }
         // Quirk Q1: the row in force is max(steps-1, 1); the row loaded after the solve is `steps`.
-        const int32_t row = start + ((MODE == MODE_STEP && steps > 1) ? (steps - 1) : 1);
+        const int32_t row = start + ((MODE == MODE_STEP && steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);
 
         // ------------------------------------------------------------ gather the profile rows
         // one coalesced 256-byte row per instruction (a different dataset row per env), written
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 8) k_env_p(const EnvParamsP pr
         __syncwarp();
         if (MODE == MODE_STEP && have_next) {
             const int32_t sn = (int32_t)(uint32_t)time_next, tn = (int32_t)(time_next >> 32);
-            const int64_t rown = (int64_t)sn + ((tn > 1) ? (tn - 1) : 1);
+            const int64_t rown = (int64_t)sn + ((tn > 1) ? min(tn - 1, c.episode_limit + c.history) : 1);
             const char* pp = reinterpret_cast<const char*>(q.P + rown * nl);
             const char* qp = reinterpret_cast<const char*>(q.Q + rown * nl);
             prefetch_l2(pp); prefetch_l2(qp);

@@ -83,6 +83,7 @@ class BatchedFlexProvisionEnv:
         self._views = None
         self._inject = None
         self._host = None
+        self._obsw = None
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -297,7 +298,22 @@ class BatchedFlexProvisionEnv:
 
     # ------------------------------------------------------------------ observations
     def get_obs(self, push=True, dtype=torch.float32):
-        """Replaces get_obs() (:370-403).  push=True reproduces its history side effect (Q7)."""
+        """Replaces get_obs() (:370-403).  push=True reproduces its history side effect (Q7).
+
+        The default call (pushing, fp32 -- what the rollout loop does once per step, model.py:223) returns a
+        view of the handle-owned window, which the library updates IN PLACE (shift by one entry + append):
+        treat it as read-only; it is valid until the next pushing call.  push=False and fp64 reads go
+        through their own buffers."""
+        if push and dtype == torch.float32:
+            if self._obsw is None:
+                p = C.c_void_p()
+                self._check(self._lib.fp_obs_window(self._h, C.byref(p)), "fp_obs_window")
+                n = self.n_envs * self.n_agents * self.obs_size
+                holder = _ExternalCudaBuffer(p.value, n * 4, self.device.index or 0)
+                self._obsw = torch.as_tensor(holder, device=self.device).view(torch.float32).view(
+                    self.n_envs, self.n_agents, self.obs_size)
+            self._check(self._lib.fp_get_obs(self._h, _ptr(self._obsw), _lib.FP_F32, 1, _stream()), "fp_get_obs")
+            return self._obsw
         buf = self._obs.get(dtype)
         if buf is None:
             buf = torch.empty(self.n_envs, self.n_agents, self.obs_size, dtype=dtype, device=self.device)
