@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from .config import convert, make_fp_config, normalize_args
 from .network import Network, create_network
 from .profiles import Profiles, synthetic_profiles
@@ -377,11 +377,11 @@ class BatchedFlexProvisionEnv:
         reduce=True the vector is all-reduced (NCCL) -- the only collective on this path."""
         self._check(self._lib.fp_stats_read(self._h, _ptr(self._stats), _stream()), "fp_stats_read")
         out = self._stats.clone()
-        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM)
+        if reduce:
+            sharding.reduce_stats(out)
         if reset:
             self._check(self._lib.fp_stats_reset(self._h, _stream()), "fp_stats_reset")
-        return {k: out[i] for i, k in enumerate(_lib.STAT_KEYS)}
+        return sharding.stats_dict(out)
 
     # ------------------------------------------------------------------ test hooks
     def inject_failure(self, mask):
