@@ -250,8 +250,10 @@ class BatchedFlexProvisionEnv:
             return self.get_obs(), self.get_state()                     # :155
         return None
 
-    def step(self, actions, mask=None, want_info=True, translate=False):
+    def step(self, actions, mask=None, want_info=True, translate=False, return_obs=False):
         """Replaces step() (:241-356).  actions: [N, na, 4] (or [N, na*4]) fp32 or fp64 tensor.
+        return_obs=True appends the next observation (one pushing get_obs, as model.py:223 does right
+        after the step) to the returned tuple: (reward, done, info, obs).
         translate=True: `actions` are the policy's raw fp32 outputs and translate_action
         (utils/util.py:121-129: clamp to [action_low, action_high], then 0.5 (x + 1)(high - low) + low,
         all in fp32 -- quirk Q5) is applied inside the step kernel, as model.py:218-220 does on the host."""
@@ -269,6 +271,8 @@ class BatchedFlexProvisionEnv:
         self._check(self._lib.fp_step(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
                                       _ptr(self._info) if want_info else None, _ptr(m), _stream()), "fp_step")
         info = {k: self._info[:, i] for i, k in enumerate(_lib.INFO_KEYS)} if want_info else {}
+        if return_obs:
+            return self._reward, self._done, info, self.get_obs()
         return self._reward, self._done, info
 
     def step_host(self, actions, want_info=False, translate=False):
