@@ -54,8 +54,10 @@ enum {
 /* kernel variants (FpConfig.variant).  All compute the same DistFlow fixed point; THREAD/PAIR and
  * WARP differ in floating-point summation order (results agree to ~1e-12):
  *   THREAD  one CUDA thread per env, one-pass sweep with the currents in registers -- the
- *           throughput path; converges on max |dl| < pf_tol (squared current, compared on the
- *           high words of the fp64 patterns), default 1e-6.
+ *           throughput path; converges on max_k |P_k^2 + Q_k^2 - v_k l_k| < pf_tol (residual of the
+ *           current row, utils/pf.py:85-88, compared on the high words of the fp64 patterns) and
+ *           updates the currents once more after the test; default 1e-5 (errors against a Newton
+ *           solution: V 1e-11, P/Q 6e-9, I 6e-8 p.u. -- the parity bar is 1e-6).
  *   WARP    one warp per env, lane = line, shuffle scans -- the lowest latency for tiny
  *           batches; converges on max |dv| <= pf_tol (squared voltage), default 1e-9.
  *   PAIR    two lanes per env (main feeder | laterals), IEEE 33-bus shape only; bit-identical to
