@@ -188,14 +188,16 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
  * of what the next pushing call would return minus the append. */
 int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream);
 
-/* Handle-owned fp32 observation window [N][na][history*6] (allocated on first call).  Passing this
- * pointer as d_out of fp_get_obs(h, d_out, FP_F32, push = 1, ...) selects the in-place path of the
- * rollout loop (one pushing get_obs per step, madrl/models/model.py:223): the window the previous call
- * returned is shifted by one 6-vector per agent and the current one appended -- a third of the
- * traffic of re-materialising it from the history ring.  The contents are valid until the next pushing
- * call and must not be modified by the caller; any other pushing fp_get_obs makes the next in-place
- * call rebuild the window from the ring first. */
-int fp_obs_window(FpHandle* h, float** d_window);
+/* get_obs() for the rollout loop (one pushing fp32 call per step, madrl/models/model.py:223) WITHOUT
+ * re-materialising the window: the handle keeps a mirror ring [N][na][2*history][6] fp32 in which every
+ * pushed 6-vector is stored twice, history slots apart, so the last `history` entries are always one
+ * contiguous run.  push != 0 appends the current 6-vector of every agent (side effect of get_obs, quirk
+ * Q7; 48 bytes per agent instead of the whole 576-byte row); *d_view then points at env 0 / agent 0 of
+ * the window [oldest .. newest], element (e, i, k) at d_view[e * env_pitch + i * agent_pitch + k],
+ * k < history*6, pitches in floats.  The view is read-only for the caller and valid until the next
+ * pushing call.  Resets restart the zero padding of the envs they reset.  Pushing through fp_get_obs
+ * instead makes the next view call rebuild the ring from the fp64 history (correct, one slower call). */
+int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream);
 
 /* Replaces get_state() (:358-368): out[N][2*n_bus + na + n_bus + 1 + na]. */
 int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream);

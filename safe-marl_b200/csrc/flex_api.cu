@@ -39,7 +39,8 @@ struct FpHandle {
     double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr, *d_PQD = nullptr;
     uint64_t* d_rec = nullptr;
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
-    float* d_obsw = nullptr; bool obsw_valid = false;   // fp32 observation window kept in place (fp_obs_window)
+    // fp32 mirror ring of the observation history (fp_get_obs_view): [N][na][2H][6], last written slot, validity
+    float* d_obsm = nullptr; int obs_q = 0; bool obsm_valid = false;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
     int stats_rows = 0, stats_cap = 0;     // rows of one launch's statistics block
@@ -296,7 +297,7 @@ int fp_destroy(FpHandle* h) {
     cudaSetDevice(h->device);
     predictor_free(&h->pred);
     cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
-    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsw);
+    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsm);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
     cudaFree(h->d_act_stage); cudaFree(h->d_act_xlat); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
     for (int i = 0; i < FP_HOST_STREAMS; ++i) {
@@ -400,6 +401,10 @@ int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const doub
     p.inject = nullptr;
     CUDA_TRY(h, launch_env_any(h, MODE_RESET, p, (cudaStream_t)stream));
     h->launches++;
+    if (h->d_obsm && h->obsm_valid) {              // restart the zero padding of the reset envs' observation windows
+        CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 2 * h->dc.history * 6, (cudaStream_t)stream));
+        h->launches++;
+    }
     return FP_OK;
 }
 
@@ -411,6 +416,10 @@ int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_
     p.inject = nullptr;
     CUDA_TRY(h, launch_env_any(h, MODE_RESET, p, (cudaStream_t)stream));
     h->launches++;
+    if (h->d_obsm && h->obsm_valid) {
+        CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 2 * h->dc.history * 6, (cudaStream_t)stream));
+        h->launches++;
+    }
     return FP_OK;
 }
 
@@ -618,30 +627,37 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_obs: bad arguments");
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
-    if (push && dtype == FP_F32 && h->d_obsw && d_out == (void*)h->d_obsw && h->obsw_valid) {
-        // the caller reads the handle-owned window: shift it in place (k_obs_shift)
-        CUDA_TRY(h, launch_obs_shift(p, h->d_obsw, h->grid_obs, (cudaStream_t)stream));
-        h->launches++;
-        return FP_OK;
-    }
     CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
-    // a pushing call that filled the window itself (re)validates it; any other pushing call leaves it behind
-    if (push) h->obsw_valid = (dtype == FP_F32 && h->d_obsw && d_out == (void*)h->d_obsw &&
-                               obs_shift_supported(h->dc.na, h->dc.history));
+    if (push) h->obsm_valid = false;               // the mirror ring missed this push: rebuilt on the next view
     return FP_OK;
 }
 
-int fp_obs_window(FpHandle* h, float** d_window) {
-    if (!h || !d_window) return FP_EINVAL;
-    if (!h->d_obsw) {
+int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream) {
+    if (!h || !d_view) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs_view: call fp_load_profiles first");
+    const int H = h->dc.history, na = h->dc.na;
+    const int64_t per_env = (int64_t)na * 2 * H * 6;
+    cudaStream_t st = (cudaStream_t)stream;
+    ObsParams p; fill_obs_params(h, p, nullptr, 1);
+    if (!h->d_obsm) {
         CUDA_TRY(h, cudaSetDevice(h->device));
-        const size_t bytes = (size_t)h->n * h->dc.na * h->dc.history * 6 * 4;
-        CUDA_TRY(h, cudaMalloc(&h->d_obsw, bytes));
-        CUDA_TRY(h, cudaMemset(h->d_obsw, 0, bytes));
-        h->obsw_valid = false;
+        CUDA_TRY(h, cudaMalloc(&h->d_obsm, (size_t)h->n * per_env * 4));
+        h->obsm_valid = false;
     }
-    *d_window = h->d_obsw;
+    if (!h->obsm_valid) {                          // (re)build from the fp64 history ring: state after a push at q = H - 1
+        CUDA_TRY(h, launch_obsm_rebuild(p, h->d_obsm, st));
+        h->launches++;
+        h->obs_q = H - 1; h->obsm_valid = true;
+    }
+    if (push) {
+        h->obs_q = (h->obs_q + 1) % H;
+        CUDA_TRY(h, launch_obs_push(p, h->d_obsm, h->obs_q, h->grid_obs, st));
+        h->launches++;
+    }
+    *d_view = h->d_obsm + (int64_t)(h->obs_q + 1) * 6;        // slots q+1 .. q+H: oldest .. newest
+    if (env_pitch) *env_pitch = per_env;
+    if (agent_pitch) *agent_pitch = (int64_t)2 * H * 6;
     return FP_OK;
 }
 

@@ -357,46 +357,29 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
     }
 }
 
-// In-place variant for the rollout loop (one pushing fp32 get_obs per step, model.py:223): the
-// window the previous call returned IS the state -- obsw[N][na][H*6] fp32, handle-owned -- and a push
-// shifts every agent's row by one 6-vector and appends the current one: 2880 B read + 2880 B written
-// per env with coalesced 8-byte accesses (a 6-float shift keeps float2 alignment), instead of
-// re-materialising the window from the fp64 ring with scattered reads.  The ring is still pushed
-// (it stays the source of truth for fp64 / non-pushing / out-of-place reads).  cnt == 0 (first push
-// after a reset) ignores the old window: zero padding in front (:393-396).
-constexpr int OBS_SHIFT_IT = 12;                   // 32 * 12 float2 >= na * H * 3 for na <= 5, H <= 25
-__global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_shift(const ObsParams prm, float* __restrict__ obsw) {
-    __shared__ float s_cur[WARPS_PER_CTA][32];
+// Mirror ring for the rollout loop (one pushing fp32 get_obs per step, model.py:223).
+// obsm[N][na][2H][6] fp32: every pushed 6-vector is written TWICE, at slot q and at slot q + H, so
+// that the last H entries are always the contiguous run of slots q+1 .. q+H -- the observation
+// window [oldest .. newest] is a strided VIEW of this buffer (agent pitch 2H*6 floats) and a push
+// costs 2 x 24 bytes per agent instead of re-writing the whole 576-byte row.  All envs push on
+// every get_obs call, so q is one number for the whole batch; a reset zeroes the ring of the
+// envs it resets (k_obsm_clear), which restarts their zero padding (:393-396).  The fp64 history
+// ring is still pushed: it stays the source of truth for fp64 / non-pushing / out-of-place reads.
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm, float* __restrict__ obsm, int q) {
     const DevCfg& c = prm.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int na = c.na, H = c.history, nl = c.nl;
-    const int W2 = H * 3, tot = na * W2;           // float2 units per agent row / per env
     const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
     for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
-        float2* w = reinterpret_cast<float2*>(obsw) + e * (int64_t)tot;
-        // 1. the old window, shifted by one entry (independent of everything below: issued first)
-        float2 v[OBS_SHIFT_IT];
-        {
-            int i = 0, j = lane;
-            while (j >= W2) { j -= W2; ++i; }
-#pragma unroll
-            for (int it = 0; it < OBS_SHIFT_IT; ++it) {
-                const int idx = lane + 32 * it;
-                v[it] = (idx < tot && j < W2 - 3) ? w[idx + 3] : make_float2(0.f, 0.f);
-                j += 32;
-                while (j >= W2) { j -= W2; ++i; }
-            }
-        }
-        // 2. the current 6-vector per agent (:376-384): lanes 0 .. 6*na-1; ring push
         uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
         const uint64_t tm = rec[FP_REC_TIME], hh = rec[FP_REC_HIST];
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
         const int32_t cnt = (int32_t)(uint32_t)hh;
         const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);   // row currently loaded (Q1)
-        double cur = 0.0;
-        if (lane < 6 * na) {
+        if (lane < 6 * na) {                       // current 6-vector per agent (:376-384)
             const int i = lane / 6, f = lane - 6 * i;
             const int col = prm.agent_col[i];
+            double cur;
             if (f == 0) cur = __ldg(prm.P + row * nl + col);
             else if (f == 1) cur = __ldg(prm.Q + row * nl + col);
             else if (f == 2) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + i);
@@ -404,27 +387,41 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_shift(const ObsParams pr
             else if (f == 4) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
             else cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
             prm.hist[e * (int64_t)(na * H * 6) + (i * H + cnt % H) * 6 + f] = cur;
-        }
-        s_cur[warp][lane] = (float)cur;
-        __syncwarp();                              // every load of the old window has landed
-        // 3. the new window, in place
-        {
-            int i = 0, j = lane;
-            while (j >= W2) { j -= W2; ++i; }
-#pragma unroll
-            for (int it = 0; it < OBS_SHIFT_IT; ++it) {
-                const int idx = lane + 32 * it;
-                if (idx < tot) {
-                    float2 x = (cnt > 0) ? v[it] : make_float2(0.f, 0.f);
-                    if (j >= W2 - 3) { const int k = i * 6 + 2 * (j - (W2 - 3)); x = make_float2(s_cur[warp][k], s_cur[warp][k + 1]); }
-                    w[idx] = x;
-                }
-                j += 32;
-                while (j >= W2) { j -= W2; ++i; }
-            }
+            float* ring = obsm + (e * na + i) * (int64_t)(2 * H * 6);
+            ring[q * 6 + f] = (float)cur;
+            ring[(q + H) * 6 + f] = (float)cur;
         }
         __syncwarp();
         if (lane == 0) rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
+    }
+}
+
+// Zero the mirror ring of the envs a reset touches (mask == nullptr: all).
+__global__ void k_obsm_clear(float4* __restrict__ obsm, const uint8_t* __restrict__ mask, int64_t n, int per_env4) {
+    const int64_t total = n * per_env4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / per_env4;
+        if (mask == nullptr || mask[e] != 0) obsm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// Rebuild the mirror ring from the fp64 history ring (after pushes that went through another path):
+// window slot s (oldest first) of every agent lands at ring slots s and s + H, i.e. the state after a
+// push at q = H - 1.
+__global__ void k_obsm_rebuild(const ObsParams prm, float* __restrict__ obsm) {
+    const DevCfg& c = prm.c;
+    const int na = c.na, H = c.history;
+    const int per_env = na * H * 6;
+    const int64_t total = prm.n * (int64_t)per_env;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / per_env;
+        const int r = (int)(i - e * per_env), a = r / (H * 6), r2 = r - a * (H * 6), sl = r2 / 6, f = r2 - 6 * sl;
+        const int32_t cnt = (int32_t)(uint32_t)prm.rec[e * FP_REC_STRIDE + FP_REC_HIST];
+        const int k = cnt - H + sl;                // push index of window slot sl
+        const float x = (k < 0) ? 0.f : (float)prm.hist[e * (int64_t)per_env + (a * H + (k % H)) * 6 + f];
+        float* ring = obsm + (e * na + a) * (int64_t)(2 * H * 6);
+        ring[sl * 6 + f] = x;
+        ring[(sl + H) * 6 + f] = x;
     }
 }
 
@@ -506,10 +503,21 @@ cudaError_t launch_obs(const ObsParams& prm, int f64, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
-int obs_shift_supported(int na, int history) { return na * history * 3 <= 32 * OBS_SHIFT_IT; }
+cudaError_t launch_obs_push(const ObsParams& prm, float* obsm, int q, int grid, cudaStream_t st) {
+    k_obs_push<<<grid, FP_CTA_THREADS, 0, st>>>(prm, obsm, q);
+    return cudaGetLastError();
+}
 
-cudaError_t launch_obs_shift(const ObsParams& prm, float* obsw, int grid, cudaStream_t st) {
-    k_obs_shift<<<grid, FP_CTA_THREADS, 0, st>>>(prm, obsw);
+cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int floats_per_env, cudaStream_t st) {
+    const int per_env4 = floats_per_env / 4;                     // 2 * H * 6 * na floats: a multiple of 4
+    const int64_t total = n * per_env4;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_obsm_clear<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(obsm), mask, n, per_env4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st) {
+    k_obsm_rebuild<<<148 * 16, 256, 0, st>>>(prm, obsm);
     return cudaGetLastError();
 }
 

@@ -84,8 +84,9 @@ cudaError_t launch_env(int mode, const EnvParams& prm, int grid, cudaStream_t st
 cudaError_t launch_power_flow(const PfParams& prm, int grid, cudaStream_t st);
 cudaError_t launch_obs(const ObsParams& prm, int f64, int grid, cudaStream_t st);
 cudaError_t launch_state(const ObsParams& prm, int f64, int grid, cudaStream_t st);
-cudaError_t launch_obs_shift(const ObsParams& prm, float* obsw, int grid, cudaStream_t st);
-int obs_shift_supported(int na, int history);
+cudaError_t launch_obs_push(const ObsParams& prm, float* obsm, int q, int grid, cudaStream_t st);
+cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int floats_per_env, cudaStream_t st);
+cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st);
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st);
 cudaError_t launch_pack_pvp(const double* pv, const double* price, int na, int64_t T, double* pvp,
                             cudaStream_t st);

@@ -83,7 +83,7 @@ class BatchedFlexProvisionEnv:
         self._views = None
         self._inject = None
         self._host = None
-        self._obsw = None
+        self._obs_views = {}
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -301,23 +301,27 @@ class BatchedFlexProvisionEnv:
         return hb["reward"].numpy(), hb["done"].numpy().astype(bool), info
 
     # ------------------------------------------------------------------ observations
-    def get_obs(self, push=True, dtype=torch.float32):
+    def get_obs(self, push=True, dtype=torch.float32, contiguous=False):
         """Replaces get_obs() (:370-403).  push=True reproduces its history side effect (Q7).
 
         The default call (pushing, fp32 -- what the rollout loop does once per step, model.py:223) returns a
-        view of the handle-owned window, which the library updates IN PLACE (shift by one entry + append):
-        treat it as read-only; it is valid until the next pushing call.  push=False and fp64 reads go
-        through their own buffers."""
-        if push and dtype == torch.float32:
-            if self._obsw is None:
-                p = C.c_void_p()
-                self._check(self._lib.fp_obs_window(self._h, C.byref(p)), "fp_obs_window")
-                n = self.n_envs * self.n_agents * self.obs_size
-                holder = _ExternalCudaBuffer(p.value, n * 4, self.device.index or 0)
-                self._obsw = torch.as_tensor(holder, device=self.device).view(torch.float32).view(
-                    self.n_envs, self.n_agents, self.obs_size)
-            self._check(self._lib.fp_get_obs(self._h, _ptr(self._obsw), _lib.FP_F32, 1, _stream()), "fp_get_obs")
-            return self._obsw
+        strided VIEW [N, na, 6*history] of the handle's mirror ring (fp_get_obs_view): the push writes 48
+        bytes per agent and nothing is re-materialised.  The view is read-only, valid until the next pushing
+        call, contiguous along the last dimension and mergeable over the first two (`.view(N * na, -1)`
+        works; use `.contiguous()` or contiguous=True for a packed copy).  push=False, fp64 and
+        contiguous=True go through their own buffers."""
+        if push and dtype == torch.float32 and not contiguous:
+            p, ep, ap = C.c_void_p(), C.c_int64(), C.c_int64()
+            self._check(self._lib.fp_get_obs_view(self._h, 1, C.byref(p), C.byref(ep), C.byref(ap), _stream()),
+                        "fp_get_obs_view")
+            view = self._obs_views.get(p.value)                   # one cached tensor per ring position
+            if view is None:
+                span = (self.n_envs - 1) * ep.value + (self.n_agents - 1) * ap.value + self.obs_size
+                holder = _ExternalCudaBuffer(p.value, span * 4, self.device.index or 0)
+                flat = torch.as_tensor(holder, device=self.device).view(torch.float32)
+                view = torch.as_strided(flat, (self.n_envs, self.n_agents, self.obs_size), (ep.value, ap.value, 1))
+                self._obs_views[p.value] = view
+            return view
         buf = self._obs.get(dtype)
         if buf is None:
             buf = torch.empty(self.n_envs, self.n_agents, self.obs_size, dtype=dtype, device=self.device)
