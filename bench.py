@@ -311,7 +311,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(); e0.record(stream)
         for k in range(60):
-            env.step(acts[k % n_act], want_info=False); env.get_obs()
+            env.step(acts[k % n_act], want_info=False, return_obs=True)
         e1.record(stream); barrier()
         obs_extra = E * world * 60 / (e0.elapsed_time(e1) * 1e-3)
 

@@ -43,8 +43,8 @@ def main():
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for t in range(args.steps):
         action = torch.tanh(obs.view(-1, env.obs_size) @ Wp) + noise[t % 8]
-        reward, done, info = env.step(action, translate=True, want_info=False)   # translate_action (util.py:121-129) fused
-        obs = env.get_obs()                                            # pushes the history (quirk Q7), in place
+        # translate_action (util.py:121-129) and the pushing get_obs (quirk Q7) are fused into the step kernel
+        reward, done, info, obs = env.step(action, translate=True, want_info=False, return_obs=True)
         if (t + 1) % (env.episode_limit - 1) == 0:                     # every env of the batch ends after 95 steps (Q1):
             env.reset(mask=done.to(torch.uint8), return_obs=False)     # auto-reset the finished ones (Philox streams)
             obs = env.get_obs()

@@ -199,6 +199,13 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream);
  * instead makes the next view call rebuild the ring from the fp64 history (correct, one slower call). */
 int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream);
 
+/* fp_step followed by fp_get_obs_view(push = 1) -- the pair the rollout loop issues every step
+ * (madrl/models/model.py:220-223) -- with the same results.  With the thread variant and no mask the
+ * observation push is fused into the step kernel (one launch); otherwise it is the two calls. */
+int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done,
+                double* d_info, const uint8_t* d_mask, float** d_view, int64_t* env_pitch,
+                int64_t* agent_pitch, void* stream);
+
 /* Replaces get_state() (:358-368): out[N][2*n_bus + na + n_bus + 1 + na]. */
 int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream);
 

@@ -36,7 +36,7 @@ struct FpHandle {
     int32_t start_range = 0;
     // device buffers
     DevTopo* d_topo = nullptr;
-    double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr, *d_PQD = nullptr;
+    double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr, *d_PQD = nullptr, *d_OBS = nullptr;
     uint64_t* d_rec = nullptr;
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
     // fp32 mirror ring of the observation history (fp_get_obs_view): [N][na][2H][6], last written slot, validity
@@ -52,6 +52,7 @@ struct FpHandle {
     int grid_step = 0, grid_reset = 0, grid_pf = 0, grid_obs = 0;
     cudaStream_t host_streams[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
     cudaEvent_t host_ev_in = nullptr, host_ev_out[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    int fuse_obs = 0;            // set around the fp_step of fp_step_obs: the step kernel pushes the observation
     int host_chunks = 0;         // 0 = not decided yet (FLEXGPU_HOST_CHUNKS or the default)
     // the chunk pipeline of fp_step_host as instantiated CUDA graphs, one per set of (pinned) host
     // buffers: one launch per step instead of five API calls per chunk
@@ -296,7 +297,7 @@ int fp_destroy(FpHandle* h) {
     if (!h) return FP_OK;
     cudaSetDevice(h->device);
     predictor_free(&h->pred);
-    cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
+    cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD); cudaFree(h->d_OBS);
     cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsm);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
     cudaFree(h->d_act_stage); cudaFree(h->d_act_xlat); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
@@ -325,8 +326,8 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
     const int64_t need = (int64_t)h->cfg.episode_limit + h->cfg.history + 1;
     if (T < need) return fail(h, FP_EINVAL, "fp_load_profiles: fewer rows than one episode slice");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD);
-    h->d_P = h->d_Q = h->d_PVP = h->d_PQD = nullptr;
+    cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD); cudaFree(h->d_OBS);
+    h->d_P = h->d_Q = h->d_PVP = h->d_PQD = h->d_OBS = nullptr;
     double *d_pv = nullptr, *d_price = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->d_P, (size_t)T * nl * 8));
     CUDA_TRY(h, cudaMalloc(&h->d_Q, (size_t)T * nl * 8));
@@ -338,6 +339,9 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
     CUDA_TRY(h, cudaMemcpy(d_pv, h_PV, (size_t)T * na * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(d_price, h_price, (size_t)T * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(h, launch_pack_pvp(d_pv, d_price, na, T, h->d_PVP, 0));
+    h->launches++;
+    CUDA_TRY(h, cudaMalloc(&h->d_OBS, (size_t)T * FP_OBS_STRIDE * 8));
+    CUDA_TRY(h, launch_pack_obsrow(h->d_P, h->d_Q, h->d_PVP, h->topo.agent_col, na, nl, T, h->d_OBS, 0));
     h->launches++;
     if (h->variant == FP_VARIANT_THREAD && !h->pair) {   // (p, q) pairs in DFS lane order for the thread kernels
         CUDA_TRY(h, cudaMalloc(&h->d_PQD, (size_t)T * nl * 16));
@@ -354,7 +358,7 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
 static void fill_env_params(FpHandle* h, EnvParams& p) {
     std::memset(&p, 0, sizeof(p));
     p.c = h->dc; p.topo = h->d_topo; p.n = h->n;
-    p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP; p.PQD = h->d_PQD;
+    p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP; p.PQD = h->d_PQD; p.OBSROW = h->d_OBS;
     p.rec = h->d_rec; p.V = h->d_V; p.setp = h->d_setp;
     if (h->keep_flows) { p.pfl = h->d_pfl; p.qfl = h->d_qfl; p.isq = h->d_isq; }
     p.inject = h->d_inject;
@@ -445,6 +449,7 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     }
     p.reward = d_reward; p.done = d_done; p.info = d_info; p.mask = d_mask;
     p.stats_partial = h->d_stats_partial;
+    if (h->fuse_obs) { p.obs_push = 1; p.obs_q = h->obs_q; p.hist = h->d_hist; p.obsm = h->d_obsm; }
     CUDA_TRY(h, launch_env_any(h, MODE_STEP, p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
@@ -616,7 +621,7 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
 
 static void fill_obs_params(FpHandle* h, ObsParams& p, void* out, int push) {
     std::memset(&p, 0, sizeof(p));
-    p.c = h->dc; p.n = h->n; p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP;
+    p.c = h->dc; p.n = h->n; p.P = h->d_P; p.Q = h->d_Q; p.PVP = h->d_PVP; p.OBSROW = h->d_OBS;
     p.rec = h->d_rec; p.V = h->d_V; p.hist = h->d_hist;
     for (int i = 0; i < 8; ++i) p.agent_col[i] = h->topo.agent_col[i];
     p.out = out; p.push = push;
@@ -658,6 +663,28 @@ int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, i
     *d_view = h->d_obsm + (int64_t)(h->obs_q + 1) * 6;        // slots q+1 .. q+H: oldest .. newest
     if (env_pitch) *env_pitch = per_env;
     if (agent_pitch) *agent_pitch = (int64_t)2 * H * 6;
+    return FP_OK;
+}
+
+/* step + the pushing get_obs that follows it in the rollout loop, as ONE launch where the kernel supports it */
+int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done, double* d_info,
+                const uint8_t* d_mask, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream) {
+    if (!h || !d_view) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_obs: call fp_load_profiles first");
+    const bool fuse = (h->variant == FP_VARIANT_THREAD) && !h->pair && d_mask == nullptr;
+    if (!fuse) {                                   // other variants / masked steps: two launches, same result
+        int rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, d_mask, stream);
+        if (rc != FP_OK) return rc;
+        return fp_get_obs_view(h, 1, d_view, env_pitch, agent_pitch, stream);
+    }
+    int rc = fp_get_obs_view(h, 0, d_view, env_pitch, agent_pitch, stream);   // allocates / rebuilds the mirror ring if needed
+    if (rc != FP_OK) return rc;
+    h->obs_q = (h->obs_q + 1) % h->dc.history;
+    h->fuse_obs = 1;
+    rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, nullptr, stream);
+    h->fuse_obs = 0;
+    if (rc != FP_OK) return rc;
+    *d_view = h->d_obsm + (int64_t)(h->obs_q + 1) * 6;
     return FP_OK;
 }
 

@@ -376,16 +376,14 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
         const int32_t cnt = (int32_t)(uint32_t)hh;
         const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);   // row currently loaded (Q1)
-        if (lane < 6 * na) {                       // current 6-vector per agent (:376-384)
-            const int i = lane / 6, f = lane - 6 * i;
-            const int col = prm.agent_col[i];
-            double cur;
-            if (f == 0) cur = __ldg(prm.P + row * nl + col);
-            else if (f == 1) cur = __ldg(prm.Q + row * nl + col);
-            else if (f == 2) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + i);
-            else if (f == 3) cur = prm.V[e * c.nb + col + 1];
-            else if (f == 4) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
-            else cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
+        // the packed observation row (P, Q at the agent buses, PV, price): one coalesced 128-byte read
+        const double orow = (lane < FP_OBS_STRIDE) ? __ldg(prm.OBSROW + row * FP_OBS_STRIDE + lane) : 0.0;
+        const int i = lane / 6, f = lane - 6 * i;  // current 6-vector per agent (:376-384): lanes 0 .. 6*na-1
+        const int src = (f == 0) ? FP_OBS_P + i : (f == 1) ? FP_OBS_Q + i : (f == 2) ? FP_OBS_PV + i : FP_OBS_PRICE;
+        double cur = __shfl_sync(FULL, orow, src & 15);
+        if (lane < 6 * na) {
+            if (f == 3) cur = prm.V[e * c.nb + prm.agent_col[i] + 1];
+            else if (f == 5) cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
             prm.hist[e * (int64_t)(na * H * 6) + (i * H + cnt % H) * 6 + f] = cur;
             float* ring = obsm + (e * na + i) * (int64_t)(2 * H * 6);
             ring[q * 6 + f] = (float)cur;
@@ -471,6 +469,21 @@ __global__ void k_translate_actions(const float* __restrict__ in, float* __restr
     if (i < n) out[i] = translate_action_f32(in[i], lo, hi, span);
 }
 
+struct AgentCols { int32_t col[8]; };
+__global__ void k_pack_obsrow(const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ pvp,
+                              const AgentCols ac, int na, int nl, int64_t T, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * FP_OBS_STRIDE) return;
+    const int64_t t = i / FP_OBS_STRIDE;
+    const int f = (int)(i - t * FP_OBS_STRIDE);
+    double x = 0.0;
+    if (f < FP_OBS_Q) { if (f < na) x = P[t * nl + ac.col[f]]; }
+    else if (f < FP_OBS_PV) { if (f - FP_OBS_Q < na) x = Q[t * nl + ac.col[f - FP_OBS_Q]]; }
+    else if (f < FP_OBS_PRICE) { if (f - FP_OBS_PV < na) x = pvp[t * FP_PVP_STRIDE + f - FP_OBS_PV]; }
+    else x = pvp[t * FP_PVP_STRIDE + FP_PVP_PRICE];
+    out[i] = x;
+}
+
 __global__ void k_pack_pvp(const double* __restrict__ pv, const double* __restrict__ price, int na,
                            int64_t T, double* __restrict__ pvp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -529,6 +542,15 @@ cudaError_t launch_state(const ObsParams& prm, int f64, int grid, cudaStream_t s
 
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st) {
     k_stats_fold<<<1, 32 * FP_NSTATS, 0, st>>>(partial, n_blocks, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_obsrow(const double* P, const double* Q, const double* pvp, const int32_t* agent_col, int na, int nl,
+                               int64_t T, double* out, cudaStream_t st) {
+    AgentCols ac;
+    for (int i = 0; i < 8; ++i) ac.col[i] = agent_col[i];
+    const int64_t n = T * FP_OBS_STRIDE;
+    k_pack_obsrow<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, Q, pvp, ac, na, nl, T, out);
     return cudaGetLastError();
 }
 

@@ -6,6 +6,11 @@
 #define FP_CTA_THREADS 256
 #define FP_PVP_STRIDE 8        // packed row: PV[0..na-1], price at slot 5, zero padding (64 B)
 #define FP_PVP_PRICE 5
+#define FP_OBS_STRIDE 16       // packed observation row: P[0..4], Q[5..9] at the agent buses, PV[10..14], price[15]
+#define FP_OBS_P 0
+#define FP_OBS_Q 5
+#define FP_OBS_PV 10
+#define FP_OBS_PRICE 15
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_PF = 2 };
 
@@ -18,6 +23,11 @@ struct EnvParams {
     // thread kernels: the same load rows as (p, q) pairs in DFS lane order, [T][nl][2] -- one
     // contiguous 16*nl-byte row per (env, step), fetched with a single bulk copy
     const double* PQD;
+    // what get_obs reads per row, packed: P and Q at the agent buses, PV, price -- one 128-byte row
+    const double* OBSROW;
+    // fused observation push of step(..., return_obs) (thread kernels): fp64 history ring, fp32 mirror ring,
+    // ring slot of this push (obs_push == 0: off)
+    double* hist; float* obsm; int32_t obs_push; int32_t obs_q;
     // per-env state
     uint64_t* rec; double* V; double* setp;
     double* pfl; double* qfl; double* isq;       // optional line-flow dump (nullptr = off)
@@ -46,6 +56,7 @@ struct ObsParams {
     DevCfg c;
     int64_t n;
     const double* P; const double* Q; const double* PVP;
+    const double* OBSROW;                         // [T][16]: P, Q at the agent buses, PV, price (see FP_OBS_*)
     uint64_t* rec; const double* V; double* hist;
     int32_t agent_col[8];
     void* out; int32_t push;
@@ -88,6 +99,8 @@ cudaError_t launch_obs_push(const ObsParams& prm, float* obsm, int q, int grid, 
 cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int floats_per_env, cudaStream_t st);
 cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st);
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st);
+cudaError_t launch_pack_obsrow(const double* P, const double* Q, const double* pvp, const int32_t* agent_col, int na, int nl,
+                               int64_t T, double* out, cudaStream_t st);
 cudaError_t launch_pack_pvp(const double* pv, const double* price, int na, int64_t T, double* pvp,
                             cudaStream_t st);
 int max_resident_grid(int mode);

@@ -268,11 +268,18 @@ class BatchedFlexProvisionEnv:
             raise ValueError("actions must have n_envs * n_agents * 4 elements")         # :260
         m = self._dev(mask, torch.uint8)
         dt = _lib.FP_F32_POLICY if translate else (_lib.FP_F64 if actions.dtype == torch.float64 else _lib.FP_F32)
-        self._check(self._lib.fp_step(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
-                                      _ptr(self._info) if want_info else None, _ptr(m), _stream()), "fp_step")
+        if return_obs:                               # step + pushing get_obs in one launch (fp_step_obs)
+            p, ep, ap = C.c_void_p(), C.c_int64(), C.c_int64()
+            self._check(self._lib.fp_step_obs(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
+                                              _ptr(self._info) if want_info else None, _ptr(m), C.byref(p), C.byref(ep),
+                                              C.byref(ap), _stream()), "fp_step_obs")
+            obs = self._obs_view(p.value, ep.value, ap.value)
+        else:
+            self._check(self._lib.fp_step(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
+                                          _ptr(self._info) if want_info else None, _ptr(m), _stream()), "fp_step")
         info = {k: self._info[:, i] for i, k in enumerate(_lib.INFO_KEYS)} if want_info else {}
         if return_obs:
-            return self._reward, self._done, info, self.get_obs()
+            return self._reward, self._done, info, obs
         return self._reward, self._done, info
 
     def step_host(self, actions, want_info=False, translate=False):
@@ -314,14 +321,7 @@ class BatchedFlexProvisionEnv:
             p, ep, ap = C.c_void_p(), C.c_int64(), C.c_int64()
             self._check(self._lib.fp_get_obs_view(self._h, 1, C.byref(p), C.byref(ep), C.byref(ap), _stream()),
                         "fp_get_obs_view")
-            view = self._obs_views.get(p.value)                   # one cached tensor per ring position
-            if view is None:
-                span = (self.n_envs - 1) * ep.value + (self.n_agents - 1) * ap.value + self.obs_size
-                holder = _ExternalCudaBuffer(p.value, span * 4, self.device.index or 0)
-                flat = torch.as_tensor(holder, device=self.device).view(torch.float32)
-                view = torch.as_strided(flat, (self.n_envs, self.n_agents, self.obs_size), (ep.value, ap.value, 1))
-                self._obs_views[p.value] = view
-            return view
+            return self._obs_view(p.value, ep.value, ap.value)
         buf = self._obs.get(dtype)
         if buf is None:
             buf = torch.empty(self.n_envs, self.n_agents, self.obs_size, dtype=dtype, device=self.device)
@@ -329,6 +329,16 @@ class BatchedFlexProvisionEnv:
         dt = _lib.FP_F64 if dtype == torch.float64 else _lib.FP_F32
         self._check(self._lib.fp_get_obs(self._h, _ptr(buf), dt, 1 if push else 0, _stream()), "fp_get_obs")
         return buf
+
+    def _obs_view(self, ptr, env_pitch, agent_pitch):
+        view = self._obs_views.get(ptr)                              # one cached tensor per ring position
+        if view is None:
+            span = (self.n_envs - 1) * env_pitch + (self.n_agents - 1) * agent_pitch + self.obs_size
+            holder = _ExternalCudaBuffer(ptr, span * 4, self.device.index or 0)
+            flat = torch.as_tensor(holder, device=self.device).view(torch.float32)
+            view = torch.as_strided(flat, (self.n_envs, self.n_agents, self.obs_size), (env_pitch, agent_pitch, 1))
+            self._obs_views[ptr] = view
+        return view
 
     def get_state(self, dtype=torch.float32):
         """Replaces get_state() (:358-368)."""

@@ -23,3 +23,4 @@ print("step(want_info=False) us/call", round(t(lambda: env.step(a, want_info=Fal
 print("get_obs()             us/call", round(t(lambda: env.get_obs()), 1))
 print("get_state()           us/call", round(t(lambda: env.get_state()), 1))
 print("step+get_obs          us/call", round(t(lambda: (env.step(a, want_info=False), env.get_obs())), 1))
+print("step(return_obs=True)  us/call", round(t(lambda: env.step(a, want_info=False, return_obs=True)), 1))
