@@ -17,7 +17,7 @@
 #include "flex_kernels.cuh"
 #include "predictor.cuh"
 
-#define FP_HOST_CHUNKS 16     // fp_step_host can pipeline the batch in up to this many chunks (copy engines || SMs)
+#define FP_HOST_CHUNKS 4      // fp_step_host can pipeline the batch in up to this many chunks (copy engines || SMs)
 #define FP_HOST_STREAMS 3
 #define FP_HOST_CHUNKS_DEFAULT 4
 #define FP_HOST_GRAPHS 8
