@@ -189,14 +189,16 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
 int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream);
 
 /* get_obs() for the rollout loop (one pushing fp32 call per step, madrl/models/model.py:223) WITHOUT
- * re-materialising the window: the handle keeps a mirror ring [N][na][2*history][6] fp32 in which every
- * pushed 6-vector is stored twice, history slots apart, so the last `history` entries are always one
- * contiguous run.  push != 0 appends the current 6-vector of every agent (side effect of get_obs, quirk
- * Q7; 48 bytes per agent instead of the whole 576-byte row); *d_view then points at env 0 / agent 0 of
- * the window [oldest .. newest], element (e, i, k) at d_view[e * env_pitch + i * agent_pitch + k],
- * k < history*6, pitches in floats.  The view is read-only for the caller and valid until the next
- * pushing call.  Resets restart the zero padding of the envs they reset.  Pushing through fp_get_obs
- * instead makes the next view call rebuild the ring from the fp64 history (correct, one slower call). */
+ * re-materialising the window: the handle keeps a window ring [N][na][3*history][6] fp32 into which every
+ * push writes the agents' current 6-vectors once, at a slot that advances by one per push, so the last
+ * `history` entries are always one contiguous run (at the end of the ring they are copied back to its
+ * front, once every 2*history+1 pushes).  push != 0 appends the current 6-vector of every agent (side
+ * effect of get_obs, quirk Q7; 24 bytes per agent instead of the whole 576-byte row); *d_view then points
+ * at env 0 / agent 0 of the window [oldest .. newest], element (e, i, k) at
+ * d_view[e * env_pitch + i * agent_pitch + k], k < history*6, pitches in floats.  The view is read-only for
+ * the caller and valid until the next pushing call.  Resets restart the zero padding of the envs they
+ * reset.  Pushing through fp_get_obs instead makes the next view call rebuild the ring from the fp64
+ * history (correct, one slower call). */
 int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream);
 
 /* fp_step followed by fp_get_obs_view(push = 1) -- the pair the rollout loop issues every step

@@ -39,7 +39,7 @@ struct FpHandle {
     double *d_P = nullptr, *d_Q = nullptr, *d_PVP = nullptr, *d_PQD = nullptr, *d_OBS = nullptr;
     uint64_t* d_rec = nullptr;
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
-    // fp32 mirror ring of the observation history (fp_get_obs_view): [N][na][2H][6], last written slot, validity
+    // fp32 window ring of the observation history (fp_get_obs_view): [N][na][3H][6], last written slot, validity
     float* d_obsm = nullptr; int obs_q = 0; bool obsm_valid = false;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
@@ -406,7 +406,7 @@ int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const doub
     CUDA_TRY(h, launch_env_any(h, MODE_RESET, p, (cudaStream_t)stream));
     h->launches++;
     if (h->d_obsm && h->obsm_valid) {              // restart the zero padding of the reset envs' observation windows
-        CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 2 * h->dc.history * 6, (cudaStream_t)stream));
+        CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 3 * h->dc.history * 6, (cudaStream_t)stream));
         h->launches++;
     }
     return FP_OK;
@@ -421,7 +421,7 @@ int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_
     CUDA_TRY(h, launch_env_any(h, MODE_RESET, p, (cudaStream_t)stream));
     h->launches++;
     if (h->d_obsm && h->obsm_valid) {
-        CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 2 * h->dc.history * 6, (cudaStream_t)stream));
+        CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 3 * h->dc.history * 6, (cudaStream_t)stream));
         h->launches++;
     }
     return FP_OK;
@@ -634,7 +634,34 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
     CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
-    if (push) h->obsm_valid = false;               // the mirror ring missed this push: rebuilt on the next view
+    if (push) h->obsm_valid = false;               // the window ring missed this push: rebuilt on the next view
+    return FP_OK;
+}
+
+// Window ring bookkeeping: make the ring usable (allocate / rebuild) and, for a push, advance the write
+// slot (compacting at the end of the ring).  Returns the slot the push writes.
+static int obs_ring_prepare(FpHandle* h, bool push, cudaStream_t st) {
+    const int H = h->dc.history, na = h->dc.na;
+    const int64_t per_env = (int64_t)na * 3 * H * 6;
+    ObsParams p; fill_obs_params(h, p, nullptr, 1);
+    if (!h->d_obsm) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaMalloc(&h->d_obsm, (size_t)h->n * per_env * 4));
+        h->obsm_valid = false;
+    }
+    if (!h->obsm_valid) {                          // (re)build from the fp64 history ring: state after a push at w = H - 1
+        CUDA_TRY(h, launch_obsm_rebuild(p, h->d_obsm, st));
+        h->launches++;
+        h->obs_q = H - 1; h->obsm_valid = true;
+    }
+    if (push) {
+        if (h->obs_q == 3 * H - 1) {               // end of the ring: the last H-1 entries move to the front
+            CUDA_TRY(h, launch_obsm_compact(h->d_obsm, h->n * na, H, st));
+            h->launches++;
+            h->obs_q = H - 2;
+        }
+        h->obs_q += 1;
+    }
     return FP_OK;
 }
 
@@ -642,27 +669,17 @@ int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, i
     if (!h || !d_view) return FP_EINVAL;
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs_view: call fp_load_profiles first");
     const int H = h->dc.history, na = h->dc.na;
-    const int64_t per_env = (int64_t)na * 2 * H * 6;
     cudaStream_t st = (cudaStream_t)stream;
-    ObsParams p; fill_obs_params(h, p, nullptr, 1);
-    if (!h->d_obsm) {
-        CUDA_TRY(h, cudaSetDevice(h->device));
-        CUDA_TRY(h, cudaMalloc(&h->d_obsm, (size_t)h->n * per_env * 4));
-        h->obsm_valid = false;
-    }
-    if (!h->obsm_valid) {                          // (re)build from the fp64 history ring: state after a push at q = H - 1
-        CUDA_TRY(h, launch_obsm_rebuild(p, h->d_obsm, st));
-        h->launches++;
-        h->obs_q = H - 1; h->obsm_valid = true;
-    }
+    int rc = obs_ring_prepare(h, push != 0, st);
+    if (rc != FP_OK) return rc;
     if (push) {
-        h->obs_q = (h->obs_q + 1) % H;
+        ObsParams p; fill_obs_params(h, p, nullptr, 1);
         CUDA_TRY(h, launch_obs_push(p, h->d_obsm, h->obs_q, h->grid_obs, st));
         h->launches++;
     }
-    *d_view = h->d_obsm + (int64_t)(h->obs_q + 1) * 6;        // slots q+1 .. q+H: oldest .. newest
-    if (env_pitch) *env_pitch = per_env;
-    if (agent_pitch) *agent_pitch = (int64_t)2 * H * 6;
+    *d_view = h->d_obsm + (int64_t)(h->obs_q - H + 1) * 6;    // slots w-H+1 .. w: oldest .. newest
+    if (env_pitch) *env_pitch = (int64_t)na * 3 * H * 6;
+    if (agent_pitch) *agent_pitch = (int64_t)3 * H * 6;
     return FP_OK;
 }
 
@@ -677,14 +694,16 @@ int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_rew
         if (rc != FP_OK) return rc;
         return fp_get_obs_view(h, 1, d_view, env_pitch, agent_pitch, stream);
     }
-    int rc = fp_get_obs_view(h, 0, d_view, env_pitch, agent_pitch, stream);   // allocates / rebuilds the mirror ring if needed
+    int rc = obs_ring_prepare(h, true, (cudaStream_t)stream);
     if (rc != FP_OK) return rc;
-    h->obs_q = (h->obs_q + 1) % h->dc.history;
     h->fuse_obs = 1;
     rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, nullptr, stream);
     h->fuse_obs = 0;
     if (rc != FP_OK) return rc;
-    *d_view = h->d_obsm + (int64_t)(h->obs_q + 1) * 6;
+    const int H = h->dc.history, na = h->dc.na;
+    *d_view = h->d_obsm + (int64_t)(h->obs_q - H + 1) * 6;
+    if (env_pitch) *env_pitch = (int64_t)na * 3 * H * 6;
+    if (agent_pitch) *agent_pitch = (int64_t)3 * H * 6;
     return FP_OK;
 }
 

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_power_flow(const PfParams pr
 }
 
 // ------------------------------------------------------------------------ observations
-// History ring hist[N][na][H][6] fp64.  Pushing call k (0-based since reset) writes slot k % H.
+// History ring hist[N][H][na][6] fp64 (slot-major: one push is one contiguous 48*na-byte run per env).
+// Pushing call k (0-based since reset) writes slot k % H.
 template <typename OutT>
 __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
     __shared__ double s_cur[WARPS_PER_CTA][32];
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
             else if (f == 3) cur = prm.V[e * c.nb + col + 1];
             else if (f == 4) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
             else cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
-            if (prm.push) hist[(i * H + slot) * 6 + f] = cur;
+            if (prm.push) hist[(slot * na + i) * 6 + f] = cur;
         }
         s_cur[warp][lane] = cur;
         __syncwarp();
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
             double x;
             if (k < 0) x = 0.0;
             else if (k == cnt) x = s_cur[warp][i * 6 + f];
-            else x = hist[(i * H + (k % H)) * 6 + f];
+            else x = hist[((k % H) * na + i) * 6 + f];
             out[o] = (OutT)x;
         }
         __syncwarp();
@@ -357,18 +358,20 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
     }
 }
 
-// Mirror ring for the rollout loop (one pushing fp32 get_obs per step, model.py:223).
-// obsm[N][na][2H][6] fp32: every pushed 6-vector is written TWICE, at slot q and at slot q + H, so
-// that the last H entries are always the contiguous run of slots q+1 .. q+H -- the observation
-// window [oldest .. newest] is a strided VIEW of this buffer (agent pitch 2H*6 floats) and a push
-// costs 2 x 24 bytes per agent instead of re-writing the whole 576-byte row.  All envs push on
-// every get_obs call, so q is one number for the whole batch; a reset zeroes the ring of the
-// envs it resets (k_obsm_clear), which restarts their zero padding (:393-396).  The fp64 history
-// ring is still pushed: it stays the source of truth for fp64 / non-pushing / out-of-place reads.
-__global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm, float* __restrict__ obsm, int q) {
+// Window ring for the rollout loop (one pushing fp32 get_obs per step, model.py:223).
+// obsm[N][na][3H][6] fp32: every push writes the agents' 6-vectors ONCE, at slot w (w grows by one per
+// push), so the last H entries are the contiguous run of slots w-H+1 .. w and the observation window
+// [oldest .. newest] is a strided VIEW of this buffer (agent pitch 3H*6 floats): a push costs 24 bytes
+// per agent instead of re-writing the 576-byte row.  When w reaches the end of the ring the last H-1
+// entries are copied to its front (k_obsm_compact, once every 2H+1 pushes; the previous view, slots
+// 2H .. 3H-1, is not touched by it).  All envs push on every get_obs call, so w is one number for the
+// whole batch; a reset zeroes the ring of the envs it resets (k_obsm_clear), which restarts their zero
+// padding (:393-396).  The fp64 history ring is still pushed: it stays the source of truth for fp64 /
+// non-pushing / out-of-place reads.
+__global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm, float* __restrict__ obsm, int w) {
     const DevCfg& c = prm.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int na = c.na, H = c.history, nl = c.nl;
+    const int na = c.na, H = c.history;
     const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
     for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
         uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
@@ -384,28 +387,40 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm
         if (lane < 6 * na) {
             if (f == 3) cur = prm.V[e * c.nb + prm.agent_col[i] + 1];
             else if (f == 5) cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
-            prm.hist[e * (int64_t)(na * H * 6) + (i * H + cnt % H) * 6 + f] = cur;
-            float* ring = obsm + (e * na + i) * (int64_t)(2 * H * 6);
-            ring[q * 6 + f] = (float)cur;
-            ring[(q + H) * 6 + f] = (float)cur;
+            prm.hist[e * (int64_t)(na * H * 6) + ((cnt % H) * na + i) * 6 + f] = cur;       // lanes 0..6na-1: one contiguous run
+            obsm[(e * na + i) * (int64_t)(3 * H * 6) + w * 6 + f] = (float)cur;
         }
         __syncwarp();
         if (lane == 0) rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
     }
 }
 
-// Zero the mirror ring of the envs a reset touches (mask == nullptr: all).
-__global__ void k_obsm_clear(float4* __restrict__ obsm, const uint8_t* __restrict__ mask, int64_t n, int per_env4) {
-    const int64_t total = n * per_env4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = i / per_env4;
-        if (mask == nullptr || mask[e] != 0) obsm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+// Zero the window ring of the envs a reset touches (mask == nullptr: all): one warp per env, so an
+// env that is not reset costs one mask byte.
+__global__ void k_obsm_clear(float* __restrict__ obsm, const uint8_t* __restrict__ mask, int64_t n, int per_env) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
+        if (mask != nullptr && mask[e] == 0) continue;
+        float* wdw = obsm + e * per_env;
+        for (int i = lane; i < per_env; i += 32) wdw[i] = 0.f;
     }
 }
 
-// Rebuild the mirror ring from the fp64 history ring (after pushes that went through another path):
-// window slot s (oldest first) of every agent lands at ring slots s and s + H, i.e. the state after a
-// push at q = H - 1.
+// End of the ring: copy the last H-1 entries (slots 2H+1 .. 3H-1) of every agent row to slots 0 .. H-2.
+__global__ void k_obsm_compact(float* __restrict__ obsm, int64_t rows, int H) {
+    const int per = (H - 1) * 6;
+    const int64_t total = rows * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per;
+        const int k = (int)(i - r * per);
+        float* ring = obsm + r * (int64_t)(3 * H * 6);
+        ring[k] = ring[(2 * H + 1) * 6 + k];
+    }
+}
+
+// Rebuild the window ring from the fp64 history ring (after pushes that went through another path):
+// window slot s (oldest first) of every agent lands at ring slot s, i.e. the state after a push at w = H - 1.
 __global__ void k_obsm_rebuild(const ObsParams prm, float* __restrict__ obsm) {
     const DevCfg& c = prm.c;
     const int na = c.na, H = c.history;
@@ -416,10 +431,8 @@ __global__ void k_obsm_rebuild(const ObsParams prm, float* __restrict__ obsm) {
         const int r = (int)(i - e * per_env), a = r / (H * 6), r2 = r - a * (H * 6), sl = r2 / 6, f = r2 - 6 * sl;
         const int32_t cnt = (int32_t)(uint32_t)prm.rec[e * FP_REC_STRIDE + FP_REC_HIST];
         const int k = cnt - H + sl;                // push index of window slot sl
-        const float x = (k < 0) ? 0.f : (float)prm.hist[e * (int64_t)per_env + (a * H + (k % H)) * 6 + f];
-        float* ring = obsm + (e * na + a) * (int64_t)(2 * H * 6);
-        ring[sl * 6 + f] = x;
-        ring[(sl + H) * 6 + f] = x;
+        const float x = (k < 0) ? 0.f : (float)prm.hist[e * (int64_t)per_env + ((k % H) * na + a) * 6 + f];
+        obsm[(e * na + a) * (int64_t)(3 * H * 6) + sl * 6 + f] = x;
     }
 }
 
@@ -522,10 +535,14 @@ cudaError_t launch_obs_push(const ObsParams& prm, float* obsm, int q, int grid, 
 }
 
 cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int floats_per_env, cudaStream_t st) {
-    const int per_env4 = floats_per_env / 4;                     // 2 * H * 6 * na floats: a multiple of 4
-    const int64_t total = n * per_env4;
-    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    k_obsm_clear<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(obsm), mask, n, per_env4);
+    const int64_t ctas = (n + 7) / 8;
+    k_obsm_clear<<<(unsigned)(ctas < 148 * 8 ? ctas : 148 * 8), 256, 0, st>>>(obsm, mask, n, floats_per_env);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obsm_compact(float* obsm, int64_t rows, int H, cudaStream_t st) {
+    if (H < 2) return cudaSuccess;
+    k_obsm_compact<<<148 * 16, 256, 0, st>>>(obsm, rows, H);
     return cudaGetLastError();
 }
 

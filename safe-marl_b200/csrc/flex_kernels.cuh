@@ -98,6 +98,7 @@ cudaError_t launch_state(const ObsParams& prm, int f64, int grid, cudaStream_t s
 cudaError_t launch_obs_push(const ObsParams& prm, float* obsm, int q, int grid, cudaStream_t st);
 cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int floats_per_env, cudaStream_t st);
 cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st);
+cudaError_t launch_obsm_compact(float* obsm, int64_t rows, int H, cudaStream_t st);
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st);
 cudaError_t launch_pack_obsrow(const double* P, const double* Q, const double* pvp, const int32_t* agent_col, int na, int nl,
                                int64_t T, double* out, cudaStream_t st);

@@ -312,7 +312,7 @@ class BatchedFlexProvisionEnv:
         """Replaces get_obs() (:370-403).  push=True reproduces its history side effect (Q7).
 
         The default call (pushing, fp32 -- what the rollout loop does once per step, model.py:223) returns a
-        strided VIEW [N, na, 6*history] of the handle's mirror ring (fp_get_obs_view): the push writes 48
+        strided VIEW [N, na, 6*history] of the handle's window ring (fp_get_obs_view): the push writes 48
         bytes per agent and nothing is re-materialised.  The view is read-only, valid until the next pushing
         call, contiguous along the last dimension and mergeable over the first two (`.view(N * na, -1)`
         works; use `.contiguous()` or contiguous=True for a packed copy).  push=False, fp64 and
