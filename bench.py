@@ -308,6 +308,8 @@ def main():
     obs_extra = None
     if not args.no_obs:
         env.reset(return_obs=False)
+        for k in range(3):                                        # warm-up: allocates the observation window ring
+            env.step(acts[k % n_act], want_info=False, return_obs=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier(); e0.record(stream)
         for k in range(60):
