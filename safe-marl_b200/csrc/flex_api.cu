@@ -688,7 +688,8 @@ int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_rew
                 const uint8_t* d_mask, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream) {
     if (!h || !d_view) return FP_EINVAL;
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_obs: call fp_load_profiles first");
-    const bool fuse = (h->variant == FP_VARIANT_THREAD) && !h->pair && d_mask == nullptr;
+    // fused for the built-in feeder shape (the run-time-table kernels keep the two-launch form)
+    const bool fuse = (h->variant == FP_VARIANT_THREAD) && !h->pair && d_mask == nullptr && h->shape == SHAPE_IEEE33;
     if (!fuse) {                                   // other variants / masked steps: two launches, same result
         int rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, d_mask, stream);
         if (rc != FP_OK) return rc;
