@@ -94,6 +94,17 @@ def test_env_steps_bit_exact_vs_mirror(setup):
     assert np.array_equal(env.pf_iterations.cpu().numpy(), mb.iters)
     obs = env.get_obs(); state = env.get_state()
     assert obs.shape == (n, na, 6 * env.history) and state.shape == (n, 3 * 14 + 2 * na + 1)
+    # step(return_obs=True) on a run-time-table feeder (fewer agents: packed observation row, two-launch
+    # fallback of fp_step_obs) == step + get_obs, and the window ring agrees with the fp64 history ring
+    a = rng.normal(0.4, 0.5, (n, 4 * na))
+    want = env.get_obs(push=False, dtype=torch.float64)            # what the next push must NOT yet contain
+    r, d, info, o2 = env.step(torch.from_numpy(a), return_obs=True)
+    rr, dd, ii = mb.step(a)
+    assert np.array_equal(r.cpu().numpy(), rr)
+    cur = mb.current_obs()                                         # [n, na, 6] after the step
+    assert np.array_equal(o2[:, :, -6:].cpu().numpy(), cur.astype(np.float32))
+    assert torch.equal(o2[:, :, :-6], obs[:, :, 6:])               # shifted by one entry
+    assert torch.equal(env.get_obs(push=False, dtype=torch.float64)[:, :, :-6].float(), o2[:, :, 6:])
 
 
 def test_pair_variant_rejects_other_shapes(cuda, args):
