@@ -94,3 +94,22 @@ def test_translate_action_matches_reference_function():
     t = prep_obs(obs)
     assert t.dtype == torch.float32 and tuple(t.shape) == (5, 144)
     assert prep_obs(torch.zeros(7, 5, 144, dtype=torch.float64)).shape == (7, 5, 144)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver launches next to the GPU arm) needs no GPU:
+    one JSON line with the contract's keys, the same metric / unit / workload naming as the GPU arm."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--envs-per-gpu", "2048", "--rows", "3000"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
+    assert line["metric"] == "33-bus env-steps/sec (incl. power flow)" and line["value"] > 0
+    assert line["config"]["workload"].startswith("fused_env_step_2048_envs_per_gpu")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
