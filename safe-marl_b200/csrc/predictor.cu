@@ -8,23 +8,30 @@
 //       (madrl/models/safemaddpg.py:205-229,264-277: 1000 * sum(max(0, v_min - V) + max(0, V - v_max)))
 //   fp_replay_*                      replace TransReplayBuffer (utils/replay_buffer.py:3-30)
 //
-// Kernel k_predict (one persistent CTA of 128 threads per SM, one 128-env tile per iteration):
-//   1. TMA: `cp.async.bulk` brings the tile's X rows (128 x 66 fp32 = 33 792 contiguous bytes)
-//      into a double-buffered staging area, completion on an mbarrier; the copy of tile i+1
-//      overlaps the MMA + epilogue of tile i.
-//   2. 3xTF32 split: thread t owns row t; x = hi + lo with hi exactly representable in TF32
-//      (low 13 mantissa bits cleared) and lo = x - hi (exact).  hi and lo are written in the
-//      UMMA K-major no-swizzle ("interleave") layout: core matrices of 8 rows x 16 bytes,
-//      [k-chunk][row][4 floats], SBO = 128 B, LBO = rows * 16 B.
-//   3. tcgen05.mma (kind::tf32, M=128, N=48, K=8 per instruction; 9 k-steps x 3 products
-//      hi*hi + lo*hi + hi*lo), issued by ONE thread, accumulating fp32 in TMEM; completion via
-//      tcgen05.commit -> mbarrier.  The weights (hi and lo parts, same layout) sit in shared
-//      memory for the lifetime of the CTA.
-//   4. Epilogue: tcgen05.ld (32x32b.x16) hands every thread the 48 accumulators of its env;
-//      add the bias, evaluate the slack penalty in fp64, stage Vhat in shared memory and store
-//      coalesced rows into the replay ring at (pos + env) mod capacity (and/or a dense output).
-// By shape (K = 66, N = 33: ~11 flop/B) the op is HBM-bound; the tensor pipe is nearly idle by
-// construction and the point of tcgen05 here is to take the contraction off the fp32 pipe.
+// Kernel k_predict: one persistent CTA per SM, 128-env tiles, WARP-SPECIALISED so that the phases of
+// consecutive tiles overlap (the op is HBM-bound by shape -- K = 66, N = 33: ~11 flop/B -- and the job
+// of the kernel is to keep three tiles of X in flight per SM while the rest hides underneath):
+//   producer warps 0-7 (two threads per env row of the tile: K halves)
+//     1. TMA: `cp.async.bulk` brings the tile's X rows (128 x 66 fp32 = 33 792 contiguous bytes) into
+//        one of THREE staging buffers, completion on an mbarrier; a buffer is refilled (three tiles
+//        ahead) as soon as the split below has read it.
+//     2. 3xTF32 split: x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits
+//        cleared) and lo = x - hi (exact), written in the UMMA K-major no-swizzle ("interleave")
+//        layout: core matrices of 8 rows x 16 bytes, [k-chunk][row][4 floats], SBO = 128 B,
+//        LBO = rows * 16 B.  The A buffers are single: the split of tile i+1 waits for the MMAs of
+//        tile i (their commit barrier), which is short against a tile's HBM time.
+//     3. tcgen05.mma (kind::tf32, M=128, N=48, K=8 per instruction; 9 k-steps x 3 products
+//        hi*hi + lo*hi + hi*lo), issued by ONE elected thread of warp 0, accumulating fp32 in one of TWO TMEM
+//        accumulators (2 x 64 columns); completion via tcgen05.commit -> mbarrier.  The weights (hi
+//        and lo parts, same layout) sit in shared memory for the lifetime of the CTA.
+//   epilogue warps 8-11 (thread t = env row t, TMEM lane quarter = warp % 4)
+//     4. tcgen05.ld (32x32b.x32 + .x1) hands every thread the 33 accumulators of its env and frees
+//        the accumulator for the tile after next; add the bias, evaluate the slack penalty in fp64,
+//        stage Vhat in shared memory and store coalesced rows into the replay ring at
+//        (pos + env) mod capacity (and/or a dense output).
+// The weights arrive by one bulk copy that overlaps the first X tiles (own mbarrier).
+// The two groups meet only through mbarriers (full[3], mma_done[2], tmem_free[2]) and synchronise
+// internally with named barriers; every wait is bounded (trap, never a hung GPU).
 #include <cmath>
 #include <cstring>
 
@@ -44,14 +51,16 @@ constexpr uint32_t A_BYTES = PRED_KC * PRED_M * 16;          // 36 864
 constexpr uint32_t B_BYTES = PRED_KC * PRED_N * 16;          // 13 824
 constexpr uint32_t STAGE_BYTES = PRED_M * N_IN * 4;          // 33 792
 constexpr uint32_t OFF_AHI = 0, OFF_ALO = OFF_AHI + A_BYTES, OFF_BHI = OFF_ALO + A_BYTES, OFF_BLO = OFF_BHI + B_BYTES;
-constexpr uint32_t OFF_STAGE = OFF_BLO + B_BYTES;            // two stages
-constexpr uint32_t OFF_OUT = OFF_STAGE + 2 * STAGE_BYTES;    // [128][33] fp32
-constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;     // 16 896 B: keeps OFF_PEN 8-byte aligned
-constexpr uint32_t OFF_PEN = OFF_BIAS + PRED_N * 4;          // [2][128] fp64 penalty partials (column halves)
-constexpr uint32_t OFF_BAR = OFF_PEN + 2 * PRED_M * 8;       // 3 mbarriers
-constexpr uint32_t OFF_TMEM = OFF_BAR + 3 * 8;
+constexpr int N_STAGES = 3;                                  // X tiles in flight per SM (3 x 33 KB covers the HBM latency)
+constexpr uint32_t OFF_STAGE = OFF_BLO + B_BYTES;
+constexpr uint32_t OFF_OUT = OFF_STAGE + N_STAGES * STAGE_BYTES;   // [128][33] fp32
+constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;
+constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[3], mma_done[2], tmem_free[2], weights
+constexpr uint32_t OFF_TMEM = OFF_BAR + 8 * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
-constexpr uint32_t TMEM_COLS = 64;                           // power of two >= 48
+constexpr uint32_t ACC_COLS = 64;                            // one accumulator: power of two >= 48
+constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                 // two accumulators
+static_assert(SMEM_BYTES <= 227 * 1024, "predictor tile buffers exceed the shared memory of one SM");
 
 struct PredParams {
     const float* X; int64_t n;
@@ -112,15 +121,31 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+template <int ID, int THREADS>
+__device__ __forceinline__ void group_sync() {               // named barrier of one warp group
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {                // one lane of a converged warp (lets ptxas keep the
+    uint32_t p;                                              // descriptors of the MMA on the uniform datapath)
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(p));
+    return p != 0u;
+}
 
-constexpr int PRED_THREADS = 2 * PRED_M;     // two threads per env row: K halves in the split, column halves in the epilogue
+constexpr int PROD_THREADS = 2 * PRED_M;     // warps 0-7: TMA + split (two threads per row) + MMA issue (warp 0)
+constexpr int PRED_THREADS = 3 * PRED_M;     // warps 8-11: epilogue
 
 __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -130,27 +155,28 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
     float* out = reinterpret_cast<float*>(smem + OFF_OUT);
     float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-    const uint32_t bar_full0 = smem_u32(smem + OFF_BAR), bar_mma = bar_full0 + 16;
-    double* pen_part = reinterpret_cast<double*>(smem + OFF_PEN);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & (PRED_M - 1), half = tid >> 7;               // env row of the tile, which half of the work
+    const uint32_t bar_full0 = smem_u32(smem + OFF_BAR), bar_mma0 = bar_full0 + 8 * N_STAGES, bar_free0 = bar_mma0 + 16,
+                   bar_w = bar_free0 + 16;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);   // warp-uniform for the compiler
+    const int row = tid & (PRED_M - 1);                                 // env row of the tile (both groups)
     const int64_t n_tiles = (prm.n + PRED_M - 1) / PRED_M;
 
     // ---- one-time setup: barriers, TMEM, weights, zero K padding
     if (tid == 0) {
-        mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1); mbar_init(bar_mma, 1);
+        for (int s = 0; s < N_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
+        mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1);
+        mbar_init(bar_free0, PRED_M); mbar_init(bar_free0 + 8, PRED_M);
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, 2 * B_BYTES);                             // weights: one bulk copy, awaited before the first MMA
+        tma_load_1d(smem_u32(Bsm), prm.B, 2 * B_BYTES, bar_w);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < (int)(2 * B_BYTES / 4); i += PRED_THREADS) Bsm[i] = prm.B[i];
     if (tid < PRED_N) bias[tid] = prm.bias[tid];
-    if (half == 0) {   // columns 66..71 of every row stay zero for the lifetime of the CTA
-        float* hz = A_hi + ((N_IN >> 2) * PRED_M + row) * 4;            // chunk 16: k = 64..67
-        float* lz = A_lo + ((N_IN >> 2) * PRED_M + row) * 4;
-        hz[2] = hz[3] = 0.0f; lz[2] = lz[3] = 0.0f;
+    if (tid < PRED_M) {   // columns 68..71 of every row stay zero for the lifetime of the CTA (66, 67: written by the split)
         float4* h4 = reinterpret_cast<float4*>(A_hi + ((PRED_KC - 1) * PRED_M + row) * 4);   // chunk 17: k = 68..71
         float4* l4 = reinterpret_cast<float4*>(A_lo + ((PRED_KC - 1) * PRED_M + row) * 4);
         *h4 = make_float4(0.f, 0.f, 0.f, 0.f); *l4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -163,144 +189,171 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
 
     auto rows_of = [&](int64_t tl) -> int { const int64_t r = prm.n - tl * PRED_M; return (int)(r < PRED_M ? r : PRED_M); };
     auto tma_ok = [&](int64_t tl) -> bool { return ((rows_of(tl) * N_IN * 4) & 15) == 0; };
-    auto issue = [&](int64_t tl, int s) {                               // thread 0 only
-        const uint32_t bytes = (uint32_t)(rows_of(tl) * N_IN * 4);
-        const uint32_t bar = bar_full0 + 8 * s;
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(smem_u32(smem + OFF_STAGE + s * STAGE_BYTES), prm.X + tl * (int64_t)(PRED_M * N_IN), bytes, bar);
-    };
+    // this CTA's tiles: blockIdx.x + k * gridDim.x, k = 0 .. n_my - 1 (the grid never exceeds the tile count)
+    const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    auto tile_of = [&](int k) -> int64_t { return (int64_t)blockIdx.x + (int64_t)k * gridDim.x; };
 
-    uint32_t ph_full[2] = {0u, 0u}, ph_mma = 0u;
-    int64_t tile = blockIdx.x;
-    if (tid == 0 && tile < n_tiles && tma_ok(tile)) issue(tile, 0);
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        const int64_t next = tile + gridDim.x;
-        const int rows = rows_of(tile);
-        float* stage = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE_BYTES);
-        if (tid == 0 && next < n_tiles && tma_ok(next)) issue(next, s ^ 1);   // overlaps this tile's MMA + epilogue
-        if (tma_ok(tile)) {
-            mbar_wait(bar_full0 + 8 * s, ph_full[s]);
-            ph_full[s] ^= 1u;
-        } else {                                                        // odd-sized last tile: plain loads
-            const float* src = prm.X + tile * (int64_t)(PRED_M * N_IN);
-            for (int i = tid; i < rows * N_IN; i += PRED_THREADS) stage[i] = src[i];
-            __syncthreads();
-        }
-
-        // ---- 3xTF32 split into the UMMA layout (two threads per row: pairs 0..16 / 17..32)
-        if (row < rows) {
-            const float2* src = reinterpret_cast<const float2*>(stage + row * N_IN);
-            const int j0 = half ? 17 : 0, j1 = half ? N_IN / 2 : 17;
-#pragma unroll
-            for (int jj = 0; jj < 17; ++jj) {
-                const int j = j0 + jj;
-                if (j < j1) {
-                    const float2 x = src[j];
-                    const float hx = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                    const float hy = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                    const int k = 2 * j, off = ((k >> 2) * PRED_M + row) * 4 + (k & 3);
-                    *reinterpret_cast<float2*>(A_hi + off) = make_float2(hx, hy);
-                    *reinterpret_cast<float2*>(A_lo + off) = make_float2(x.x - hx, x.y - hy);
-                }
+    if (warp < PROD_THREADS / 32) {
+        // =============================================================== producers: TMA, split, MMA issue
+        const int half = tid >> 7;                                      // K half of the row this thread splits
+        auto issue = [&](int k) {                                       // one thread only
+            const int64_t tl = tile_of(k);
+            if (!tma_ok(tl)) return;                                    // odd-sized last tile: plain loads below
+            const uint32_t bytes = (uint32_t)(rows_of(tl) * N_IN * 4);
+            const int s = k % N_STAGES;
+            const uint32_t bar = bar_full0 + 8 * s;
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(smem_u32(smem + OFF_STAGE + s * STAGE_BYTES), prm.X + tl * (int64_t)(PRED_M * N_IN), bytes, bar);
+        };
+        if (tid == 0)
+            for (int k = 0; k < N_STAGES && k < n_my; ++k) issue(k);
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k % N_STAGES, b = k & 1;
+            const int64_t tile = tile_of(k);
+            const int rows = rows_of(tile);
+            float* stage = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE_BYTES);
+            if (tma_ok(tile)) {
+                mbar_wait(bar_full0 + 8 * s, (uint32_t)((k / N_STAGES) & 1));
+            } else {
+                const float* src = prm.X + tile * (int64_t)(PRED_M * N_IN);
+                for (int i = tid; i < rows * N_IN; i += PROD_THREADS) stage[i] = src[i];
+                group_sync<1, PROD_THREADS>();
             }
-        }
-        fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
+            // the MMAs of the previous tile have read the A buffers
+            if (k > 0) mbar_wait(bar_mma0 + 8 * ((k - 1) & 1), (uint32_t)(((k - 1) >> 1) & 1));
 
-        // ---- MMA: one thread issues 9 k-steps x 3 products into TMEM
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < PRED_K / 8; ++ks) {
-                const uint32_t ao = ks * 2 * (PRED_M * 16), bo = ks * 2 * (PRED_N * 16);
-                const uint64_t dah = umma_desc(a_hi + ao, PRED_M * 16, 128), dal = umma_desc(a_lo + ao, PRED_M * 16, 128);
-                const uint64_t dbh = umma_desc(b_hi + bo, PRED_N * 16, 128), dbl = umma_desc(b_lo + bo, PRED_N * 16, 128);
-                umma_tf32(tmem_base, dah, dbh, ks > 0 ? 1u : 0u);
-                umma_tf32(tmem_base, dal, dbh, 1u);
-                umma_tf32(tmem_base, dah, dbl, 1u);
-            }
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, ph_mma);
-        ph_mma ^= 1u;
-        tc_fence_after();
-
-        // ---- epilogue: TMEM lane = env row; warps 0-3 take columns 0..16, warps 4-7 columns 17..32
-        // (a warp may only touch the TMEM lane quarter 32 * (warp % 4))
-        {
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (half ? 17u : 0u);
-            uint32_t r0[16], r1 = 0u;
-            tmem_ld16(taddr, r0);
-            if (half == 0) tmem_ld1(taddr + 16, r1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            double pen = 0.0;
+            // ---- 3xTF32 split into the UMMA layout: one 16-byte (4 k) chunk per store, chunks 0..8 / 9..16
             if (row < rows) {
-                const int c0 = half ? 17 : 0;
+                const float2* src = reinterpret_cast<const float2*>(stage + row * N_IN);
+                const int c0 = half ? 9 : 0;
 #pragma unroll
-                for (int i = 0; i < 17; ++i) {
-                    if (i < 16 || half == 0) {
-                        const float V = __uint_as_float(i < 16 ? r0[i] : r1) + bias[c0 + i];
-                        out[row * N_OUT + c0 + i] = V;
-                        // in-limit voltages (the common case) contribute exactly zero: the fp64 terms are
-                        // only evaluated outside the conservative fp32 bounds lo_f >= v_min, hi_f <= v_max
-                        if (V < prm.lo_f || V > prm.hi_f) {
-                            const double under = prm.v_min - (double)V, over = (double)V - prm.v_max;
-                            pen = pen + ((under > 0.0 ? under : 0.0) + (over > 0.0 ? over : 0.0));
-                        }
+                for (int cc = 0; cc < 9; ++cc) {
+                    const int c = c0 + cc;
+                    if (c <= N_IN / 4) {                                // chunk 16 holds k = 64, 65 and two zeros
+                        const float2 x = src[2 * c];
+                        float2 y = make_float2(0.0f, 0.0f);
+                        if (2 * c + 1 < N_IN / 2) y = src[2 * c + 1];
+                        float4 h;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                        h.z = __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u);
+                        h.w = __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
+                        const int off = (c * PRED_M + row) * 4;
+                        *reinterpret_cast<float4*>(A_hi + off) = h;
+                        *reinterpret_cast<float4*>(A_lo + off) = make_float4(x.x - h.x, x.y - h.y, y.x - h.z, y.y - h.w);
                     }
                 }
             }
-            pen_part[half * PRED_M + row] = pen;
-        }
-        tc_fence_before();
-        __syncthreads();
-        const int64_t e = tile * PRED_M + row;
-        if (half == 0 && row < rows) {
-            const double pen = prm.w * (pen_part[row] + pen_part[PRED_M + row]);
-            if (prm.penalty != nullptr) prm.penalty[e] = pen;
-            if (prm.ring_pen != nullptr) {               // pos < cap and n <= cap: one conditional subtraction wraps
-                const int64_t rr = prm.ring_pos + e;
-                prm.ring_pen[rr >= prm.ring_cap ? rr - prm.ring_cap : rr] = (float)pen;
-            }
-        }
+            fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
+            group_sync<1, PROD_THREADS>();           // A complete; the staging buffer has been read by everyone
 
-        // ---- coalesced row stores: dense output and/or replay ring (wraps at capacity)
-        // (the tile's rows are contiguous in the dense output; in the ring they are contiguous up to
-        //  one wrap, so element i of the tile lands at i + base, minus the ring size past the end)
-        const int64_t e0 = tile * PRED_M;
-        const int64_t ring_elems = prm.ring_cap * N_OUT, ring_base = (prm.ring_pos + e0) * N_OUT;
-        const int n_el = rows * N_OUT;
-        float* dense = prm.vhat != nullptr ? prm.vhat + e0 * N_OUT : nullptr;
-        // 16-byte stores where the destination allows it: a full tile is 1056 float4 (e0 * 33 * 4 bytes is
-        // a multiple of 16); the ring segment qualifies when it does not wrap and starts 16-byte aligned
-        const bool ring_vec = prm.ring_vhat != nullptr && ((ring_base & 3) == 0) && (ring_base + n_el <= ring_elems);
-        if ((n_el & 3) == 0 && (dense == nullptr || ((reinterpret_cast<uintptr_t>(dense) & 15) == 0)) &&
-            (prm.ring_vhat == nullptr || (ring_vec && ((reinterpret_cast<uintptr_t>(prm.ring_vhat) & 15) == 0)))) {
-            const float4* o4 = reinterpret_cast<const float4*>(out);
-            float4* d4 = reinterpret_cast<float4*>(dense);
-            float4* r4 = prm.ring_vhat != nullptr ? reinterpret_cast<float4*>(prm.ring_vhat + ring_base) : nullptr;
-            for (int i = tid; i < (n_el >> 2); i += PRED_THREADS) {
-                const float4 v = o4[i];
-                if (d4 != nullptr) d4[i] = v;
-                if (r4 != nullptr) r4[i] = v;
+            if (warp == 0) {
+                // the epilogue of tile k - 2 has drained this accumulator; the weights have landed
+                if (k >= 2) mbar_wait(bar_free0 + 8 * b, (uint32_t)(((k >> 1) - 1) & 1));
+                if (k == 0) mbar_wait(bar_w, 0u);
+                tc_fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    if (k + N_STAGES < n_my) issue(k + N_STAGES);       // refill this staging buffer, three tiles ahead
+                    const uint32_t acc = tmem_base + (uint32_t)b * ACC_COLS;
+                    const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < PRED_K / 8; ++ks) {
+                        const uint32_t ao = ks * 2 * (PRED_M * 16), bo = ks * 2 * (PRED_N * 16);
+                        const uint64_t dah = umma_desc(a_hi + ao, PRED_M * 16, 128), dal = umma_desc(a_lo + ao, PRED_M * 16, 128);
+                        const uint64_t dbh = umma_desc(b_hi + bo, PRED_N * 16, 128), dbl = umma_desc(b_lo + bo, PRED_N * 16, 128);
+                        umma_tf32(acc, dah, dbh, ks > 0 ? 1u : 0u);
+                        umma_tf32(acc, dal, dbh, 1u);
+                        umma_tf32(acc, dah, dbl, 1u);
+                    }
+                    umma_commit(bar_mma0 + 8 * b);
+                }
+                __syncwarp();
             }
-        } else {
-            for (int i = tid; i < n_el; i += PRED_THREADS) {
-                const float v = out[i];
-                if (dense != nullptr) dense[i] = v;
-                if (prm.ring_vhat != nullptr) {
-                    int64_t o = ring_base + i;
-                    o = o >= ring_elems ? o - ring_elems : o;
-                    prm.ring_vhat[o] = v;
+        }
+    } else {
+        // =============================================================== epilogue: TMEM -> bias, penalty -> ring
+        for (int k = 0; k < n_my; ++k) {
+            const int b = k & 1;
+            const int64_t tile = tile_of(k);
+            const int rows = rows_of(tile);
+            mbar_wait(bar_mma0 + 8 * b, (uint32_t)((k >> 1) & 1));
+            tc_fence_after();
+            // TMEM lane = env row; a warp may only touch the lane quarter 32 * (warp % 4)
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)b * ACC_COLS;
+            uint32_t r0[32], r1 = 0u;
+            tmem_ld32(taddr, r0);
+            tmem_ld1(taddr + 32, r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(bar_free0 + 8 * b);              // the accumulator may be overwritten (tile k + 2)
+            double pen = 0.0;
+            if (row < rows) {
+                float vmn = INFINITY, vmx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < N_OUT; ++i) {
+                    const float V = __uint_as_float(i < 32 ? r0[i < 32 ? i : 0] : r1) + bias[i];
+                    out[row * N_OUT + i] = V;
+                    vmn = fminf(vmn, V); vmx = fmaxf(vmx, V);
+                }
+                // in-limit voltages (the common case) contribute exactly zero: the fp64 terms are only
+                // evaluated for a row that leaves the conservative fp32 bounds lo_f >= v_min, hi_f <= v_max
+                if (vmn < prm.lo_f || vmx > prm.hi_f) {
+#pragma unroll
+                    for (int i = 0; i < N_OUT; ++i) {
+                        const float V = __uint_as_float(i < 32 ? r0[i < 32 ? i : 0] : r1) + bias[i];
+                        const double under = prm.v_min - (double)V, over = (double)V - prm.v_max;
+                        pen = pen + ((under > 0.0 ? under : 0.0) + (over > 0.0 ? over : 0.0));
+                    }
                 }
             }
+            const int64_t e = tile * PRED_M + row;
+            if (row < rows) {
+                pen = prm.w * pen;
+                if (prm.penalty != nullptr) prm.penalty[e] = pen;
+                if (prm.ring_pen != nullptr) {               // pos < cap and n <= cap: one conditional subtraction wraps
+                    const int64_t rr = prm.ring_pos + e;
+                    prm.ring_pen[rr >= prm.ring_cap ? rr - prm.ring_cap : rr] = (float)pen;
+                }
+            }
+            group_sync<2, PRED_M>();                             // the tile's Vhat rows are staged
+
+            // ---- coalesced row stores: dense output and/or replay ring (wraps at capacity)
+            // (the tile's rows are contiguous in the dense output; in the ring they are contiguous up to
+            //  one wrap, so element i of the tile lands at i + base, minus the ring size past the end)
+            const int64_t e0 = tile * PRED_M;
+            const int64_t ring_elems = prm.ring_cap * N_OUT, ring_base = (prm.ring_pos + e0) * N_OUT;
+            const int n_el = rows * N_OUT;
+            float* dense = prm.vhat != nullptr ? prm.vhat + e0 * N_OUT : nullptr;
+            // 16-byte stores where the destination allows it: a full tile is 1056 float4 (e0 * 33 * 4 bytes is
+            // a multiple of 16); the ring segment qualifies when it does not wrap and starts 16-byte aligned
+            const bool ring_vec = prm.ring_vhat != nullptr && ((ring_base & 3) == 0) && (ring_base + n_el <= ring_elems);
+            if ((n_el & 3) == 0 && (dense == nullptr || ((reinterpret_cast<uintptr_t>(dense) & 15) == 0)) &&
+                (prm.ring_vhat == nullptr || (ring_vec && ((reinterpret_cast<uintptr_t>(prm.ring_vhat) & 15) == 0)))) {
+                const float4* o4 = reinterpret_cast<const float4*>(out);
+                float4* d4 = reinterpret_cast<float4*>(dense);
+                float4* r4 = prm.ring_vhat != nullptr ? reinterpret_cast<float4*>(prm.ring_vhat + ring_base) : nullptr;
+                for (int i = row; i < (n_el >> 2); i += PRED_M) {
+                    const float4 v = o4[i];
+                    if (d4 != nullptr) d4[i] = v;
+                    if (r4 != nullptr) r4[i] = v;
+                }
+            } else {
+                for (int i = row; i < n_el; i += PRED_M) {
+                    const float v = out[i];
+                    if (dense != nullptr) dense[i] = v;
+                    if (prm.ring_vhat != nullptr) {
+                        int64_t o = ring_base + i;
+                        o = o >= ring_elems ? o - ring_elems : o;
+                        prm.ring_vhat[o] = v;
+                    }
+                }
+            }
+            group_sync<2, PRED_M>();                             // `out` is free for the next tile
         }
-        // the next iteration's transform does not touch `out`; its epilogue is two barriers away
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
