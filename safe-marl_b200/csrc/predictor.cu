@@ -24,8 +24,8 @@
 //        hi*hi + lo*hi + hi*lo), issued by ONE elected thread of warp 0, accumulating fp32 in one of TWO TMEM
 //        accumulators (2 x 64 columns); completion via tcgen05.commit -> mbarrier.  The weights (hi
 //        and lo parts, same layout) sit in shared memory for the lifetime of the CTA.
-//   epilogue warps 8-11 (thread t = env row t, TMEM lane quarter = warp % 4)
-//     4. tcgen05.ld (32x32b.x32 + .x1) hands every thread the 33 accumulators of its env and frees
+//   epilogue warps 8-15 (two threads per env row: column halves; TMEM lane quarter = warp % 4)
+//     4. tcgen05.ld (32x32b.x16 + .x1) hands every thread its 17 / 16 accumulators of its env and frees
 //        the accumulator for the tile after next; add the bias, evaluate the slack penalty in fp64,
 //        stage Vhat in shared memory and store coalesced rows into the replay ring at
 //        (pos + env) mod capacity (and/or a dense output).
@@ -55,8 +55,9 @@ constexpr int N_STAGES = 3;                                  // X tiles in fligh
 constexpr uint32_t OFF_STAGE = OFF_BLO + B_BYTES;
 constexpr uint32_t OFF_OUT = OFF_STAGE + N_STAGES * STAGE_BYTES;   // [128][33] fp32
 constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;
-constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[3], mma_done[2], tmem_free[2], weights
-constexpr uint32_t OFF_TMEM = OFF_BAR + 8 * 8;
+constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[3], mma_done[2], tmem_free[2], weights, half_done, a_ready[2]
+constexpr uint32_t OFF_PEN = OFF_BAR + 12 * 8;                // [2][128] fp64 penalty partials (column halves)
+constexpr uint32_t OFF_TMEM = OFF_PEN + 2 * PRED_M * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 constexpr uint32_t ACC_COLS = 64;                            // one accumulator: power of two >= 48
 constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                 // two accumulators
@@ -121,16 +122,21 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// Bulk shared -> global stores (TMA engine)
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -145,7 +151,10 @@ __device__ __forceinline__ bool elect_one() {                // one lane of a co
 }
 
 constexpr int PROD_THREADS = 2 * PRED_M;     // warps 0-7: TMA + split (two threads per row) + MMA issue (warp 0)
-constexpr int PRED_THREADS = 3 * PRED_M;     // warps 8-11: epilogue
+constexpr int EPI_THREADS = 2 * PRED_M;      // warps 8-15: epilogue (two threads per row: column halves)
+constexpr int MMA_WARP = (PROD_THREADS + EPI_THREADS) / 32;   // warp 16: TMA + tcgen05.mma issue
+constexpr int PRED_THREADS = PROD_THREADS + EPI_THREADS + 32;
+constexpr int KS_SPLIT = 5;                  // k-steps 0..4 read A chunks 0..9 (part 1), k-steps 5..8 chunks 10..17 (part 2)
 
 __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -155,8 +164,9 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
     float* out = reinterpret_cast<float*>(smem + OFF_OUT);
     float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+    double* pen_part = reinterpret_cast<double*>(smem + OFF_PEN);
     const uint32_t bar_full0 = smem_u32(smem + OFF_BAR), bar_mma0 = bar_full0 + 8 * N_STAGES, bar_free0 = bar_mma0 + 16,
-                   bar_w = bar_free0 + 16;
+                   bar_w = bar_free0 + 16, bar_half = bar_w + 8, bar_a0 = bar_half + 8;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);   // warp-uniform for the compiler
     const int row = tid & (PRED_M - 1);                                 // env row of the tile (both groups)
     const int64_t n_tiles = (prm.n + PRED_M - 1) / PRED_M;
@@ -165,8 +175,9 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
     if (tid == 0) {
         for (int s = 0; s < N_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
         mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1);
-        mbar_init(bar_free0, PRED_M); mbar_init(bar_free0 + 8, PRED_M);
-        mbar_init(bar_w, 1);
+        mbar_init(bar_free0, EPI_THREADS); mbar_init(bar_free0 + 8, EPI_THREADS);
+        mbar_init(bar_w, 1); mbar_init(bar_half, 1);
+        mbar_init(bar_a0, PROD_THREADS); mbar_init(bar_a0 + 8, PROD_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar_w, 2 * B_BYTES);                             // weights: one bulk copy, awaited before the first MMA
         tma_load_1d(smem_u32(Bsm), prm.B, 2 * B_BYTES, bar_w);
@@ -193,22 +204,66 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
     const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     auto tile_of = [&](int k) -> int64_t { return (int64_t)blockIdx.x + (int64_t)k * gridDim.x; };
 
-    if (warp < PROD_THREADS / 32) {
-        // =============================================================== producers: TMA, split, MMA issue
-        const int half = tid >> 7;                                      // K half of the row this thread splits
-        auto issue = [&](int k) {                                       // one thread only
-            const int64_t tl = tile_of(k);
-            if (!tma_ok(tl)) return;                                    // odd-sized last tile: plain loads below
-            const uint32_t bytes = (uint32_t)(rows_of(tl) * N_IN * 4);
-            const int s = k % N_STAGES;
-            const uint32_t bar = bar_full0 + 8 * s;
-            mbar_expect_tx(bar, bytes);
-            tma_load_1d(smem_u32(smem + OFF_STAGE + s * STAGE_BYTES), prm.X + tl * (int64_t)(PRED_M * N_IN), bytes, bar);
-        };
-        if (tid == 0)
+    auto issue = [&](int k) {                                           // one thread only (MMA warp)
+        const int64_t tl = tile_of(k);
+        if (!tma_ok(tl)) return;                                        // odd-sized last tile: plain loads by the producers
+        const uint32_t bytes = (uint32_t)(rows_of(tl) * N_IN * 4);
+        const int s = k % N_STAGES;
+        const uint32_t bar = bar_full0 + 8 * s;
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(smem_u32(smem + OFF_STAGE + s * STAGE_BYTES), prm.X + tl * (int64_t)(PRED_M * N_IN), bytes, bar);
+    };
+    // one tile's MMAs for k-steps [ks0, ks1): 3 products each (hi*hi + lo*hi + hi*lo)
+    auto mma_steps = [&](uint32_t acc, int ks0, int ks1) {
+        const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < PRED_K / 8; ++ks) {
+            if (ks >= ks0 && ks < ks1) {
+                const uint32_t ao = ks * 2 * (PRED_M * 16), bo = ks * 2 * (PRED_N * 16);
+                const uint64_t dah = umma_desc(a_hi + ao, PRED_M * 16, 128), dal = umma_desc(a_lo + ao, PRED_M * 16, 128);
+                const uint64_t dbh = umma_desc(b_hi + bo, PRED_N * 16, 128), dbl = umma_desc(b_lo + bo, PRED_N * 16, 128);
+                umma_tf32(acc, dah, dbh, ks > 0 ? 1u : 0u);
+                umma_tf32(acc, dal, dbh, 1u);
+                umma_tf32(acc, dah, dbl, 1u);
+            }
+        }
+    };
+
+    if (warp == MMA_WARP) {
+        // =============================================================== MMA warp: TMA issue, tcgen05.mma issue
+        // A is produced and consumed in two K parts (k-steps 0..4 = chunks 0..9, k-steps 5..8 = chunks 10..17), so
+        // that the split of one part overlaps the MMAs of the other and the A buffers never need a second copy
+        if (elect_one())
             for (int k = 0; k < N_STAGES && k < n_my; ++k) issue(k);
+        __syncwarp();
         for (int k = 0; k < n_my; ++k) {
-            const int s = k % N_STAGES, b = k & 1;
+            const int b = k & 1;
+            const uint32_t acc = tmem_base + (uint32_t)b * ACC_COLS;
+            mbar_wait(bar_a0, (uint32_t)(k & 1));                       // part 1 of A is in place
+            if (k >= 2) mbar_wait(bar_free0 + 8 * b, (uint32_t)(((k >> 1) - 1) & 1));   // epilogue of tile k - 2 drained the accumulator
+            if (k == 0) mbar_wait(bar_w, 0u);                           // the weights have landed
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
+                mma_steps(acc, 0, KS_SPLIT);
+                umma_commit(bar_half);
+            }
+            __syncwarp();
+            mbar_wait(bar_a0 + 8, (uint32_t)(k & 1));                   // part 2 of A is in place; the staging buffer is read
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
+                if (k + N_STAGES < n_my) issue(k + N_STAGES);           // refill this staging buffer, three tiles ahead
+                mma_steps(acc, KS_SPLIT, PRED_K / 8);
+                umma_commit(bar_mma0 + 8 * b);
+            }
+            __syncwarp();
+        }
+    } else if (warp < PROD_THREADS / 32) {
+        // =============================================================== producers: 3xTF32 split into the UMMA layout
+        const int half = tid >> 7;                                      // which chunks of the row this thread splits
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k % N_STAGES;
             const int64_t tile = tile_of(k);
             const int rows = rows_of(tile);
             float* stage = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE_BYTES);
@@ -219,104 +274,102 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
                 for (int i = tid; i < rows * N_IN; i += PROD_THREADS) stage[i] = src[i];
                 group_sync<1, PROD_THREADS>();
             }
-            // the MMAs of the previous tile have read the A buffers
-            if (k > 0) mbar_wait(bar_mma0 + 8 * ((k - 1) & 1), (uint32_t)(((k - 1) >> 1) & 1));
-
-            // ---- 3xTF32 split into the UMMA layout: one 16-byte (4 k) chunk per store, chunks 0..8 / 9..16
+            const float2* src = reinterpret_cast<const float2*>(stage + row * N_IN);
+            // one 16-byte (4 k) chunk per store; chunk 16 holds k = 64, 65 and two zeros
+            auto split_chunk = [&](int c) {
+                const float2 x = src[2 * c];
+                float2 y = make_float2(0.0f, 0.0f);
+                if (2 * c + 1 < N_IN / 2) y = src[2 * c + 1];
+                float4 h;
+                h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                h.z = __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u);
+                h.w = __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
+                const int off = (c * PRED_M + row) * 4;
+                *reinterpret_cast<float4*>(A_hi + off) = h;
+                *reinterpret_cast<float4*>(A_lo + off) = make_float4(x.x - h.x, x.y - h.y, y.x - h.z, y.y - h.w);
+            };
+            // ---- part 1: chunks 0..9 (five per thread), free once the first MMAs of the previous tile are done
+            if (k > 0) mbar_wait(bar_half, (uint32_t)((k - 1) & 1));
             if (row < rows) {
-                const float2* src = reinterpret_cast<const float2*>(stage + row * N_IN);
-                const int c0 = half ? 9 : 0;
 #pragma unroll
-                for (int cc = 0; cc < 9; ++cc) {
-                    const int c = c0 + cc;
-                    if (c <= N_IN / 4) {                                // chunk 16 holds k = 64, 65 and two zeros
-                        const float2 x = src[2 * c];
-                        float2 y = make_float2(0.0f, 0.0f);
-                        if (2 * c + 1 < N_IN / 2) y = src[2 * c + 1];
-                        float4 h;
-                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                        h.z = __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u);
-                        h.w = __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
-                        const int off = (c * PRED_M + row) * 4;
-                        *reinterpret_cast<float4*>(A_hi + off) = h;
-                        *reinterpret_cast<float4*>(A_lo + off) = make_float4(x.x - h.x, x.y - h.y, y.x - h.z, y.y - h.w);
-                    }
-                }
+                for (int cc = 0; cc < 5; ++cc) split_chunk((half ? 5 : 0) + cc);
             }
             fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
-            group_sync<1, PROD_THREADS>();           // A complete; the staging buffer has been read by everyone
-
-            if (warp == 0) {
-                // the epilogue of tile k - 2 has drained this accumulator; the weights have landed
-                if (k >= 2) mbar_wait(bar_free0 + 8 * b, (uint32_t)(((k >> 1) - 1) & 1));
-                if (k == 0) mbar_wait(bar_w, 0u);
-                tc_fence_after();
-                __syncwarp();
-                if (elect_one()) {
-                    if (k + N_STAGES < n_my) issue(k + N_STAGES);       // refill this staging buffer, three tiles ahead
-                    const uint32_t acc = tmem_base + (uint32_t)b * ACC_COLS;
-                    const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
+            mbar_arrive(bar_a0);
+            // ---- part 2: chunks 10..16 (four / three per thread), free once the previous tile's MMAs are done
+            if (k > 0) mbar_wait(bar_mma0 + 8 * ((k - 1) & 1), (uint32_t)(((k - 1) >> 1) & 1));
+            if (row < rows) {
 #pragma unroll
-                    for (int ks = 0; ks < PRED_K / 8; ++ks) {
-                        const uint32_t ao = ks * 2 * (PRED_M * 16), bo = ks * 2 * (PRED_N * 16);
-                        const uint64_t dah = umma_desc(a_hi + ao, PRED_M * 16, 128), dal = umma_desc(a_lo + ao, PRED_M * 16, 128);
-                        const uint64_t dbh = umma_desc(b_hi + bo, PRED_N * 16, 128), dbl = umma_desc(b_lo + bo, PRED_N * 16, 128);
-                        umma_tf32(acc, dah, dbh, ks > 0 ? 1u : 0u);
-                        umma_tf32(acc, dal, dbh, 1u);
-                        umma_tf32(acc, dah, dbl, 1u);
-                    }
-                    umma_commit(bar_mma0 + 8 * b);
-                }
-                __syncwarp();
+                for (int cc = 0; cc < 4; ++cc)
+                    if (half == 0 || cc < 3) split_chunk((half ? 14 : 10) + cc);
             }
+            fence_proxy_async();
+            mbar_arrive(bar_a0 + 8);
         }
-    } else {
+    } else if (warp < (PROD_THREADS + EPI_THREADS) / 32) {
         // =============================================================== epilogue: TMEM -> bias, penalty -> ring
+        const int etid = tid - PROD_THREADS, ehalf = etid >> 7;         // two threads per env row: column halves
+        const double neg_vmax = -prm.v_max;
         for (int k = 0; k < n_my; ++k) {
             const int b = k & 1;
             const int64_t tile = tile_of(k);
             const int rows = rows_of(tile);
             mbar_wait(bar_mma0 + 8 * b, (uint32_t)((k >> 1) & 1));
             tc_fence_after();
-            // TMEM lane = env row; a warp may only touch the lane quarter 32 * (warp % 4)
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)b * ACC_COLS;
-            uint32_t r0[32], r1 = 0u;
-            tmem_ld32(taddr, r0);
-            tmem_ld1(taddr + 32, r1);
+            // TMEM lane = env row; a warp may only touch the lane quarter 32 * (warp % 4): warps 8-11 take
+            // columns 0..16 of their quarter, warps 12-15 columns 17..32
+            const int c0 = ehalf ? 17 : 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)b * ACC_COLS + (uint32_t)c0;
+            uint32_t r0[16], r1 = 0u;
+            tmem_ld16(taddr, r0);
+            if (ehalf == 0) tmem_ld1(taddr + 16, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(bar_free0 + 8 * b);              // the accumulator may be overwritten (tile k + 2)
+            if (etid == 0) bulk_wait_read();             // the previous tile's bulk stores have read `out`
+            group_sync<2, EPI_THREADS>();                // ... and so have its store loops: `out` is free
             double pen = 0.0;
             if (row < rows) {
+                float V[17];
                 float vmn = INFINITY, vmx = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < N_OUT; ++i) {
-                    const float V = __uint_as_float(i < 32 ? r0[i < 32 ? i : 0] : r1) + bias[i];
-                    out[row * N_OUT + i] = V;
-                    vmn = fminf(vmn, V); vmx = fmaxf(vmx, V);
+                for (int i = 0; i < 17; ++i) {
+                    if (i < 16 || ehalf == 0) {
+                        V[i] = __uint_as_float(i < 16 ? r0[i < 16 ? i : 0] : r1) + bias[c0 + i];
+                        out[row * N_OUT + c0 + i] = V[i];
+                        vmn = fminf(vmn, V[i]); vmx = fmaxf(vmx, V[i]);
+                    }
                 }
-                // in-limit voltages (the common case) contribute exactly zero: the fp64 terms are only
-                // evaluated for a row that leaves the conservative fp32 bounds lo_f >= v_min, hi_f <= v_max
+                // in-limit voltages (the common case) contribute exactly zero, and the fp32 tests are EXACT
+                // (lo_f is the smallest float >= v_min, hi_f the largest <= v_max, V is a float): the fp64 terms
+                // are only evaluated for a row that leaves the limits, selected per column by the fp32 test
                 if (vmn < prm.lo_f || vmx > prm.hi_f) {
 #pragma unroll
-                    for (int i = 0; i < N_OUT; ++i) {
-                        const float V = __uint_as_float(i < 32 ? r0[i < 32 ? i : 0] : r1) + bias[i];
-                        const double under = prm.v_min - (double)V, over = (double)V - prm.v_max;
-                        pen = pen + ((under > 0.0 ? under : 0.0) + (over > 0.0 ? over : 0.0));
+                    for (int i = 0; i < 17; ++i) {
+                        if (i < 16 || ehalf == 0) {
+                            // v_min - V or V - v_max as ONE fused multiply-add with selected operands (the same
+                            // single rounding as the subtraction): a third of the fp64 work of computing both
+                            const bool un = V[i] < prm.lo_f, ov = V[i] > prm.hi_f;
+                            const double sg = un ? -1.0 : (ov ? 1.0 : 0.0);
+                            const double cc = un ? prm.v_min : (ov ? neg_vmax : 0.0);
+                            pen = pen + fma(sg, (double)V[i], cc);
+                        }
                     }
                 }
             }
+            pen_part[ehalf * PRED_M + row] = pen;
+            fence_proxy_async();                                 // `out` is read by the bulk stores (async proxy)
+            group_sync<2, EPI_THREADS>();                        // the tile's Vhat rows and penalty halves are staged
             const int64_t e = tile * PRED_M + row;
-            if (row < rows) {
-                pen = prm.w * pen;
-                if (prm.penalty != nullptr) prm.penalty[e] = pen;
+            if (ehalf == 0 && row < rows) {
+                const double pw = prm.w * (pen_part[row] + pen_part[PRED_M + row]);
+                if (prm.penalty != nullptr) prm.penalty[e] = pw;
                 if (prm.ring_pen != nullptr) {               // pos < cap and n <= cap: one conditional subtraction wraps
                     const int64_t rr = prm.ring_pos + e;
-                    prm.ring_pen[rr >= prm.ring_cap ? rr - prm.ring_cap : rr] = (float)pen;
+                    prm.ring_pen[rr >= prm.ring_cap ? rr - prm.ring_cap : rr] = (float)pw;
                 }
             }
-            group_sync<2, PRED_M>();                             // the tile's Vhat rows are staged
 
             // ---- coalesced row stores: dense output and/or replay ring (wraps at capacity)
             // (the tile's rows are contiguous in the dense output; in the ring they are contiguous up to
@@ -330,16 +383,14 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
             const bool ring_vec = prm.ring_vhat != nullptr && ((ring_base & 3) == 0) && (ring_base + n_el <= ring_elems);
             if ((n_el & 3) == 0 && (dense == nullptr || ((reinterpret_cast<uintptr_t>(dense) & 15) == 0)) &&
                 (prm.ring_vhat == nullptr || (ring_vec && ((reinterpret_cast<uintptr_t>(prm.ring_vhat) & 15) == 0)))) {
-                const float4* o4 = reinterpret_cast<const float4*>(out);
-                float4* d4 = reinterpret_cast<float4*>(dense);
-                float4* r4 = prm.ring_vhat != nullptr ? reinterpret_cast<float4*>(prm.ring_vhat + ring_base) : nullptr;
-                for (int i = row; i < (n_el >> 2); i += PRED_M) {
-                    const float4 v = o4[i];
-                    if (d4 != nullptr) d4[i] = v;
-                    if (r4 != nullptr) r4[i] = v;
+                // one bulk store (TMA engine) per destination: the staged tile is the contiguous image of its rows
+                if (etid == 0) {
+                    if (dense != nullptr) bulk_s2g(dense, out, (uint32_t)n_el * 4u);
+                    if (prm.ring_vhat != nullptr) bulk_s2g(prm.ring_vhat + ring_base, out, (uint32_t)n_el * 4u);
+                    bulk_commit();
                 }
             } else {
-                for (int i = row; i < n_el; i += PRED_M) {
+                for (int i = etid; i < n_el; i += EPI_THREADS) {
                     const float v = out[i];
                     if (dense != nullptr) dense[i] = v;
                     if (prm.ring_vhat != nullptr) {
@@ -349,8 +400,8 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
                     }
                 }
             }
-            group_sync<2, PRED_M>();                             // `out` is free for the next tile
         }
+        if (etid == 0) bulk_wait_all();                  // shared memory must outlive the bulk stores
     }
 
     tc_fence_before();
