@@ -8,30 +8,35 @@
 //       (madrl/models/safemaddpg.py:205-229,264-277: 1000 * sum(max(0, v_min - V) + max(0, V - v_max)))
 //   fp_replay_*                      replace TransReplayBuffer (utils/replay_buffer.py:3-30)
 //
-// Kernel k_predict: one persistent CTA per SM, 128-env tiles, WARP-SPECIALISED so that the phases of
-// consecutive tiles overlap (the op is HBM-bound by shape -- K = 66, N = 33: ~11 flop/B -- and the job
-// of the kernel is to keep three tiles of X in flight per SM while the rest hides underneath):
-//   producer warps 0-7 (two threads per env row of the tile: K halves)
-//     1. TMA: `cp.async.bulk` brings the tile's X rows (128 x 66 fp32 = 33 792 contiguous bytes) into
-//        one of THREE staging buffers, completion on an mbarrier; a buffer is refilled (three tiles
-//        ahead) as soon as the split below has read it.
-//     2. 3xTF32 split: x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits
-//        cleared) and lo = x - hi (exact), written in the UMMA K-major no-swizzle ("interleave")
-//        layout: core matrices of 8 rows x 16 bytes, [k-chunk][row][4 floats], SBO = 128 B,
-//        LBO = rows * 16 B.  The A buffers are single: the split of tile i+1 waits for the MMAs of
-//        tile i (their commit barrier), which is short against a tile's HBM time.
+// Kernel k_predict: one persistent CTA per SM (17 warps), 128-env tiles, WARP-SPECIALISED so that the
+// phases of consecutive tiles overlap.  The op is HBM-bound by shape (K = 66, N = 33: ~11 flop/B); the
+// job of the kernel is to keep four tiles of X in flight per SM while everything else hides underneath,
+// and to keep shared-memory traffic (the second bound: 128 B/clk/SM) to the X tile and the Vhat tile.
+//   TMA/MMA warp 16 (one elected thread)
+//     1. TMA: `cp.async.bulk` brings a tile's X rows (128 x 66 fp32 = 33 792 contiguous bytes) into one
+//        of FOUR staging buffers, completion on an mbarrier; a buffer is refilled (four tiles ahead) as
+//        soon as every producer has read it.
 //     3. tcgen05.mma (kind::tf32, M=128, N=48, K=8 per instruction; 9 k-steps x 3 products
-//        hi*hi + lo*hi + hi*lo), issued by ONE elected thread of warp 0, accumulating fp32 in one of TWO TMEM
-//        accumulators (2 x 64 columns); completion via tcgen05.commit -> mbarrier.  The weights (hi
-//        and lo parts, same layout) sit in shared memory for the lifetime of the CTA.
+//        hi*hi + lo*hi + hi*lo) with the A OPERAND IN TMEM and the weights (hi and lo parts, UMMA K-major
+//        no-swizzle layout: [k-chunk][n][4 floats], SBO = 128 B, LBO = 48 * 16 B) in shared memory for the
+//        lifetime of the CTA; fp32 accumulation in one of TWO TMEM accumulators; completion via
+//        tcgen05.commit -> mbarrier.
+//   producer warps 0-7 (two threads per env row of the tile: K halves)
+//     2. 3xTF32 split: x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared)
+//        and lo = x - hi (exact).  A thread owns a row, and a TMEM lane IS a row: `tcgen05.st.32x32b.x4`
+//        writes hi and lo straight into one of TWO A buffers in TMEM (lane = env row, column = k;
+//        144 columns per buffer), so A never touches shared memory (it would cost 70 KB of stores and
+//        110 KB of operand reads per tile there) and the split of tile i+1 overlaps the MMAs of tile i.
 //   epilogue warps 8-15 (two threads per env row: column halves; TMEM lane quarter = warp % 4)
 //     4. tcgen05.ld (32x32b.x16 + .x1) hands every thread its 17 / 16 accumulators of its env and frees
-//        the accumulator for the tile after next; add the bias, evaluate the slack penalty in fp64,
-//        stage Vhat in shared memory and store coalesced rows into the replay ring at
-//        (pos + env) mod capacity (and/or a dense output).
-// The weights arrive by one bulk copy that overlaps the first X tiles (own mbarrier).
-// The two groups meet only through mbarriers (full[3], mma_done[2], tmem_free[2]) and synchronise
-// internally with named barriers; every wait is bounded (trap, never a hung GPU).
+//        the accumulator for the tile after next; add the bias, evaluate the slack penalty (fp64, only
+//        for rows that leave the limits), stage Vhat in shared memory; ONE bulk store per destination
+//        (TMA engine) writes the tile into the replay ring at (pos + env) mod capacity and/or a dense
+//        output (a wrapping or unaligned segment falls back to a coalesced store loop).
+// TMEM map (512 columns): accumulators at 0 and 64, A buffers at 128 and 272 (hi 72 | lo 72 columns).
+// The weights arrive by one bulk copy that overlaps the first X tiles (own mbarrier).  The groups meet
+// only through mbarriers (full[4], a_ready[2], mma_done[2], tmem_free[2]); the epilogue synchronises
+// internally with a named barrier; every wait is bounded (trap, never a hung GPU).
 #include <cmath>
 #include <cstring>
 
@@ -47,20 +52,21 @@ int fp_internal_device(FpHandle* h);
 namespace {
 
 constexpr int N_IN = 66, N_OUT = 33;
-constexpr uint32_t A_BYTES = PRED_KC * PRED_M * 16;          // 36 864
 constexpr uint32_t B_BYTES = PRED_KC * PRED_N * 16;          // 13 824
 constexpr uint32_t STAGE_BYTES = PRED_M * N_IN * 4;          // 33 792
-constexpr uint32_t OFF_AHI = 0, OFF_ALO = OFF_AHI + A_BYTES, OFF_BHI = OFF_ALO + A_BYTES, OFF_BLO = OFF_BHI + B_BYTES;
-constexpr int N_STAGES = 3;                                  // X tiles in flight per SM (3 x 33 KB covers the HBM latency)
+constexpr uint32_t OFF_BHI = 0, OFF_BLO = OFF_BHI + B_BYTES;
+constexpr int N_STAGES = 4;                                  // X tiles in flight per SM (4 x 33 KB covers the HBM latency)
 constexpr uint32_t OFF_STAGE = OFF_BLO + B_BYTES;
 constexpr uint32_t OFF_OUT = OFF_STAGE + N_STAGES * STAGE_BYTES;   // [128][33] fp32
 constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;
-constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[3], mma_done[2], tmem_free[2], weights, half_done, a_ready[2]
+constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[4], mma_done[2], tmem_free[2], weights, a_ready[2]
 constexpr uint32_t OFF_PEN = OFF_BAR + 12 * 8;                // [2][128] fp64 penalty partials (column halves)
 constexpr uint32_t OFF_TMEM = OFF_PEN + 2 * PRED_M * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
-constexpr uint32_t ACC_COLS = 64;                            // one accumulator: power of two >= 48
-constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                 // two accumulators
+constexpr uint32_t ACC_COLS = 64;                            // one accumulator (48 columns used)
+constexpr uint32_t A_COL0 = 2 * ACC_COLS;                    // A operand in TMEM: [2 buffers][hi 72 | lo 72] columns, lane = env row
+constexpr uint32_t A_COLS = 2 * PRED_K;
+constexpr uint32_t TMEM_COLS = 512;                          // 2 accumulators + 2 A buffers = 416 columns -> the whole TMEM (one CTA per SM)
 static_assert(SMEM_BYTES <= 227 * 1024, "predictor tile buffers exceed the shared memory of one SM");
 
 struct PredParams {
@@ -109,12 +115,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // Instruction descriptor: D fp32, A/B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PRED_N >> 3) << 17) | ((uint32_t)(PRED_M >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// A operand from TMEM (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -154,19 +165,16 @@ constexpr int PROD_THREADS = 2 * PRED_M;     // warps 0-7: TMA + split (two thre
 constexpr int EPI_THREADS = 2 * PRED_M;      // warps 8-15: epilogue (two threads per row: column halves)
 constexpr int MMA_WARP = (PROD_THREADS + EPI_THREADS) / 32;   // warp 16: TMA + tcgen05.mma issue
 constexpr int PRED_THREADS = PROD_THREADS + EPI_THREADS + 32;
-constexpr int KS_SPLIT = 5;                  // k-steps 0..4 read A chunks 0..9 (part 1), k-steps 5..8 chunks 10..17 (part 2)
 
 __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
-    float* A_hi = reinterpret_cast<float*>(smem + OFF_AHI);
-    float* A_lo = reinterpret_cast<float*>(smem + OFF_ALO);
     float* Bsm = reinterpret_cast<float*>(smem + OFF_BHI);              // hi then lo, contiguous
     float* out = reinterpret_cast<float*>(smem + OFF_OUT);
     float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     double* pen_part = reinterpret_cast<double*>(smem + OFF_PEN);
     const uint32_t bar_full0 = smem_u32(smem + OFF_BAR), bar_mma0 = bar_full0 + 8 * N_STAGES, bar_free0 = bar_mma0 + 16,
-                   bar_w = bar_free0 + 16, bar_half = bar_w + 8, bar_a0 = bar_half + 8;
+                   bar_w = bar_free0 + 16, bar_a0 = bar_w + 8;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);   // warp-uniform for the compiler
     const int row = tid & (PRED_M - 1);                                 // env row of the tile (both groups)
     const int64_t n_tiles = (prm.n + PRED_M - 1) / PRED_M;
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
         for (int s = 0; s < N_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
         mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1);
         mbar_init(bar_free0, EPI_THREADS); mbar_init(bar_free0 + 8, EPI_THREADS);
-        mbar_init(bar_w, 1); mbar_init(bar_half, 1);
+        mbar_init(bar_w, 1);
         mbar_init(bar_a0, PROD_THREADS); mbar_init(bar_a0 + 8, PROD_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar_w, 2 * B_BYTES);                             // weights: one bulk copy, awaited before the first MMA
@@ -187,11 +195,6 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < PRED_N) bias[tid] = prm.bias[tid];
-    if (tid < PRED_M) {   // columns 68..71 of every row stay zero for the lifetime of the CTA (66, 67: written by the split)
-        float4* h4 = reinterpret_cast<float4*>(A_hi + ((PRED_KC - 1) * PRED_M + row) * 4);   // chunk 17: k = 68..71
-        float4* l4 = reinterpret_cast<float4*>(A_lo + ((PRED_KC - 1) * PRED_M + row) * 4);
-        *h4 = make_float4(0.f, 0.f, 0.f, 0.f); *l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -213,57 +216,45 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
         mbar_expect_tx(bar, bytes);
         tma_load_1d(smem_u32(smem + OFF_STAGE + s * STAGE_BYTES), prm.X + tl * (int64_t)(PRED_M * N_IN), bytes, bar);
     };
-    // one tile's MMAs for k-steps [ks0, ks1): 3 products each (hi*hi + lo*hi + hi*lo)
-    auto mma_steps = [&](uint32_t acc, int ks0, int ks1) {
-        const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
+    // one tile's MMAs: 9 k-steps x 3 products (hi*hi + lo*hi + hi*lo), A from TMEM buffer `ab`
+    auto mma_tile = [&](uint32_t acc, uint32_t ab) {
+        const uint32_t b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
+        const uint32_t t_hi = tmem_base + A_COL0 + ab * A_COLS, t_lo = t_hi + PRED_K;
 #pragma unroll
         for (int ks = 0; ks < PRED_K / 8; ++ks) {
-            if (ks >= ks0 && ks < ks1) {
-                const uint32_t ao = ks * 2 * (PRED_M * 16), bo = ks * 2 * (PRED_N * 16);
-                const uint64_t dah = umma_desc(a_hi + ao, PRED_M * 16, 128), dal = umma_desc(a_lo + ao, PRED_M * 16, 128);
-                const uint64_t dbh = umma_desc(b_hi + bo, PRED_N * 16, 128), dbl = umma_desc(b_lo + bo, PRED_N * 16, 128);
-                umma_tf32(acc, dah, dbh, ks > 0 ? 1u : 0u);
-                umma_tf32(acc, dal, dbh, 1u);
-                umma_tf32(acc, dah, dbl, 1u);
-            }
+            const uint32_t bo = ks * 2 * (PRED_N * 16);
+            const uint64_t dbh = umma_desc(b_hi + bo, PRED_N * 16, 128), dbl = umma_desc(b_lo + bo, PRED_N * 16, 128);
+            umma_tf32_ts(acc, t_hi + 8 * ks, dbh, ks > 0 ? 1u : 0u);
+            umma_tf32_ts(acc, t_lo + 8 * ks, dbh, 1u);
+            umma_tf32_ts(acc, t_hi + 8 * ks, dbl, 1u);
         }
     };
 
     if (warp == MMA_WARP) {
         // =============================================================== MMA warp: TMA issue, tcgen05.mma issue
-        // A is produced and consumed in two K parts (k-steps 0..4 = chunks 0..9, k-steps 5..8 = chunks 10..17), so
-        // that the split of one part overlaps the MMAs of the other and the A buffers never need a second copy
         if (elect_one())
             for (int k = 0; k < N_STAGES && k < n_my; ++k) issue(k);
         __syncwarp();
         for (int k = 0; k < n_my; ++k) {
             const int b = k & 1;
-            const uint32_t acc = tmem_base + (uint32_t)b * ACC_COLS;
-            mbar_wait(bar_a0, (uint32_t)(k & 1));                       // part 1 of A is in place
+            mbar_wait(bar_a0 + 8 * b, (uint32_t)((k >> 1) & 1));        // A buffer b holds tile k; its staging buffer is read
             if (k >= 2) mbar_wait(bar_free0 + 8 * b, (uint32_t)(((k >> 1) - 1) & 1));   // epilogue of tile k - 2 drained the accumulator
             if (k == 0) mbar_wait(bar_w, 0u);                           // the weights have landed
             tc_fence_after();
             __syncwarp();
             if (elect_one()) {
-                mma_steps(acc, 0, KS_SPLIT);
-                umma_commit(bar_half);
-            }
-            __syncwarp();
-            mbar_wait(bar_a0 + 8, (uint32_t)(k & 1));                   // part 2 of A is in place; the staging buffer is read
-            tc_fence_after();
-            __syncwarp();
-            if (elect_one()) {
-                if (k + N_STAGES < n_my) issue(k + N_STAGES);           // refill this staging buffer, three tiles ahead
-                mma_steps(acc, KS_SPLIT, PRED_K / 8);
+                if (k + N_STAGES < n_my) issue(k + N_STAGES);           // refill the staging buffer, N_STAGES tiles ahead
+                mma_tile(tmem_base + (uint32_t)b * ACC_COLS, (uint32_t)b);
                 umma_commit(bar_mma0 + 8 * b);
             }
             __syncwarp();
         }
     } else if (warp < PROD_THREADS / 32) {
-        // =============================================================== producers: 3xTF32 split into the UMMA layout
-        const int half = tid >> 7;                                      // which chunks of the row this thread splits
+        // =============================================================== producers: 3xTF32 split -> A operand in TMEM
+        // thread = (env row, K half); a warp writes the TMEM lane quarter 32 * (warp % 4) = its rows
+        const int half = tid >> 7;
         for (int k = 0; k < n_my; ++k) {
-            const int s = k % N_STAGES;
+            const int s = k % N_STAGES, b = k & 1;
             const int64_t tile = tile_of(k);
             const int rows = rows_of(tile);
             float* stage = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE_BYTES);
@@ -274,38 +265,26 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
                 for (int i = tid; i < rows * N_IN; i += PROD_THREADS) stage[i] = src[i];
                 group_sync<1, PROD_THREADS>();
             }
+            // the MMAs of tile k - 2 have read A buffer b
+            if (k >= 2) mbar_wait(bar_mma0 + 8 * b, (uint32_t)(((k >> 1) - 1) & 1));
+            tc_fence_after();
             const float2* src = reinterpret_cast<const float2*>(stage + row * N_IN);
-            // one 16-byte (4 k) chunk per store; chunk 16 holds k = 64, 65 and two zeros
-            auto split_chunk = [&](int c) {
-                const float2 x = src[2 * c];
-                float2 y = make_float2(0.0f, 0.0f);
+            const uint32_t t_hi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0 + (uint32_t)b * A_COLS, t_lo = t_hi + PRED_K;
+            // rows past the end of a partial tile split whatever the staging buffer holds: never stored
+#pragma unroll
+            for (int cc = 0; cc < 9; ++cc) {
+                const int c = (half ? 9 : 0) + cc;                      // 4-k chunk; 16 holds k = 64, 65 and zeros, 17 zeros
+                float2 x = make_float2(0.0f, 0.0f), y = make_float2(0.0f, 0.0f);
+                if (2 * c < N_IN / 2) x = src[2 * c];
                 if (2 * c + 1 < N_IN / 2) y = src[2 * c + 1];
-                float4 h;
-                h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                h.z = __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u);
-                h.w = __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
-                const int off = (c * PRED_M + row) * 4;
-                *reinterpret_cast<float4*>(A_hi + off) = h;
-                *reinterpret_cast<float4*>(A_lo + off) = make_float4(x.x - h.x, x.y - h.y, y.x - h.z, y.y - h.w);
-            };
-            // ---- part 1: chunks 0..9 (five per thread), free once the first MMAs of the previous tile are done
-            if (k > 0) mbar_wait(bar_half, (uint32_t)((k - 1) & 1));
-            if (row < rows) {
-#pragma unroll
-                for (int cc = 0; cc < 5; ++cc) split_chunk((half ? 5 : 0) + cc);
+                const float hx = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), hy = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                const float hz = __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u), hw = __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
+                tmem_st4(t_hi + 4 * c, hx, hy, hz, hw);
+                tmem_st4(t_lo + 4 * c, x.x - hx, x.y - hy, y.x - hz, y.y - hw);
             }
-            fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
-            mbar_arrive(bar_a0);
-            // ---- part 2: chunks 10..16 (four / three per thread), free once the previous tile's MMAs are done
-            if (k > 0) mbar_wait(bar_mma0 + 8 * ((k - 1) & 1), (uint32_t)(((k - 1) >> 1) & 1));
-            if (row < rows) {
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc)
-                    if (half == 0 || cc < 3) split_chunk((half ? 14 : 10) + cc);
-            }
-            fence_proxy_async();
-            mbar_arrive(bar_a0 + 8);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(bar_a0 + 8 * b);
         }
     } else if (warp < (PROD_THREADS + EPI_THREADS) / 32) {
         // =============================================================== epilogue: TMEM -> bias, penalty -> ring
