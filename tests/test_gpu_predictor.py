@@ -139,3 +139,37 @@ def test_argument_validation(env, cuda):
     with pytest.raises(FlexGpuError):
         buf.reserve(0)
     buf.close()
+
+
+@pytest.mark.parametrize("n", [127, 129, 18944, 148 * 128 * 5 + 77, 262144 + 33, 1 << 20])
+def test_pipeline_every_row_all_tile_shapes(env, pred, cuda, n):
+    """The warp-specialised pipeline (TMA ring of 4 tiles, two TMEM A buffers, two accumulators) over launches
+    that end on full, partial and odd tiles and run 1..56 tiles per CTA, with HBM traffic on a second stream
+    racing the kernel: EVERY row against a torch fp64 evaluation of the same affine map (1e-6 p.u.), the
+    penalty against the fp64 formula on the returned Vhat (exact arithmetic), the ring segment (wrapping) bit
+    for bit against the dense output."""
+    from flexgpu.predictor import DeviceReplayBuffer
+    from flexgpu import Network, create_network, DEFAULT_ENV_ARGS
+    net = Network(create_network(DEFAULT_ENV_ARGS))
+    base = torch.from_numpy(np.stack([net.base_p, net.base_q], axis=1).reshape(-1)).to(cuda)
+    g = torch.Generator(device=cuda).manual_seed(n)
+    X = (base[None, :] * (0.7 + 1.3 * torch.rand(n, 66, device=cuda, dtype=torch.float64, generator=g))).float().contiguous()
+    A = torch.from_numpy(pred.A).to(cuda); c = torch.from_numpy(pred.c).to(cuda)
+    buf = DeviceReplayBuffer(n + 5, {"v_pred": 33, "safety_penalty": 1}, device=cuda)
+    buf.reserve(n + 5)                                  # full ring: physical row = logical row
+    pos = n // 3
+    noise = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        noise.add_(1)
+    vhat, pen = pred.predict(X, sink=buf, pos=pos)
+    torch.cuda.synchronize()
+    assert float((vhat.double() - (X.double() @ A.T + c)).abs().max()) < TOL_V
+    vd = vhat.double()
+    want = 1000.0 * (torch.clamp(pred.v_min - vd, min=0) + torch.clamp(vd - pred.v_max, min=0)).sum(dim=1)
+    assert torch.allclose(pen, want, rtol=1e-12, atol=1e-9)
+    assert int((pen > 0).sum()) > 0 or n < 1000          # the 2x-load scenarios leave the limits somewhere
+    idx = (pos + torch.arange(n, device=cuda)) % (n + 5)
+    got = buf.get_batch(n + 5, start=0)
+    assert torch.equal(got["v_pred"][idx], vhat) and torch.equal(got["safety_penalty"][idx, 0], pen.float())
+    buf.close()
