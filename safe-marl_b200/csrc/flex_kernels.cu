@@ -38,7 +38,6 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_env(const EnvParams prm) {
     const int nl = c.nl, na = c.na;
     const int my_col = s_topo.col[lane];
     const int my_agent = s_topo.agent[lane];               // agent living on this lane's bus
-    const int a_lane = (lane < na) ? s_topo.agent_lane[lane] : 0;   // as agent `lane`: my bus's lane
     const int a_col = (lane < na) ? s_topo.agent_col[lane] : 0;
     double* scratch = s_scratch[warp];
     double stat_acc = 0.0;                                 // lane j < FP_NSTATS accumulates stat j
