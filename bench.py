@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config3", action="store_true", help="skip the extra 65 536-env (config 3) measurement at N=1")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostics only)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the extra predictor (config 4) measurement at N=1")
     ap.add_argument("--no-obs", action="store_true", help="skip the extra step+get_obs measurement (rollout-loop cost)")
     ap.add_argument("--variant", default="thread", choices=["thread", "warp", "pair"], help="kernel variant (see include/flexgpu.h)")
     args = ap.parse_args()
@@ -338,6 +339,35 @@ def main():
                    "roofline_frac": B_ALG * E3 / (statistics.median(ms3) * 1e-3) / 1e9 / peaks()[0]}
         env3.close()
 
+    # ---- BASELINE config 4 (voltage predictor + safety penalty -> replay ring, 262 144 envs), N = 1 only
+    config4 = None
+    if world == 1 and not args.no_config4:
+        import numpy as np
+        from flexgpu import Network, create_network, DEFAULT_ENV_ARGS
+        from flexgpu.predictor import DeviceReplayBuffer, VoltagePredictor
+        E4 = 262144
+        gp = np.load(os.path.join(ROOT, "tests", "golden", "predictor_golden.npz"))
+        pred = VoltagePredictor.from_linear_model(env, gp["coef"], gp["intercept"], gp["x_scale"], gp["x_min"], gp["y_scale"], gp["y_min"])
+        net4 = Network(create_network(DEFAULT_ENV_ARGS))
+        base4 = torch.from_numpy(np.stack([net4.base_p, net4.base_q], axis=1).reshape(-1)).to(dev)
+        # X = interleaved [p_n, q_n] of load scenarios: base loads x U(0.7, 1.3) (data_generation.py:27-36)
+        X4 = (base4[None, :] * (0.7 + 0.6 * torch.rand(E4, 66, device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(4)))).float().contiguous()
+        ring = DeviceReplayBuffer(2 * E4, {"v_pred": 33, "safety_penalty": 1}, device=dev)
+        K4 = 40
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K4)]
+        for k in range(5):
+            pred.predict(X4, want_vhat=False, want_penalty=False, sink=ring)
+        for k in range(K4):
+            flush.zero_()
+            ev4[k][0].record(stream); pred.predict(X4, want_vhat=False, want_penalty=False, sink=ring); ev4[k][1].record(stream)
+        torch.cuda.synchronize()
+        ms4 = statistics.median(a.elapsed_time(b) for a, b in ev4)
+        b4 = 66 * 4 + 33 * 4 + 4                                  # X row in, Vhat row + penalty into the ring
+        config4 = {"workload": "predictor_penalty_to_replay_ring_262144_envs (BASELINE config 4)", "value": E4 / (ms4 * 1e-3),
+                   "unit": "envs/s", "kernel": "k_predict (tcgen05 kind::tf32, 3xTF32, A operand in TMEM)", "kernel_ms_median": ms4,
+                   "bytes_per_env": b4, "roofline_frac": b4 * E4 / (ms4 * 1e-3) / 1e9 / peaks()[0], "steps": K4}
+        ring.close()
+
     t = torch.tensor([dev_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -377,6 +407,8 @@ def main():
             line["step_plus_get_obs_env_steps_per_s"] = obs_extra
         if config3 is not None:
             line["config3"] = config3
+        if config4 is not None:
+            line["config4"] = config4
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_rate(prof, E, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -179,28 +179,6 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
     const int row = tid & (PRED_M - 1);                                 // env row of the tile (both groups)
     const int64_t n_tiles = (prm.n + PRED_M - 1) / PRED_M;
 
-    // ---- one-time setup: barriers, TMEM, weights, zero K padding
-    if (tid == 0) {
-        for (int s = 0; s < N_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
-        mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1);
-        mbar_init(bar_free0, EPI_THREADS); mbar_init(bar_free0 + 8, EPI_THREADS);
-        mbar_init(bar_w, 1);
-        mbar_init(bar_a0, PROD_THREADS); mbar_init(bar_a0 + 8, PROD_THREADS);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_w, 2 * B_BYTES);                             // weights: one bulk copy, awaited before the first MMA
-        tma_load_1d(smem_u32(Bsm), prm.B, 2 * B_BYTES, bar_w);
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (tid < PRED_N) bias[tid] = prm.bias[tid];
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
     auto rows_of = [&](int64_t tl) -> int { const int64_t r = prm.n - tl * PRED_M; return (int)(r < PRED_M ? r : PRED_M); };
     auto tma_ok = [&](int64_t tl) -> bool { return ((rows_of(tl) * N_IN * 4) & 15) == 0; };
     // this CTA's tiles: blockIdx.x + k * gridDim.x, k = 0 .. n_my - 1 (the grid never exceeds the tile count)
@@ -216,6 +194,29 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
         mbar_expect_tx(bar, bytes);
         tma_load_1d(smem_u32(smem + OFF_STAGE + s * STAGE_BYTES), prm.X + tl * (int64_t)(PRED_M * N_IN), bytes, bar);
     };
+    // ---- one-time setup: barriers, TMEM, weights; the first TMA loads are issued before anything else
+    if (tid == 0) {
+        for (int s = 0; s < N_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
+        mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1);
+        mbar_init(bar_free0, EPI_THREADS); mbar_init(bar_free0 + 8, EPI_THREADS);
+        mbar_init(bar_w, 1);
+        mbar_init(bar_a0, PROD_THREADS); mbar_init(bar_a0 + 8, PROD_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, 2 * B_BYTES);                             // weights: one bulk copy, awaited before the first MMA
+        tma_load_1d(smem_u32(Bsm), prm.B, 2 * B_BYTES, bar_w);
+        for (int k = 0; k < N_STAGES && k < n_my; ++k) issue(k);        // the first X tiles travel during the rest of the setup
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < PRED_N) bias[tid] = prm.bias[tid];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
     // one tile's MMAs: 9 k-steps x 3 products (hi*hi + lo*hi + hi*lo), A from TMEM buffer `ab`
     auto mma_tile = [&](uint32_t acc, uint32_t ab) {
         const uint32_t b_hi = smem_u32(Bsm), b_lo = b_hi + B_BYTES;
@@ -232,9 +233,6 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) k_predict(const PredParams pr
 
     if (warp == MMA_WARP) {
         // =============================================================== MMA warp: TMA issue, tcgen05.mma issue
-        if (elect_one())
-            for (int k = 0; k < N_STAGES && k < n_my; ++k) issue(k);
-        __syncwarp();
         for (int k = 0; k < n_my; ++k) {
             const int b = k & 1;
             mbar_wait(bar_a0 + 8 * b, (uint32_t)((k >> 1) & 1));        // A buffer b holds tile k; its staging buffer is read
