@@ -10,11 +10,11 @@
 //
 // Kernel k_predict: one persistent CTA per SM (17 warps), 128-env tiles, WARP-SPECIALISED so that the
 // phases of consecutive tiles overlap.  The op is HBM-bound by shape (K = 66, N = 33: ~11 flop/B); the
-// job of the kernel is to keep four tiles of X in flight per SM while everything else hides underneath,
+// job of the kernel is to keep five tiles of X in flight per SM while everything else hides underneath,
 // and to keep shared-memory traffic (the second bound: 128 B/clk/SM) to the X tile and the Vhat tile.
 //   TMA/MMA warp 16 (one elected thread)
 //     1. TMA: `cp.async.bulk` brings a tile's X rows (128 x 66 fp32 = 33 792 contiguous bytes) into one
-//        of FOUR staging buffers, completion on an mbarrier; a buffer is refilled (four tiles ahead) as
+//        of FIVE staging buffers, completion on an mbarrier; a buffer is refilled (five tiles ahead) as
 //        soon as every producer has read it.
 //     3. tcgen05.mma (kind::tf32, M=128, N=48, K=8 per instruction; 9 k-steps x 3 products
 //        hi*hi + lo*hi + hi*lo) with the A OPERAND IN TMEM and the weights (hi and lo parts, UMMA K-major
@@ -35,7 +35,7 @@
 //        output (a wrapping or unaligned segment falls back to a coalesced store loop).
 // TMEM map (512 columns): accumulators at 0 and 64, A buffers at 128 and 272 (hi 72 | lo 72 columns).
 // The weights arrive by one bulk copy that overlaps the first X tiles (own mbarrier).  The groups meet
-// only through mbarriers (full[4], a_ready[2], mma_done[2], tmem_free[2]); the epilogue synchronises
+// only through mbarriers (full[5], a_ready[2], mma_done[2], tmem_free[2]); the epilogue synchronises
 // internally with a named barrier; every wait is bounded (trap, never a hung GPU).
 #include <cmath>
 #include <cstring>
@@ -55,11 +55,11 @@ constexpr int N_IN = 66, N_OUT = 33;
 constexpr uint32_t B_BYTES = PRED_KC * PRED_N * 16;          // 13 824
 constexpr uint32_t STAGE_BYTES = PRED_M * N_IN * 4;          // 33 792
 constexpr uint32_t OFF_BHI = 0, OFF_BLO = OFF_BHI + B_BYTES;
-constexpr int N_STAGES = 4;                                  // X tiles in flight per SM (4 x 33 KB covers the HBM latency)
+constexpr int N_STAGES = 5;                                  // X tiles in flight per SM (5 x 33 KB covers the HBM latency)
 constexpr uint32_t OFF_STAGE = OFF_BLO + B_BYTES;
 constexpr uint32_t OFF_OUT = OFF_STAGE + N_STAGES * STAGE_BYTES;   // [128][33] fp32
 constexpr uint32_t OFF_BIAS = OFF_OUT + PRED_M * N_OUT * 4;
-constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[4], mma_done[2], tmem_free[2], weights, a_ready[2]
+constexpr uint32_t OFF_BAR = OFF_BIAS + PRED_N * 4;          // full[5], mma_done[2], tmem_free[2], weights, a_ready[2]
 constexpr uint32_t OFF_PEN = OFF_BAR + 12 * 8;                // [2][128] fp64 penalty partials (column halves)
 constexpr uint32_t OFF_TMEM = OFF_PEN + 2 * PRED_M * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
