@@ -240,8 +240,8 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     CREATE_TRY(cudaMemset(h->d_V, 0, (size_t)n_envs * nb * 8));
     CREATE_TRY(cudaMalloc(&h->d_setp, (size_t)n_envs * 4 * na * 8));
     CREATE_TRY(cudaMemset(h->d_setp, 0, (size_t)n_envs * 4 * na * 8));
-    CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_envs * na * H * 6 * 8));
-    CREATE_TRY(cudaMemset(h->d_hist, 0, (size_t)n_envs * na * H * 6 * 8));
+    CREATE_TRY(cudaMalloc(&h->d_hist, (size_t)n_envs * H * FP_HIST_SLOT * 8));
+    CREATE_TRY(cudaMemset(h->d_hist, 0, (size_t)n_envs * H * FP_HIST_SLOT * 8));
     {   // observation / state kernels are streaming kernels: a full SM worth of warps (8 CTAs of 256 threads)
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

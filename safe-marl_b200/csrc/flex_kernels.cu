@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
         const int32_t cnt = (int32_t)(uint32_t)hh;
         const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);   // row currently loaded (Q1)
-        double* hist = prm.hist + e * (int64_t)(na * H * 6);
+        double* hist = prm.hist + e * (int64_t)(H * FP_HIST_SLOT);
         // current 6-vector per agent (:376-384): lanes 0 .. 6*na-1
         const int slot = cnt % H;
         double cur = 0.0;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
             else if (f == 3) cur = prm.V[e * c.nb + col + 1];
             else if (f == 4) cur = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);
             else cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
-            if (prm.push) hist[(slot * na + i) * 6 + f] = cur;
+            if (prm.push) hist[slot * FP_HIST_SLOT + i * 6 + f] = cur;
         }
         s_cur[warp][lane] = cur;
         __syncwarp();
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs(const ObsParams prm) {
             double x;
             if (k < 0) x = 0.0;
             else if (k == cnt) x = s_cur[warp][i * 6 + f];
-            else x = hist[((k % H) * na + i) * 6 + f];
+            else x = hist[(k % H) * FP_HIST_SLOT + i * 6 + f];
             out[o] = (OutT)x;
         }
         __syncwarp();
@@ -386,9 +386,10 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm
         if (lane < 6 * na) {
             if (f == 3) cur = prm.V[e * c.nb + prm.agent_col[i] + 1];
             else if (f == 5) cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
-            prm.hist[e * (int64_t)(na * H * 6) + ((cnt % H) * na + i) * 6 + f] = cur;       // lanes 0..6na-1: one contiguous run
             obsm[(e * na + i) * (int64_t)(3 * H * 6) + w * 6 + f] = (float)cur;
         }
+        // the whole warp writes the aligned 256-byte slot (lane = 6 i + f; the pad lanes write zeros): full sectors
+        prm.hist[e * (int64_t)(H * FP_HIST_SLOT) + (cnt % H) * FP_HIST_SLOT + lane] = (lane < 6 * na) ? cur : 0.0;
         __syncwarp();
         if (lane == 0) rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
     }
@@ -430,7 +431,7 @@ __global__ void k_obsm_rebuild(const ObsParams prm, float* __restrict__ obsm) {
         const int r = (int)(i - e * per_env), a = r / (H * 6), r2 = r - a * (H * 6), sl = r2 / 6, f = r2 - 6 * sl;
         const int32_t cnt = (int32_t)(uint32_t)prm.rec[e * FP_REC_STRIDE + FP_REC_HIST];
         const int k = cnt - H + sl;                // push index of window slot sl
-        const float x = (k < 0) ? 0.f : (float)prm.hist[e * (int64_t)per_env + ((k % H) * na + a) * 6 + f];
+        const float x = (k < 0) ? 0.f : (float)prm.hist[e * (int64_t)(H * FP_HIST_SLOT) + (k % H) * FP_HIST_SLOT + a * 6 + f];
         obsm[(e * na + a) * (int64_t)(3 * H * 6) + sl * 6 + f] = x;
     }
 }

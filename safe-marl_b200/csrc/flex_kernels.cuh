@@ -14,6 +14,10 @@
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_PF = 2 };
 
+// fp64 history ring: one slot = the agents' 6-vectors (<= 30 doubles) padded to 32 doubles = 256 bytes, so that a
+// push writes whole, aligned 32-byte sectors (a partial sector costs a DRAM read-modify-write under ECC)
+#define FP_HIST_SLOT 32
+
 struct EnvParams {
     DevCfg c;
     const DevTopo* topo;
@@ -27,7 +31,7 @@ struct EnvParams {
     const double* OBSROW;
     // fused observation push of step(..., return_obs) (thread kernels): fp64 history ring, fp32 mirror ring,
     // ring slot of this push (obs_push == 0: off)
-    double* hist; float* obsm; int32_t obs_push; int32_t obs_q;
+    double* hist; float* obsm; int32_t obs_push; int32_t obs_q;   // hist: [N][H][FP_HIST_SLOT] doubles
     // per-env state
     uint64_t* rec; double* V; double* setp;
     double* pfl; double* qfl; double* isq;       // optional line-flow dump (nullptr = off)
