@@ -1,4 +1,5 @@
-"""Driver for an ncu capture of the fused step+observation kernel: 12 L2-flushed calls of step(return_obs=True)\non 131 072 envs (ncu -k regex:k_env_t -s 9 -c 1 ... python tools/profile_step_obs.py)."""
+"""Driver for an ncu capture of the fused step+observation kernel: 12 L2-flushed calls of step(return_obs=True)
+on 131 072 envs (ncu -k regex:k_env_t -s 9 -c 1 ... python tools/profile_step_obs.py)."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "safe-marl_b200")]
