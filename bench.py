@@ -397,7 +397,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(E), "kernel": {"thread": "k_env_t<STEP>", "pair": "k_env_p<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
                          "kernel_ms_median": kern_ms, "peak_source": peak_src,
-                         "note": "not HBM-bound: 17 fp64 ops x 32 lines x 6-7 one-pass sweeps + the final pass + the setpoint "
+                         "note": "not HBM-bound: 17 fp64 ops x 32 lines x ~6 one-pass sweeps (a warp runs the maximum of its 32 envs; mean 5.2) + the final pass + the setpoint "
                                  "arithmetic = ~4400 fp64 lane-ops per env-step, which cap the kernel at ~3.9e9 env-steps/s "
                                  "on the fp64 pipe (59 lane-ops/clk/SM measured), i.e. 75 % of this HBM roofline at best; "
                                  "see DESIGN.md section 3"},
