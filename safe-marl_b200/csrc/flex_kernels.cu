@@ -443,23 +443,34 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_state(const ObsParams prm) {
     const int na = c.na, nl = c.nl, nb = c.nb;
     const int W = 3 * nb + 2 * na + 1;
     const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
-    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+    // one element of the state vector of env e (row in force `row`): [P(nb) | Q(nb) | Ppv(na) | V(nb) | price | E(na)]
+    auto fetch = [&](int64_t e, const uint64_t* rec, int64_t row, int o) -> double {
+        int r = o;
+        if (r < nb) return (r == 0) ? 0.0 : __ldg(prm.P + row * nl + r - 1);                // :361
+        if ((r -= nb) < nb) return (r == 0) ? 0.0 : __ldg(prm.Q + row * nl + r - 1);        // :362
+        if ((r -= nb) < na) return __ldg(prm.PVP + row * FP_PVP_STRIDE + r);                // :363
+        if ((r -= na) < nb) return prm.V[e * nb + r];                                       // :364
+        if ((r -= nb) < 1) return __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);      // :365
+        return __longlong_as_double((long long)rec[FP_REC_E_CUR + (r - 1)]);                // :366
+    };
+    // the (start, step) word of the NEXT env of this warp is requested before the current env's loads, and the
+    // four loads a lane owns (W <= 128) are issued together: the kernel is a chain of dependent DRAM round trips
+    int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+    uint64_t tm = (e < prm.n) ? prm.rec[e * FP_REC_STRIDE + FP_REC_TIME] : 0ull;
+    for (; e < prm.n; e += warps_total) {
         const uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
-        const uint64_t tm = rec[FP_REC_TIME];
+        const int64_t en = e + warps_total;
+        const uint64_t tm_next = (en < prm.n) ? prm.rec[en * FP_REC_STRIDE + FP_REC_TIME] : 0ull;
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
         const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);
         OutT* out = reinterpret_cast<OutT*>(prm.out) + e * (int64_t)W;
-        for (int o = lane; o < W; o += 32) {
-            double x;
-            int r = o;
-            if (r < nb) x = (r == 0) ? 0.0 : __ldg(prm.P + row * nl + r - 1);               // :361
-            else if ((r -= nb) < nb) x = (r == 0) ? 0.0 : __ldg(prm.Q + row * nl + r - 1);  // :362
-            else if ((r -= nb) < na) x = __ldg(prm.PVP + row * FP_PVP_STRIDE + r);          // :363
-            else if ((r -= na) < nb) x = prm.V[e * nb + r];                                 // :364
-            else if ((r -= nb) < 1) x = __ldg(prm.PVP + row * FP_PVP_STRIDE + FP_PVP_PRICE);// :365
-            else { r -= 1; x = __longlong_as_double((long long)rec[FP_REC_E_CUR + r]); }    // :366
-            out[o] = (OutT)x;
-        }
+        double x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int o = lane + 32 * j; x[j] = (o < W) ? fetch(e, rec, row, o) : 0.0; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int o = lane + 32 * j; if (o < W) out[o] = (OutT)x[j]; }
+        for (int o = lane + 128; o < W; o += 32) out[o] = (OutT)fetch(e, rec, row, o);      // feeders wider than 128 entries
+        tm = tm_next;
     }
 }
 
