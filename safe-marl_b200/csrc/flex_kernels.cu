@@ -372,9 +372,16 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int na = c.na, H = c.history;
     const int64_t warps_total = (int64_t)gridDim.x * WARPS_PER_CTA;
-    for (int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; e < prm.n; e += warps_total) {
+    // the record words of the warp's NEXT env are requested before the current env's dependent loads (the kernel is
+    // a chain of DRAM round trips: record -> row -> packed observation row)
+    int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+    uint64_t tm = 0ull, hh = 0ull;
+    if (e < prm.n) { tm = prm.rec[e * FP_REC_STRIDE + FP_REC_TIME]; hh = prm.rec[e * FP_REC_STRIDE + FP_REC_HIST]; }
+    for (; e < prm.n; e += warps_total) {
         uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
-        const uint64_t tm = rec[FP_REC_TIME], hh = rec[FP_REC_HIST];
+        const int64_t en = e + warps_total;
+        uint64_t tm_next = 0ull, hh_next = 0ull;
+        if (en < prm.n) { tm_next = prm.rec[en * FP_REC_STRIDE + FP_REC_TIME]; hh_next = prm.rec[en * FP_REC_STRIDE + FP_REC_HIST]; }
         const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
         const int32_t cnt = (int32_t)(uint32_t)hh;
         const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);   // row currently loaded (Q1)
@@ -392,6 +399,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_obs_push(const ObsParams prm
         prm.hist[e * (int64_t)(H * FP_HIST_SLOT) + (cnt % H) * FP_HIST_SLOT + lane] = (lane < 6 * na) ? cur : 0.0;
         __syncwarp();
         if (lane == 0) rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
+        tm = tm_next; hh = hh_next;
     }
 }
 

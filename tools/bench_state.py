@@ -16,3 +16,9 @@ for k in range(30):
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record(); st = env.get_state(); s1.record(); torch.cuda.synchronize(); ts.append(s0.elapsed_time(s1))
 print("get_state us", float(np.median(ts)) * 1e3, tuple(st.shape), st.dtype)
+ts = []
+for k in range(30):
+    flush.zero_()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(); ob = env.get_obs(); s1.record(); torch.cuda.synchronize(); ts.append(s0.elapsed_time(s1))
+print("get_obs (push + window view) us", float(np.median(ts)) * 1e3, tuple(ob.shape), ob.dtype)
