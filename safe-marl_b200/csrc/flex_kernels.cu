@@ -417,13 +417,16 @@ __global__ void k_obsm_clear(float* __restrict__ obsm, const uint8_t* __restrict
 
 // End of the ring: copy the last H-1 entries (slots 2H+1 .. 3H-1) of every agent row to slots 0 .. H-2.
 __global__ void k_obsm_compact(float* __restrict__ obsm, int64_t rows, int H) {
-    const int per = (H - 1) * 6;
+    // 8-byte pieces: entries are 6 floats, so the row pitch (18 H floats), the source offset ((2 H + 1) * 6) and the
+    // run length ((H - 1) * 6) are all even
+    const int per = (H - 1) * 3;
     const int64_t total = rows * per;
+    float2* o2 = reinterpret_cast<float2*>(obsm);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / per;
         const int k = (int)(i - r * per);
-        float* ring = obsm + r * (int64_t)(3 * H * 6);
-        ring[k] = ring[(2 * H + 1) * 6 + k];
+        float2* ring = o2 + r * (int64_t)(3 * H * 3);
+        ring[k] = ring[(2 * H + 1) * 3 + k];
     }
 }
 
