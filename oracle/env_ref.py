@@ -215,6 +215,24 @@ class RefFlexEnv:
     def manual_reset(self, day, hour, interval):                                    # :157-239
         return self._reset_common(lambda: (day, hour, interval))
 
+    def reset_with(self, start, e0, a0):
+        """reset() with the draws handed in (test hook): episode starting at dataset row `start`, initial ESS
+        energies `e0`, initial actions `a0` -- what the reference draws at :85-87, :100, :103."""
+        class _Given:
+            def __init__(self, e0, a0):
+                self.e0, self.a0 = list(np.asarray(e0, dtype=np.float64)), np.asarray(a0, dtype=np.float64)
+
+            def uniform(self, low=0.0, high=1.0, size=None):
+                return self.a0.copy() if size is not None else self.e0.pop(0)
+        per_day = 24 * (60 // self.time_delta)
+        day, rem = divmod(int(start), per_day)
+        hour, interval = divmod(rem, 60 // self.time_delta)
+        keep, self.rng = self.rng, _Given(e0, a0)
+        try:
+            return self._reset_common(lambda: (day, hour, interval))
+        finally:
+            self.rng = keep
+
     # --------------------------------------------------------------------- step
     def step(self, actions):                                                        # :241-356
         G, A = self.base_powergrid, self.args

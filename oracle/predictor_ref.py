@@ -1,10 +1,12 @@
 """fp64 restatement of the safety-signal voltage predictor and the safety penalty (oracle side).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY: fit unpinned -- the reference's training data
-(data/net_power_inputs.csv, data/bus_voltages_outputs.csv) are Git-LFS pointers and its fitted
-model is not shipped; what is pinned here is the *pipeline* -- scikit-learn's own MinMaxScaler /
-LinearRegression run in this container on scenarios generated the way the reference generates
-them, with the oracle power flow standing in for IPOPT.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY: pinned on the reference's own scripts --
+tests/golden/ref_predictor.npz holds the scenarios, the fitted regressor, the (unsaved) scalers and the
+predictions produced by safety_signal/data_generation.py and train_safety_signal_model.py executed
+unchanged (tests/golden/make_ref_golden.py; file I/O intercepted, Newton behind the Pyomo stand-in), and
+tests/test_oracle_predictor.py checks this restatement against them: scenarios bit for bit, voltages
+1e-10, predictions 1e-9.  Not pinned: the reference's shipped training data (Git-LFS pointers) and
+scikit-learn 1.5.2 vs the version in this image.
 
   generate_scenarios   safety_signal/data_generation.py:27-58  (+-30 % loads -> simplified PF -> V)
   fit_pipeline         safety_signal/train_safety_signal_model.py:33-46,73

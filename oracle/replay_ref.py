@@ -3,6 +3,10 @@
 TEST INFRASTRUCTURE (see oracle/__init__.py).  A Python list FIFO exactly like the reference:
 add_experience pops the oldest entry when full (:23-27), get_batch returns `batch_size`
 CONSECUTIVE entries from a uniformly drawn start (:14-21), clear empties it (:29-30).
+PARITY: pinned -- tests/golden/ref_replay.npz records the reference class itself (imported from
+utils/replay_buffer.py by tests/golden/make_ref_golden.py) under a sequence of adds and seeded
+get_batch calls; tests/test_oracle_predictor.py replays it here, tests/test_gpu_predictor.py on the
+device ring.
 """
 import numpy as np
 

@@ -15,6 +15,7 @@ only owns device memory and the stream.  Output tensors are allocated once and o
 by the next call of the same verb.
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -22,7 +23,7 @@ import torch
 from . import _lib, sharding
 from .config import convert, make_fp_config, normalize_args
 from .network import Network, create_network
-from .profiles import Profiles, synthetic_profiles
+from .profiles import Profiles, csv_profiles_available, load_csv_profiles, synthetic_profiles
 
 
 def _ptr(t):
@@ -68,9 +69,19 @@ class BatchedFlexProvisionEnv:
         _lib.check(self._lib.fp_create(C.byref(self._cfg), self.n_envs, dev_index, C.byref(self._h)),
                    None, "fp_create")
         self.profiles = None
-        self.load_profiles(profiles if profiles is not None else
-                           synthetic_profiles(self.network, self.n_agents, seed=0,
-                                              pv_scale=self.args_dict["pv_scale"]))
+        if profiles is None:
+            # the reference's __init__ loads the four CSVs under data_path (:55-58); they ship as Git-LFS
+            # pointers, so a checkout without the payloads has nothing to load -- say so instead of
+            # silently training on made-up data
+            data_path = self.args_dict.get("data_path")
+            if csv_profiles_available(data_path):
+                profiles = load_csv_profiles(data_path, self.args_dict)
+            else:
+                warnings.warn(f"no profile CSVs under data_path={data_path!r} (pv_active/load_active/load_reactive/"
+                              "prices.csv missing or Git-LFS pointers): using SYNTHETIC profiles of the bundled "
+                              "data's shape; pass profiles= or point data_path at the real files", stacklevel=2)
+                profiles = synthetic_profiles(self.network, self.n_agents, seed=0, pv_scale=self.args_dict["pv_scale"])
+        self.load_profiles(profiles)
         N, na, nb = self.n_envs, self.n_agents, self.n_bus
         dev = self.device
         self._reward = torch.empty(N, dtype=torch.float64, device=dev)

@@ -6,8 +6,11 @@ do not ship with the repository; when they are not readable the public IEEE 33-b
 (Baran & Wu 1989) is used, which is what those files describe.
 """
 import os
+import warnings
 
 import numpy as np
+
+from .profiles import _is_lfs_pointer
 
 # (FROM, TO, R ohm, X ohm, Imax A) -- Baran & Wu 33-bus; Imax is a synthetic rating
 # (400 A head of the trunk, 200 A elsewhere): the reference's column is not public.
@@ -48,10 +51,14 @@ def create_network(env_args, data_path=None):
     """Same return dict as utils/create_net.py:27-38."""
     nodes = lines = None
     if data_path is not None:
-        try:
-            nodes, lines = _read_xlsx_tables(data_path)
-        except Exception:       # LFS pointer / openpyxl missing / file absent
-            nodes = lines = None
+        files = [os.path.join(data_path, n) for n in ("Nodes_33.xlsx", "Lines_33.xlsx")]
+        if all(os.path.isfile(f) and not _is_lfs_pointer(f) for f in files):
+            nodes, lines = _read_xlsx_tables(data_path)     # real files: a read error is the caller's to see
+        else:
+            # absent, or the Git-LFS pointers the repository ships: the public case the files describe,
+            # with SYNTHETIC line ratings (the Imax column is not public)
+            warnings.warn(f"Nodes_33.xlsx / Lines_33.xlsx not readable under {data_path!r}: using the public "
+                          "IEEE 33-bus case (Baran & Wu 1989) with synthetic Imax ratings", stacklevel=2)
     if nodes is None:
         nodes, lines = _ieee33_tables()
     s_nom, v_nom = env_args["s_nom"], env_args["v_nom"]

@@ -56,8 +56,31 @@ def synthetic_profiles(network, n_agents=5, T=105216, seed=0, pv_scale=0.15):
     return Profiles(P, Q, PV, price, 15)
 
 
+CSV_NAMES = ('pv_active.csv', 'load_active.csv', 'load_reactive.csv', 'prices.csv')
+
+
+def _is_lfs_pointer(path):
+    try:
+        with open(path, 'rb') as f:
+            return f.read(40).startswith(b'version https://git-lfs')
+    except OSError:
+        return False
+
+
+def csv_profiles_available(data_path):
+    """True when the four profile CSVs the reference loads (:431-465) exist under data_path as real files
+    (the bundled ones are Git-LFS pointers until `git lfs pull` has run)."""
+    if not data_path:
+        return False
+    paths = [os.path.join(data_path, n) for n in CSV_NAMES]
+    return all(os.path.isfile(p) and not _is_lfs_pointer(p) for p in paths)
+
+
 def load_csv_profiles(data_path, args):
-    """The reference's four loaders (:431-465) + resample_data (:467-471)."""
+    """The reference's four loaders (:431-465) + resample_data (:467-471): read_csv, first column -> time index,
+    scale, resample(sample_interval).mean(), linear interpolate.  The reference keeps four frames of possibly
+    different lengths and slices all of them with the same row offsets (:473-547); here they are cut to the
+    shortest one, which is every row the reference can address in all four."""
     import pandas as pd
 
     def load(name, scale):
@@ -73,4 +96,5 @@ def load_csv_profiles(data_path, args):
     q = load('load_reactive.csv', args["reactive_scale"])
     price = load('prices.csv', 1.0)
     delta = (pv.index[1] - pv.index[0]).seconds // 60          # :422
-    return Profiles(p.values, q.values, pv.values, price.values[:, 0], delta)
+    T = min(len(pv), len(p), len(q), len(price))
+    return Profiles(p.values[:T], q.values[:T], pv.values[:T], price.values[:T, 0], delta)

@@ -173,3 +173,45 @@ def test_pipeline_every_row_all_tile_shapes(env, pred, cuda, n):
     got = buf.get_batch(n + 5, start=0)
     assert torch.equal(got["v_pred"][idx], vhat) and torch.equal(got["safety_penalty"][idx, 0], pen.float())
     buf.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# PINNED on the reference's own scripts (tests/golden/ref_predictor.npz, ref_replay.npz: made by
+# safety_signal/data_generation.py, train_safety_signal_model.py and utils/replay_buffer.py themselves,
+# tests/golden/make_ref_golden.py)
+def test_reference_fit_predictions(env, cuda):
+    """k_predict with the REFERENCE'S regressor + scalers against sklearn's predictions of all 1000 scenarios the
+    reference generated, and against the scaled predictions its training script computed on its test split."""
+    from flexgpu.predictor import VoltagePredictor
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_predictor.npz"))
+    p = VoltagePredictor.from_linear_model(env, g["coef"], g["intercept"], g["x_scale"], g["x_min"], g["y_scale"], g["y_min"])
+    vhat, pen = p.predict(torch.from_numpy(g["X"].astype(np.float32)).to(cuda))
+    V = vhat.cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(V - g["V_pred"])) < 2e-6               # 1e-6 kernel tolerance + the fp32 rounding of the inputs
+    assert np.max(np.abs(V - g["Y"])) < 5e-3                    # ... and it does predict the power-flow voltages
+    Xte = ((g["X_test_scaled"] - g["x_min"]) / g["x_scale"]).astype(np.float32)
+    vte, _ = p.predict(torch.from_numpy(Xte).to(cuda))
+    scaled = vte.cpu().numpy().astype(np.float64) * g["y_scale"] + g["y_min"]
+    assert np.max(np.abs(scaled[:, 1:] - g["Y_pred_scaled"][:, 1:]) / g["y_scale"][1:]) < 2e-6   # back in p.u.
+    want = predictor_ref.slack_penalty(V)
+    assert np.allclose(pen.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+
+
+def test_reference_replay_buffer_sequence(cuda):
+    """DeviceReplayBuffer driven with the adds and the numpy seed that drove the reference's TransReplayBuffer:
+    the same window starts (np.random.choice, :18) and the same transitions in every batch, FIFO eviction included."""
+    from flexgpu.predictor import DeviceReplayBuffer
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_replay.npz"))
+    buf = DeviceReplayBuffer(int(g["size"][0]), {"row": 7}, device=cuda)
+    rows = torch.from_numpy(g["rows"]).to(cuda)
+    np.random.seed(int(g["seed"][0]))
+    n_added = 0
+    for k, (n_target, batch) in enumerate(g["events"]):
+        if n_target > n_added:
+            buf.add_experience({"row": rows[n_added:n_target]}); n_added = int(n_target)
+        got = buf.get_batch(int(batch))["row"].cpu().numpy()
+        assert [int(x) for x in got[:, 0]] == list(g["ids"][k][:batch]), k
+        assert np.array_equal(got, g["rows"][g["ids"][k][:batch]])
+    assert len(buf) == len(g["final_ids"])
+    assert [int(x) for x in buf.get_batch(len(buf), start=0)["row"][:, 0].cpu().numpy()] == list(g["final_ids"])
+    buf.close()

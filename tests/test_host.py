@@ -113,3 +113,35 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["config"]["workload"].startswith("fused_env_step_2048_envs_per_gpu")
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_load_csv_profiles_equals_the_reference_loaders(tmp_path):
+    """flexgpu.load_csv_profiles against the output of the reference's own _load_*_data + resample_data
+    (flexibility_provision_env.py:431-471), which parsed the SAME csv text (tests/golden/make_ref_golden.py):
+    5-minute load / PV rows with missing stretches and hourly prices -> 15-minute means, up-sampling, linear
+    interpolation, the three scale factors."""
+    import os
+    from flexgpu.profiles import csv_profiles_available, load_csv_profiles
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_loaders.npz"))
+    assert not csv_profiles_available(str(tmp_path))
+    for name in ("pv_active", "load_active", "load_reactive", "prices"):
+        (tmp_path / f"{name}.csv").write_bytes(g["csv_" + name].tobytes())
+    assert csv_profiles_available(str(tmp_path))
+    args = dict(sample_interval="15min", demand_scale=float(g["demand_scale"][0]),
+                reactive_scale=float(g["reactive_scale"][0]), pv_scale=float(g["pv_scale"][0]))
+    prof = load_csv_profiles(str(tmp_path), args)
+    T = prof.T
+    assert T == min(len(g["P"]), len(g["price"])) and prof.time_delta == int(g["time_delta"][0])
+    assert np.array_equal(prof.P, g["P"][:T]) and np.array_equal(prof.Q, g["Q"][:T])
+    assert np.array_equal(prof.PV, g["PV"][:T]) and np.array_equal(prof.price, g["price"][:T])
+    assert not np.isnan(prof.P).any() and prof.n_days() >= int(g["pv_days"][0]) - 1
+    # the gap of a whole hour was filled by interpolation, the hourly prices were up-sampled
+    assert np.all(np.diff(prof.price[:5]) != 0)
+
+
+def test_lfs_pointer_is_not_mistaken_for_data(tmp_path):
+    from flexgpu.profiles import CSV_NAMES, csv_profiles_available
+    for n in CSV_NAMES:
+        (tmp_path / n).write_text("version https://git-lfs.github.com/spec/v1\noid sha256:0\nsize 1\n")
+    assert not csv_profiles_available(str(tmp_path))

@@ -262,3 +262,69 @@ def test_philox_draws_are_shard_invariant_and_in_range(fonet):
     assert a0.min() >= 0.0 and a0.max() < 1.0 and abs(a0.mean() - 0.5) < 0.05
     assert c_mirror.draw_random(fonet, 1234, 3, 1, 1000)[0] != a[3][0] or True         # episode changes the stream
     assert not np.array_equal(c_mirror.draw_random(fonet, 1234, 3, 1, 1000)[2], a[3][2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# The branches that make this a SAFE-MARL env, pinned on episodes produced by the reference's own code
+# (tests/golden/make_ref_golden.py): voltage violations in the reward (:685), the solver-failure
+# roll-back with -200 and termination (:314-337), and the 'safemaddpg' raw-action branch (:268-274).
+from _ref_episode import replay_reference_episode  # noqa: E402
+
+
+def mirror_adapter(fonet, g):
+    prof = dict(P=g['P'], Q=g['Q'], PV=g['PV'], price=g['price'])
+    mb = c_mirror.MirrorBatch(fonet, prof, 1)
+
+    def step(a):
+        r, d, info = mb.step(a)
+        return r[0], d[0], info[0]
+
+    def state():
+        return dict(V=mb.V[0], E=mb.E_cur[0], setp=mb.setp[0], state=mb.get_state()[0], vmask=mb.vmask[0], vcount=mb.vcount[0])
+    return (lambda e0, a0: mb.reset([0], e0, a0)), step, state, mb
+
+
+def test_reference_heavy_loading_episode_mirror(fonet):
+    """demand_scale = reactive_scale = 2.4: 872 voltage violations over 95 steps, voltage_penalty > 0 in 56."""
+    g = np.load(os.path.join(GOLD, "ref_env_heavy.npz"))
+    assert (g['info'][:, 5] > 0).sum() >= 50 and g['max_residual'].max() < 1e-11
+    reset, step, state, _ = mirror_adapter(fonet, g)
+    assert replay_reference_episode(g, reset, step, state) >= 800
+
+
+def test_reference_solver_failure_episode_mirror(fonet):
+    """Step 41 has no power-flow solution: the reference's except path ran (roll-back, -200, solver_failed, done)."""
+    g = np.load(os.path.join(GOLD, "ref_env_failure.npz"))
+    assert g['failed'][-1] and g['done'][-1] and not g['failed'][:-1].any() and g['reward'][-1] < -199
+    reset, step, state, mb = mirror_adapter(fonet, g)
+    replay_reference_episode(g, reset, step, state)
+    assert np.array_equal(g['V'][-1], g['V'][-2])                                          # the reference rolled back (:318)
+    assert (mb.flags[0] & 3) == 3 and mb.steps[0] == 42
+
+
+def test_reference_safemaddpg_episode_mirror(tree, args):
+    g = np.load(os.path.join(GOLD, "ref_env_safemaddpg.npz"))
+    fo = c_mirror.make_net(tree, args, args['buildings'], raw_actions=True)
+    reset, step, state, _ = mirror_adapter(fo, g)
+    replay_reference_episode(g, reset, step, state)
+    assert np.abs(g['actions'][:, 3::4]).max() > 0.05 and g['setp'][:, 3].min() < 0                 # raw q_pv went through unclipped
+
+
+@pytest.mark.parametrize("tag,alg", [("heavy", None), ("failure", None), ("safemaddpg", "safemaddpg")])
+def test_restatement_equals_reference_code_on_the_hard_episodes(tag, alg):
+    """The Python restatement (oracle/env_ref.py, Newton) against the reference's own episodes."""
+    g = np.load(os.path.join(GOLD, f"ref_env_{tag}.npz"))
+    a = dict(env_ref.DEFAULT_ARGS)
+    if alg:
+        a['alg'] = alg
+    # the constructor resets once at a random start (:69): give it a few days of rows to draw from
+    prof = {k: np.concatenate([g[k]] * 4) for k in ('P', 'Q', 'PV', 'price')}
+    env = env_ref.RefFlexEnv(a, ieee33.create_network(), prof, rng=np.random.RandomState(0))
+    env.reset_with(0, g['e0'], g['a0'])
+    assert np.max(np.abs(env._get_bus_v() - g['V0'])) < 1e-12
+    for t in range(len(g['reward'])):
+        r, d, info = env.step(g['actions'][t])
+        assert abs(r - g['reward'][t]) < 1e-12 and d == bool(g['done'][t])
+        assert bool(info.get('solver_failed', False)) == bool(g['failed'][t])
+        assert np.max(np.abs(env._get_bus_v() - g['V'][t])) < 1e-12
+        assert np.max(np.abs(env.get_state() - g['state'][t])) < 1e-12
