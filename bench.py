@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostics only)")
     ap.add_argument("--no-config4", action="store_true", help="skip the extra predictor (config 4) measurement at N=1")
     ap.add_argument("--no-obs", action="store_true", help="skip the extra step+get_obs measurement (rollout-loop cost)")
-    ap.add_argument("--variant", default="thread", choices=["thread", "warp", "pair"], help="kernel variant (see include/flexgpu.h)")
+    ap.add_argument("--variant", default="thread", choices=["thread", "warp"], help="kernel variant (see include/flexgpu.h)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -395,7 +395,7 @@ def main():
                     "steps": Ke, "api": "BatchedFlexProvisionEnv.step_host -> fp_step_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(E), "kernel": {"thread": "k_env_t<STEP>", "pair": "k_env_p<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
+                         "traffic": ncu_traffic(E), "kernel": {"thread": "k_env_t<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
                          "kernel_ms_median": kern_ms, "peak_source": peak_src,
                          "note": "not HBM-bound: 17 fp64 ops x 32 lines x ~6 one-pass sweeps (a warp runs the maximum of its 32 envs; mean 5.2) + the final pass + the setpoint "
                                  "arithmetic = ~4400 fp64 lane-ops per env-step, which cap the kernel at ~3.9e9 env-steps/s "

@@ -51,7 +51,7 @@ enum {
     FP_ENOMEM = -4
 };
 
-/* kernel variants (FpConfig.variant).  All compute the same DistFlow fixed point; THREAD/PAIR and
+/* kernel variants (FpConfig.variant).  All compute the same DistFlow fixed point; THREAD and
  * WARP differ in floating-point summation order (results agree to ~1e-12):
  *   THREAD  one CUDA thread per env, one-pass sweep with the currents in registers -- the
  *           throughput path; converges on max_k |P_k^2 + Q_k^2 - v_k l_k| < pf_tol (residual of the
@@ -59,10 +59,8 @@ enum {
  *           updates the currents once more after the test; default 1e-5 (errors against a Newton
  *           solution: V 1e-11, P/Q 6e-9, I 6e-8 p.u. -- the parity bar is 1e-6).
  *   WARP    one warp per env, lane = line, shuffle scans -- the lowest latency for tiny
- *           batches; converges on max |dv| <= pf_tol (squared voltage), default 1e-9.
- *   PAIR    two lanes per env (main feeder | laterals), IEEE 33-bus shape only; bit-identical to
- *           THREAD, twice the resident warps; measured slightly slower on B200. */
-enum { FP_VARIANT_THREAD = 0, FP_VARIANT_WARP = 1, FP_VARIANT_PAIR = 2 };
+ *           batches; converges on max |dv| <= pf_tol (squared voltage), default 1e-9. */
+enum { FP_VARIANT_THREAD = 0, FP_VARIANT_WARP = 1 };
 
 /* action dtypes accepted by fp_step */
 /* Action dtypes of fp_step / fp_step_host.  FP_F32_POLICY: raw fp32 policy outputs; the kernel

@@ -27,8 +27,6 @@ struct FpHandle {
     DevCfg dc;
     DevTopo topo;
     ThreadTopo tt;               // thread-per-env tables (by-value kernel parameter)
-    PairTopo pt;                 // pair-per-env tables (IEEE 33-bus shape only)
-    int pair = 0;                // 1: the thread variant runs the pair-per-env kernels
     int variant = FP_VARIANT_THREAD, shape = SHAPE_RUNTIME;
     int64_t n = 0;
     int device = 0;
@@ -213,7 +211,7 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     std::string err;
     int rc = build_topology(*cfg, h->topo, h->tt, h->shape, err);
     if (rc != FP_OK) { delete h; return fail(nullptr, rc, "fp_create: " + err); }
-    if (cfg->variant != FP_VARIANT_THREAD && cfg->variant != FP_VARIANT_WARP && cfg->variant != FP_VARIANT_PAIR) {
+    if (cfg->variant != FP_VARIANT_THREAD && cfg->variant != FP_VARIANT_WARP) {
         delete h; return fail(nullptr, FP_EINVAL, "fp_create: unknown kernel variant");
     }
     h->variant = cfg->variant;
@@ -247,26 +245,7 @@ int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->grid_obs = grid_for(n_envs, 8 * (sms > 0 ? sms : 1));
     }
-    // FP_VARIANT_PAIR: two lanes per env (flex_pair_kernels.cu), IEEE 33-bus shape only -- same results bit
-    // for bit; measured ~10 % slower than one thread per env on B200 (profiles/), kept as a selectable variant
-    h->pair = 0;
-    if (cfg->variant == FP_VARIANT_PAIR) {
-        if (h->shape != SHAPE_IEEE33) {
-            delete h; return fail(nullptr, FP_EINVAL, "fp_create: FP_VARIANT_PAIR needs the IEEE 33-bus feeder shape");
-        }
-        h->pair = 1; h->variant = FP_VARIANT_THREAD;              // shares the thread variant's host paths and mirror order
-    }
-    if (h->pair) {
-        pair_topo_from(h->tt, h->pt);
-        CREATE_TRY(pair_kernels_configure());
-        const int64_t ctas = (n_envs + 31) / 32;                  // two 16-env tiles (warps) per CTA
-        const int cap_step = pair_kernel_max_grid(MODE_STEP), cap_reset = pair_kernel_max_grid(MODE_RESET);
-        h->grid_step = (int)((ctas < cap_step) ? ctas : cap_step);
-        h->grid_reset = (int)((ctas < cap_reset) ? ctas : cap_reset);
-        h->grid_pf = pair_kernel_max_grid(MODE_PF);
-        h->stats_cap = 2 * cap_step;                               // one statistics row per warp
-        h->stats_rows = h->stats_cap * (1 + FP_HOST_CHUNKS);
-    } else if (h->variant == FP_VARIANT_THREAD) {
+    if (h->variant == FP_VARIANT_THREAD) {
         CREATE_TRY(thread_kernels_configure(FP_MAX_SLOTS));
         const int64_t tiles = (n_envs + 31) / 32;
         const int cap_step = thread_kernel_max_grid(MODE_STEP, h->tt.n_slots, h->shape);
@@ -343,7 +322,7 @@ int fp_load_profiles(FpHandle* h, const double* h_P, const double* h_Q, const do
     CUDA_TRY(h, cudaMalloc(&h->d_OBS, (size_t)T * FP_OBS_STRIDE * 8));
     CUDA_TRY(h, launch_pack_obsrow(h->d_P, h->d_Q, h->d_PVP, h->topo.agent_col, na, nl, T, h->d_OBS, 0));
     h->launches++;
-    if (h->variant == FP_VARIANT_THREAD && !h->pair) {   // (p, q) pairs in DFS lane order for the thread kernels
+    if (h->variant == FP_VARIANT_THREAD) {   // (p, q) pairs in DFS lane order for the thread kernels
         CUDA_TRY(h, cudaMalloc(&h->d_PQD, (size_t)T * nl * 16));
         CUDA_TRY(h, launch_pack_pq(h->d_P, h->d_Q, h->tt, T, h->d_PQD, 0));
         h->launches++;
@@ -381,11 +360,6 @@ static void set_translate(const FpHandle* h, EnvParams& p) {
 
 static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cudaStream_t st) {
     const int grid = (mode == MODE_STEP) ? h->grid_step : h->grid_reset;
-    if (h->pair) {
-        EnvParamsP pp;
-        pp.e = p; pp.t = h->pt;
-        return launch_env_p(mode, pp, grid, st);
-    }
     if (h->variant == FP_VARIANT_THREAD) {
         EnvParamsT pt;
         pt.e = p; pt.t = h->tt;
@@ -436,7 +410,7 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     EnvParams p; fill_env_params(h, p);
     p.actions = d_actions; p.act_f64 = (act_dtype == FP_F64);
     if (act_dtype == FP_F32_POLICY) {
-        if (h->variant == FP_VARIANT_THREAD && !h->pair) set_translate(h, p);      // fused into the step kernel
+        if (h->variant == FP_VARIANT_THREAD) set_translate(h, p);      // fused into the step kernel
         else {                                                                     // other variants: elementwise pre-pass
             const size_t cnt = (size_t)h->n * h->dc.na * 4;
             if (!h->d_act_xlat) CUDA_TRY(h, cudaMalloc(&h->d_act_xlat, cnt * 4));
@@ -466,7 +440,7 @@ static int enqueue_host_chunks(FpHandle* h, const void* h_actions, int act_dtype
     CUDA_TRY(h, cudaEventRecord(h->host_ev_in, st));
     for (int i = 0; i < FP_HOST_STREAMS; ++i) CUDA_TRY(h, cudaStreamWaitEvent(h->host_streams[i], h->host_ev_in, 0));
     const int cap = h->stats_cap;                                       // statistics rows of one launch
-    const int cap_grid = h->pair ? cap / 2 : cap;
+    const int cap_grid = cap;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t t0 = tiles * c / n_chunks, t1 = tiles * (c + 1) / n_chunks;
         const size_t e0 = (size_t)t0 * 32, e1 = ((size_t)t1 * 32 < n) ? (size_t)t1 * 32 : n, ne = e1 - e0;
@@ -483,10 +457,7 @@ static int enqueue_host_chunks(FpHandle* h, const void* h_actions, int act_dtype
         p.stats_partial = h->d_stats_partial + (size_t)(1 + c) * cap * FP_NSTATS;
         p.tile_begin = t0; p.tile_end = t1;
         const int grid = (int)((t1 - t0 < cap_grid) ? (t1 - t0) : cap_grid);
-        if (h->pair) {
-            EnvParamsP pp; pp.e = p; pp.t = h->pt;
-            CUDA_TRY(h, launch_env_p(MODE_STEP, pp, grid, s_k));
-        } else {
+        {
             EnvParamsT pt; pt.e = p; pt.t = h->tt;
             pt.e.bulk_io = bulk_io_ok(p);
             CUDA_TRY(h, launch_env_t(MODE_STEP, h->shape, pt, grid, s_k));
@@ -535,7 +506,7 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
         h->host_chunks = (k < 1) ? 1 : ((k > FP_HOST_CHUNKS) ? FP_HOST_CHUNKS : k);
     }
     const int n_chunks = h->host_chunks;
-    if (h->variant != FP_VARIANT_THREAD || (h->pair && act_dtype == FP_F32_POLICY) || n_chunks == 1 || tiles < 4 * n_chunks) {  // small batch / warp variant: one shot
+    if (h->variant != FP_VARIANT_THREAD || n_chunks == 1 || tiles < 4 * n_chunks) {  // small batch / warp variant: one shot
         CUDA_TRY(h, cudaMemcpyAsync(h->d_act_stage, h_actions, n * abpe, cudaMemcpyHostToDevice, st));
         int rc = fp_step(h, h->d_act_stage, act_dtype, h->d_reward_stage, h->d_done_stage,
                          h_info ? h->d_info_stage : nullptr, nullptr, stream);
@@ -568,7 +539,7 @@ int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_re
     // FLEXGPU_HOST_ZEROCOPY: 2 (default) = inputs and outputs, 1 = inputs only, 0 = staged chunk pipeline below
     // (measured at 131 072 envs: 294 / 310 / 310 us per step; the 10.5 MB of actions alone take 240 us by DMA)
     static const int zc_mode = std::getenv("FLEXGPU_HOST_ZEROCOPY") ? std::atoi(std::getenv("FLEXGPU_HOST_ZEROCOPY")) : 2;
-    if (all_pinned && zc_mode > 0 && !h->pair && act_dtype != FP_F64) {
+    if (all_pinned && zc_mode > 0 && act_dtype != FP_F64) {
         double* out_r = h_reward; uint8_t* out_d = h_done; double* out_i = h_info;
         if (zc_mode == 1) { out_r = h->d_reward_stage; out_d = h->d_done_stage; out_i = h_info ? h->d_info_stage : nullptr; }   // inputs only
         int rc = fp_step(h, h_actions, act_dtype, out_r, out_d, out_i, nullptr, stream);
@@ -689,7 +660,7 @@ int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_rew
     if (!h || !d_view) return FP_EINVAL;
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_obs: call fp_load_profiles first");
     // fused for the built-in feeder shape (the run-time-table kernels keep the two-launch form)
-    const bool fuse = (h->variant == FP_VARIANT_THREAD) && !h->pair && d_mask == nullptr && h->shape == SHAPE_IEEE33;
+    const bool fuse = (h->variant == FP_VARIANT_THREAD) && d_mask == nullptr && h->shape == SHAPE_IEEE33;
     if (!fuse) {                                   // other variants / masked steps: two launches, same result
         int rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, d_mask, stream);
         if (rc != FP_OK) return rc;
@@ -753,12 +724,7 @@ int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, 
     PfParams p;
     p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol;
     p.p = d_p; p.q = d_q; p.V = d_V; p.Pl = d_Pl; p.Ql = d_Ql; p.Isq = d_Isq; p.iters = d_iters; p.fail = d_fail;
-    if (h->pair) {
-        PfParamsP pp;
-        pp.p = p; pp.t = h->pt;
-        const int64_t ctas = (n + 31) / 32;
-        CUDA_TRY(h, launch_power_flow_p(pp, (int)((ctas < h->grid_pf) ? ctas : h->grid_pf), (cudaStream_t)stream));
-    } else if (h->variant == FP_VARIANT_THREAD) {
+    if (h->variant == FP_VARIANT_THREAD) {
         PfParamsT pt;
         pt.p = p; pt.t = h->tt;
         const int64_t tiles = (n + 31) / 32;

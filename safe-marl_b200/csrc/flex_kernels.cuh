@@ -71,22 +71,6 @@ struct EnvParamsT { EnvParams e; ThreadTopo t; };
 struct PfParamsT { PfParams p; ThreadTopo t; };
 enum { VARIANT_THREAD = 0, VARIANT_WARP = 1 };
 
-// pair-per-env kernels (flex_pair_kernels.cu, IEEE 33-bus shape): tables indexed by line POSITION
-// (role 0 = main feeder at 0..16, role 1 = laterals at 17..33 with two padding positions)
-struct PairTopo {
-    double R[34], X[34], Z2h[34], imax2[34];
-    int8_t pos_of_col[FP_NL], pos_of_lane[FP_NL], col_of_lane[FP_NL], agent_pos[8];
-    int32_t any_imax, nl;
-};
-struct EnvParamsP { EnvParams e; PairTopo t; };
-struct PfParamsP { PfParams p; PairTopo t; };
-cudaError_t launch_env_p(int mode, const EnvParamsP& prm, int grid, cudaStream_t st);
-cudaError_t launch_power_flow_p(const PfParamsP& prm, int grid, cudaStream_t st);
-cudaError_t pair_kernels_configure();
-int pair_kernel_max_grid(int mode);
-size_t pair_kernel_smem_bytes();
-void pair_topo_from(const ThreadTopo& t, PairTopo& p);
-
 cudaError_t launch_env_t(int mode, int shape, const EnvParamsT& prm, int grid, cudaStream_t st);
 cudaError_t launch_power_flow_t(int shape, const PfParamsT& prm, int grid, cudaStream_t st);
 cudaError_t thread_kernels_configure(int n_slots);

@@ -17,8 +17,8 @@ FP_INFO_STRIDE = 8
 FP_NSTATS = 16
 FP_REC_STRIDE = 16
 FP_F32, FP_F64, FP_F32_POLICY = 0, 1, 2
-VARIANT_THREAD, VARIANT_WARP, VARIANT_PAIR = 0, 1, 2
-VARIANTS = {"thread": VARIANT_THREAD, "warp": VARIANT_WARP, "pair": VARIANT_PAIR}
+VARIANT_THREAD, VARIANT_WARP = 0, 1
+VARIANTS = {"thread": VARIANT_THREAD, "warp": VARIANT_WARP}
 
 # record slots (include/flexgpu.h FP_REC_*)
 REC_E_INIT, REC_E_CUR, REC_CUM, REC_TIME, REC_HIST, REC_VMASK, REC_COUNTS, REC_LINES = 0, 5, 10, 11, 12, 13, 14, 15

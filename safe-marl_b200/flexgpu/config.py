@@ -21,7 +21,7 @@ DEFAULT_ENV_ARGS = dict(
 
 # Solver knobs that the reference leaves to IPOPT's defaults (utils/pf.py:101-102).
 DEFAULT_SOLVER_ARGS = dict(
-    kernel_variant="thread",  # "thread" (one thread per env, throughput) | "warp" (one warp per env) | "pair" (two lanes per env)
+    kernel_variant="thread",  # "thread" (one thread per env, throughput) | "warp" (one warp per env)
     pf_tol=None,        # None -> DEFAULT_PF_TOL[variant]; see DESIGN.md "convergence"
     pf_max_iter=32,     # exceeding it counts as solver failure (:314-337)
     fail_penalty=200.0,  # :336
@@ -30,11 +30,11 @@ DEFAULT_SOLVER_ARGS = dict(
 
 
 # thread variant: max |dl| (squared current) between sweeps; warp variant: max |dv| (squared voltage)
-# thread / pair: residual of the current row (pf.py:85-88) before the last update of the currents; that
+# thread: residual of the current row (pf.py:85-88) before the last update of the currents; that
 # update contracts it by another ~0.05, so 1e-5 leaves V / P,Q / I within 1e-11 / 6e-9 / 6e-8 p.u. of the
 # Newton solution (parity bar 1e-6) and saves the pass that 1e-6 would cost every warp (the slowest of its
 # 32 envs decides): 7.0 -> 6.0 passes per tile on the bench workload.  warp: max |dv|.
-DEFAULT_PF_TOL = {"thread": 1e-5, "warp": 1e-9, "pair": 1e-5}
+DEFAULT_PF_TOL = {"thread": 1e-5, "warp": 1e-9}
 
 
 def convert(dictionary):
@@ -81,7 +81,7 @@ def make_fp_config(args, network):
     c.pf_max_iter = int(args["pf_max_iter"])
     variant = args.get("kernel_variant", "thread")
     if variant not in _lib.VARIANTS:
-        raise ValueError("kernel_variant must be 'thread', 'warp' or 'pair'")
+        raise ValueError("kernel_variant must be 'thread' or 'warp'")
     c.variant = _lib.VARIANTS[variant]
     c.pf_tol = float(DEFAULT_PF_TOL[variant] if args.get("pf_tol") is None else args["pf_tol"])
     c.v_min, c.v_max = float(args["v_min"]), float(args["v_max"])

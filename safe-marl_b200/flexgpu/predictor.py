@@ -75,6 +75,9 @@ class DeviceReplayBuffer:
 
     def add_experience(self, trans):                                       # :23-27, n rows at once
         n = next(iter(trans.values())).shape[0]
+        if n > self.size:                      # more rows than the FIFO holds: all but the last `size` are popped again
+            trans = {k: v[n - self.size:] for k, v in trans.items()}
+            n = self.size
         pos = self.reserve(n)
         for k, v in trans.items():
             self.write(k, pos, v)

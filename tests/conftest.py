@@ -50,12 +50,10 @@ def fonets(tree, args):
     """C mirrors keyed by kernel variant name."""
     from oracle import c_mirror
     return {"thread": c_mirror.make_net(tree, args, args["buildings"], variant=c_mirror.VARIANT_THREAD),
-            "warp": c_mirror.make_net(tree, args, args["buildings"], variant=c_mirror.VARIANT_WARP),
-            # two lanes per env: the thread variant's arithmetic and order, hence the same mirror
-            "pair": c_mirror.make_net(tree, args, args["buildings"], variant=c_mirror.VARIANT_THREAD)}
+            "warp": c_mirror.make_net(tree, args, args["buildings"], variant=c_mirror.VARIANT_WARP)}
 
 
-@pytest.fixture(params=["thread", "warp", "pair"])
+@pytest.fixture(params=["thread", "warp"])
 def variant(request):
     return request.param
 

@@ -105,10 +105,3 @@ def test_env_steps_bit_exact_vs_mirror(setup):
     assert np.array_equal(o2[:, :, -6:].cpu().numpy(), cur.astype(np.float32))
     assert torch.equal(o2[:, :, :-6], obs[:, :, 6:])               # shifted by one entry
     assert torch.equal(env.get_obs(push=False, dtype=torch.float64)[:, :, :-6].float(), o2[:, :, 6:])
-
-
-def test_pair_variant_rejects_other_shapes(cuda, args):
-    from flexgpu import BatchedFlexProvisionEnv, FlexGpuError
-    a = dict(args); a.update(buildings=BUILDINGS, pv_nodes=BUILDINGS, ess_nodes=BUILDINGS, kernel_variant="pair")
-    with pytest.raises(FlexGpuError):
-        BatchedFlexProvisionEnv(a, n_envs=4, device=cuda, network=custom_network(a))

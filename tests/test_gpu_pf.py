@@ -14,7 +14,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL_PU = 1e-6          # north_star: voltages and line flows within 1e-6 p.u.
 
 
-@pytest.fixture(scope="module", params=["thread", "warp", "pair"])
+@pytest.fixture(scope="module", params=["thread", "warp"])
 def env(cuda, profiles, request):
     from flexgpu import BatchedFlexProvisionEnv
     e = BatchedFlexProvisionEnv({"kernel_variant": request.param}, n_envs=8, device=cuda, profiles=profiles)
