@@ -107,7 +107,8 @@ typedef struct FpConfig {
     int32_t raw_actions;         /* 1 = 'safemaddpg' branch of step (:268-274): setpoints unscaled */
     int32_t pf_max_iter;         /* sweep iteration cap; exceeding it == solver failure */
     int32_t variant;             /* FP_VARIANT_* */
-    int32_t reserved_;
+    int32_t pf_f32_passes;       /* THREAD: opening passes of every solve that run in fp32 (0 = none); the fixed
+                                  * point does not depend on how its early iterates were rounded, see DESIGN.md */
     double pf_tol;               /* convergence threshold of the sweep, see FP_VARIANT_* */
     double v_min, v_max;
     double e_min, e_max;

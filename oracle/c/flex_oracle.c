@@ -32,6 +32,7 @@
 
 typedef struct {
     int32_t nb, nl, na, history, episode_limit, raw_actions, pf_max_iter, variant;   /* variant: 0 = thread-per-env order, 1 = warp-per-env order */
+    int32_t pf_f32, pad_;        /* thread order: opening passes of a solve that run in fp32 */
     double pf_tol, v_min, v_max, e_min, e_max, p_ch_max, p_dis_max, eta_ch, eta_dis;
     double mpr, kappa, pv_cost, ess_cost, discomfort_coeff, voltage_coeff, delta_t, fail_penalty, e_next_lb;
     /* lane tables (pre-order; lane k <-> bus position col[k]+1) */
@@ -233,6 +234,54 @@ static void sweep_t(const FoNet* t, const double* p, const double* q, double tol
     for (int k = 0; k < NL; ++k) { ell[k] = 0.0; v[k] = 1.0; o->P[k] = o->Q[k] = 0.0; SP[k] = SQ[k] = 0.0; }
     for (int c = 0; c < MAXCH; ++c) UP[c] = UQ[c] = 0.0;
     setup_t(t, p, q, SP, SQ);
+    if (t->pf_f32 > 0) {
+        /* fp32 opening passes (t_open_f32 in flex_thread_kernels.cu): the same pass in IEEE fp32 -- S, the line
+         * constants and every intermediate rounded to float, explicit fmaf -- without a convergence test; the
+         * currents and the chain loss totals are then widened exactly and the fp64 passes take over */
+        float lf[NL], vf[NL], SPf[NL], SQf[NL], UPf[MAXCH], UQf[MAXCH], aPf[MAXCH], aQf[MAXCH];
+        for (int k = 0; k < NL; ++k) { lf[k] = 0.0f; vf[k] = 1.0f; SPf[k] = (float)SP[k]; SQf[k] = (float)SQ[k]; }
+        for (int c = 0; c < MAXCH; ++c) UPf[c] = UQf[c] = 0.0f;
+        for (int n = 0; n < t->pf_f32; ++n) {
+            float wP = 0.0f, wQ = 0.0f;
+            for (int c = 0; c < MAXCH; ++c) aPf[c] = aQf[c] = 0.0f;
+            for (int k = 0; k < t->nl; ++k) {
+                const float R = (float)t->R[k], X = (float)t->X[k], Z2h = (float)(0.5 * t->Z2[k]);
+                float w, wq, vp;
+                if (ch.head[k]) {
+                    w = UPf[ch.chain_of[k]]; wq = UQf[ch.chain_of[k]];
+                    vp = t->par[k] >= 0 ? vf[t->par[k]] : 1.0f;
+                } else {
+                    w = wP; wq = wQ; vp = vf[k - 1];
+                    for (int c = 0; c < ch.n; ++c) if ((ch.attach[k - 1] >> c) & 1u) { w = w - UPf[c]; wq = wq - UQf[c]; }
+                }
+                w = fmaf(-R, lf[k], w); wq = fmaf(-X, lf[k], wq);
+                wP = w; wQ = wq;
+                const float P = SPf[k] + w, Q = SQf[k] + wq;
+                float g = R * P;
+                g = fmaf(X, Q, g);
+                g = fmaf(Z2h, lf[k], g);
+                const float vk = fmaf(-2.0f, g, vp);
+                vf[k] = vk;
+                float sq = P * P;
+                sq = fmaf(Q, Q, sq);
+                const float e = fmaf(-vk, lf[k], sq);
+                const float d = 1.0f - vk;
+                float rt = 2.0f - vk;
+                rt = fmaf(d, rt, 1.0f);
+                const float en = fmaf(e, rt, lf[k]);
+                lf[k] = en;
+                const int c = ch.chain_of[k];
+                aPf[c] = fmaf(R, en, aPf[c]); aQf[c] = fmaf(X, en, aQf[c]);
+            }
+            for (int c = ch.n - 1; c >= 0; --c) {
+                UPf[c] = aPf[c]; UQf[c] = aQf[c];
+                for (int d = c + 1; d < ch.n; ++d) if ((ch.child[c] >> d) & 1u) { UPf[c] = UPf[c] + UPf[d]; UQf[c] = UQf[c] + UQf[d]; }
+            }
+            ++it;
+        }
+        for (int k = 0; k < NL; ++k) ell[k] = (double)lf[k];
+        for (int c = 0; c < MAXCH; ++c) { UP[c] = (double)UPf[c]; UQ[c] = (double)UQf[c]; }
+    }
     while (it < max_iter) {
         ++it;
         conv = 1;

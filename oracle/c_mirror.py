@@ -28,6 +28,7 @@ class FoNet(C.Structure):
     _fields_ = [
         ("nb", C.c_int32), ("nl", C.c_int32), ("na", C.c_int32), ("history", C.c_int32),
         ("episode_limit", C.c_int32), ("raw_actions", C.c_int32), ("pf_max_iter", C.c_int32), ("variant", C.c_int32),
+        ("pf_f32", C.c_int32), ("pad_", C.c_int32),
         ("pf_tol", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double), ("e_min", C.c_double),
         ("e_max", C.c_double), ("p_ch_max", C.c_double), ("p_dis_max", C.c_double), ("eta_ch", C.c_double),
         ("eta_dis", C.c_double), ("mpr", C.c_double), ("kappa", C.c_double), ("pv_cost", C.c_double),
@@ -50,6 +51,7 @@ class FoState(C.Structure):
 
 
 DEFAULT_TOL = {0: 1e-5, 1: 1e-9}     # must match flexgpu.config (pf_tol per kernel variant)
+DEFAULT_F32_PASSES = {0: 5, 1: 0}    # must match flexgpu.config.DEFAULT_PF_F32_PASSES
 _lib = None
 
 
@@ -94,7 +96,7 @@ def translate_action_f32(x, low=0.0, high=1.0):
 
 
 def make_net(tree, args, agent_buses, pf_tol=None, pf_max_iter=32, raw_actions=False,
-             fail_penalty=200.0, e_next_lb=-1e-8, variant=VARIANT_THREAD):
+             fail_penalty=200.0, e_next_lb=-1e-8, variant=VARIANT_THREAD, pf_f32_passes=None):
     """tree: oracle.ieee33.tree_arrays(net); args: dict with the reference's yaml keys.
     variant selects which kernel's floating-point operation order is mirrored (the thread-per-env
     kernel converges on max |dl| <= pf_tol, the warp-per-env kernel on max |dv| <= pf_tol)."""
@@ -115,6 +117,7 @@ def make_net(tree, args, agent_buses, pf_tol=None, pf_max_iter=32, raw_actions=F
     net.raw_actions = 1 if raw_actions else 0
     net.variant = variant
     net.pf_max_iter = pf_max_iter; net.pf_tol = pf_tol
+    net.pf_f32 = DEFAULT_F32_PASSES[variant] if pf_f32_passes is None else int(pf_f32_passes)
     net.v_min, net.v_max = args['v_min'], args['v_max']
     net.e_min, net.e_max = args['e_min'], args['e_max']
     net.p_ch_max, net.p_dis_max = args['p_ch_max'], args['p_dis_max']

@@ -154,6 +154,7 @@ static int build_topology(const FpConfig& c, DevTopo& t, ThreadTopo& tt, int& sh
     bool any_imax = false;
     for (int k = 0; k < FP_NL; ++k) {
         tt.R[k] = t.R[k]; tt.X[k] = t.X[k]; tt.Z2h[k] = 0.5 * t.Z2[k]; tt.imax2[k] = t.imax2[k];
+        tt.Rf[k] = (float)tt.R[k]; tt.Xf[k] = (float)tt.X[k]; tt.Z2hf[k] = (float)tt.Z2h[k];
         any_imax = any_imax || (k < nl && std::isfinite(t.imax2[k]));
         tt.par_src[k] = tb.par_src[k]; tt.own_slot[k] = tb.own_slot[k]; tt.dep_slot[k] = tb.dep_slot[k];
         tt.dep_first[k] = tb.dep_first[k]; tt.next_is_child[k] = tb.next_is_child[k];
@@ -186,6 +187,7 @@ static void fill_devcfg(const FpConfig& c, DevCfg& d) {
     const double over = 1.0 - c.v_max, under = c.v_min - 1.0;
     d.slack_viol = (over > 0.0 || under > 0.0) ? 1 : 0;
     d.slack_pen = d.slack_viol ? c.voltage_coeff * ((over > under) ? over : under) : 0.0;
+    d.pf_f32 = c.pf_f32_passes;
 }
 
 static int grid_for(int64_t n, int cap) {
@@ -199,6 +201,7 @@ extern "C" {
 int fp_create(const FpConfig* cfg, int64_t n_envs, int device, FpHandle** out) {
     if (!cfg || !out || n_envs < 1) return fail(nullptr, FP_EINVAL, "fp_create: bad arguments");
     if (cfg->history < 1 || cfg->episode_limit < 2 || cfg->pf_max_iter < 1 || !(cfg->pf_tol > 0.0) ||
+        cfg->pf_f32_passes < 0 || cfg->pf_f32_passes >= cfg->pf_max_iter ||
         !(cfg->eta_ch > 0.0) || !(cfg->eta_dis > 0.0))
         return fail(nullptr, FP_EINVAL, "fp_create: bad scalar configuration");
     int ndev = 0;
@@ -722,7 +725,7 @@ int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, 
     if (!h) return FP_EINVAL;
     if (n < 1 || !d_p || !d_q || !d_V) return fail(h, FP_EINVAL, "fp_power_flow: bad arguments");
     PfParams p;
-    p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol;
+    p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol; p.n32 = h->dc.pf_f32; p.pad_ = 0;
     p.p = d_p; p.q = d_q; p.V = d_V; p.Pl = d_Pl; p.Ql = d_Ql; p.Isq = d_Isq; p.iters = d_iters; p.fail = d_fail;
     if (h->variant == FP_VARIANT_THREAD) {
         PfParamsT pt;

@@ -28,7 +28,7 @@ struct DevCfg {
     double pf_tol, v_min, v_max, e_min, e_max, p_ch_max, p_dis_max, eta_ch, eta_dis, inv_eta_dis, inv_eta_ch;
     double mpr, kappa, pv_cost, ess_cost, discomfort_coeff, voltage_coeff, delta_t, fail_penalty;
     double e_next_lb, slack_pen;
-    int32_t slack_viol, pad_;
+    int32_t slack_viol, pf_f32;      // pf_f32: opening passes of the thread kernels' solve that run in fp32
 };
 
 // Per-lane topology tables.  Lives in global memory (handle-owned); every CTA stages it into
@@ -56,6 +56,7 @@ struct DevTopo {
 #define FP_MAX_CHAINS 16
 struct ThreadTopo {
     double R[FP_NL], X[FP_NL], Z2h[FP_NL], imax2[FP_NL];      // Z2h = |z|^2 / 2 (exact scaling)
+    float Rf[FP_NL], Xf[FP_NL], Z2hf[FP_NL];                   // the same, rounded to fp32 (opening passes)
     int8_t par_src[FP_NL];    // forward: TT_ROOT, TT_CARRY or the slot holding v_parent
     int8_t own_slot[FP_NL];   // slot owned by this lane's bus (it has non-adjacent children), else -1
     int8_t dep_slot[FP_NL];   // backward: TT_ROOT (nothing), TT_CARRY (to lane k-1) or slot to deposit into

@@ -51,7 +51,7 @@ struct EnvParams {
 
 struct PfParams {
     const DevTopo* topo;
-    int64_t n; int32_t nl; int32_t max_iter; double tol;
+    int64_t n; int32_t nl; int32_t max_iter; double tol; int32_t n32; int32_t pad_;
     const double* p; const double* q;
     double* V; double* Pl; double* Ql; double* Isq; int32_t* iters; uint8_t* fail;
 };

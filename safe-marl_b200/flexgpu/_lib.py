@@ -35,7 +35,7 @@ class FpConfig(C.Structure):
     _fields_ = [
         ("n_bus", C.c_int32), ("n_agents", C.c_int32), ("history", C.c_int32),
         ("episode_limit", C.c_int32), ("raw_actions", C.c_int32), ("pf_max_iter", C.c_int32),
-        ("variant", C.c_int32), ("reserved_", C.c_int32),
+        ("variant", C.c_int32), ("pf_f32_passes", C.c_int32),
         ("pf_tol", C.c_double), ("v_min", C.c_double), ("v_max", C.c_double),
         ("e_min", C.c_double), ("e_max", C.c_double), ("p_ch_max", C.c_double),
         ("p_dis_max", C.c_double), ("eta_ch", C.c_double), ("eta_dis", C.c_double),

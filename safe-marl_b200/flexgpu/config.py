@@ -24,6 +24,7 @@ DEFAULT_SOLVER_ARGS = dict(
     kernel_variant="thread",  # "thread" (one thread per env, throughput) | "warp" (one warp per env)
     pf_tol=None,        # None -> DEFAULT_PF_TOL[variant]; see DESIGN.md "convergence"
     pf_max_iter=32,     # exceeding it counts as solver failure (:314-337)
+    pf_f32_passes=None,  # None -> DEFAULT_PF_F32_PASSES[variant]: opening passes of a solve that run in fp32
     fail_penalty=200.0,  # :336
     e_next_lb=-1e-8,    # E_next >= 0 (pf.py:46) relaxed by IPOPT's bound_relax_factor
 )
@@ -35,6 +36,10 @@ DEFAULT_SOLVER_ARGS = dict(
 # Newton solution (parity bar 1e-6) and saves the pass that 1e-6 would cost every warp (the slowest of its
 # 32 envs decides): 7.0 -> 6.0 passes per tile on the bench workload.  warp: max |dv|.
 DEFAULT_PF_TOL = {"thread": 1e-5, "warp": 1e-9}
+# thread: the first four passes of the fixed point run in fp32 (error after four passes ~1e-5 relative either
+# way, fp32 rounding noise ~2e-7), the fp64 passes that follow converge on the same tolerance -- same pass count
+# and the same accuracy against Newton as an all-fp64 solve (tests hold 1e-8 on the reference's vectors)
+DEFAULT_PF_F32_PASSES = {"thread": 5, "warp": 0}
 
 
 def convert(dictionary):
@@ -84,6 +89,7 @@ def make_fp_config(args, network):
         raise ValueError("kernel_variant must be 'thread' or 'warp'")
     c.variant = _lib.VARIANTS[variant]
     c.pf_tol = float(DEFAULT_PF_TOL[variant] if args.get("pf_tol") is None else args["pf_tol"])
+    c.pf_f32_passes = int(DEFAULT_PF_F32_PASSES[variant] if args.get("pf_f32_passes") is None else args["pf_f32_passes"])
     c.v_min, c.v_max = float(args["v_min"]), float(args["v_max"])
     c.e_min, c.e_max = float(args["e_min"]), float(args["e_max"])
     c.p_ch_max, c.p_dis_max = float(args["p_ch_max"]), float(args["p_dis_max"])
