@@ -200,12 +200,28 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream);
  * history (correct, one slower call). */
 int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream);
 
-/* fp_step followed by fp_get_obs_view(push = 1) -- the pair the rollout loop issues every step
- * (madrl/models/model.py:220-223) -- with the same results.  With the thread variant and no mask the
- * observation push is fused into the step kernel (one launch); otherwise it is the two calls. */
+/* fp_step followed by fp_get_obs_view(push = 1) -- the two calls the rollout loop issues every step
+ * (madrl/models/model.py:220-223) -- as one entry point (dense view; the one-launch form is fp_step_ring). */
 int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done,
                 double* d_info, const uint8_t* d_mask, float** d_view, int64_t* env_pitch,
                 int64_t* agent_pitch, void* stream);
+
+/* The observation history in its NATIVE device layout, for consumers that stay on the GPU (the policy kernel of the
+ * rollout loop, madrl/models/model.py:213-254): an env-minor fp32 ring  ring[history][n_agents][6][n_pad]  (n_pad =
+ * n_envs rounded up to 32) in which one pushing get_obs (flexibility_provision_env.py:370-403) writes every
+ * (agent, feature) of 32 envs as one aligned 128-byte line at slot `slot` = push number mod history.  The window of
+ * an env is slots slot-history+1 .. slot (mod history), oldest first; a reset zeroes its column (the zero padding
+ * of :393-396).  Same contents as fp_get_obs; fp_obs_ring_gather materialises the dense [n_envs][n_agents][6 history].
+ *   fp_step_ring             fp_step + the pushing get_obs that follows it (model.py:220-223) in ONE launch
+ *   fp_obs_ring              the ring as it stands (no push)
+ *   fp_obs_ring_reset_push   the get_obs at the end of reset() (:155) for the envs of a masked reset: their column is
+ *                            zeroed and the post-reset observation overwrites the newest slot
+ *   fp_obs_ring_gather       d_out[n_envs][n_agents][6 history] fp32 = the windows, oldest entry first */
+int fp_step_ring(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done, double* d_info,
+                 const uint8_t* d_mask, float** d_ring, int32_t* slot, int64_t* n_pad, void* stream);
+int fp_obs_ring(FpHandle* h, float** d_ring, int32_t* slot, int64_t* n_pad, void* stream);
+int fp_obs_ring_reset_push(FpHandle* h, const uint8_t* d_mask, void* stream);
+int fp_obs_ring_gather(FpHandle* h, float* d_out, void* stream);
 
 /* Replaces get_state() (:358-368): out[N][2*n_bus + na + n_bus + 1 + na]. */
 int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream);

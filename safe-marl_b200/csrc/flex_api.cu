@@ -39,6 +39,8 @@ struct FpHandle {
     double *d_V = nullptr, *d_setp = nullptr, *d_hist = nullptr;
     // fp32 window ring of the observation history (fp_get_obs_view): [N][na][3H][6], last written slot, validity
     float* d_obsm = nullptr; int obs_q = 0; bool obsm_valid = false;
+    // env-minor fp32 ring [H][na][6][n_pad] (fp_step_ring / fp_obs_ring): slot of the newest push, validity
+    float* d_obsr = nullptr; int ring_q = 0; bool obsr_valid = false; int64_t n_pad = 0;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
     int stats_rows = 0, stats_cap = 0;     // rows of one launch's statistics block
@@ -280,7 +282,7 @@ int fp_destroy(FpHandle* h) {
     cudaSetDevice(h->device);
     predictor_free(&h->pred);
     cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD); cudaFree(h->d_OBS);
-    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsm);
+    cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsm); cudaFree(h->d_obsr);
     cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
     cudaFree(h->d_act_stage); cudaFree(h->d_act_xlat); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
     for (int i = 0; i < FP_HOST_STREAMS; ++i) {
@@ -386,6 +388,10 @@ int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const doub
         CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 3 * h->dc.history * 6, (cudaStream_t)stream));
         h->launches++;
     }
+    if (h->d_obsr && h->obsr_valid) {
+        CUDA_TRY(h, launch_obsr_clear(h->d_obsr, d_mask, h->n, h->n_pad, h->dc.history * h->dc.na * 6, (cudaStream_t)stream));
+        h->launches++;
+    }
     return FP_OK;
 }
 
@@ -399,6 +405,10 @@ int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_
     h->launches++;
     if (h->d_obsm && h->obsm_valid) {
         CUDA_TRY(h, launch_obsm_clear(h->d_obsm, d_mask, h->n, h->dc.na * 3 * h->dc.history * 6, (cudaStream_t)stream));
+        h->launches++;
+    }
+    if (h->d_obsr && h->obsr_valid) {
+        CUDA_TRY(h, launch_obsr_clear(h->d_obsr, d_mask, h->n, h->n_pad, h->dc.history * h->dc.na * 6, (cudaStream_t)stream));
         h->launches++;
     }
     return FP_OK;
@@ -426,7 +436,7 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     }
     p.reward = d_reward; p.done = d_done; p.info = d_info; p.mask = d_mask;
     p.stats_partial = h->d_stats_partial;
-    if (h->fuse_obs) { p.obs_push = 1; p.obs_q = h->obs_q; p.hist = h->d_hist; p.obsm = h->d_obsm; }
+    if (h->fuse_obs) { p.obs_push = 1; p.obs_q = h->ring_q; p.hist = h->d_hist; p.obsr = h->d_obsr; p.n_pad = h->n_pad; }
     CUDA_TRY(h, launch_env_any(h, MODE_STEP, p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
@@ -608,7 +618,7 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
     CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
-    if (push) h->obsm_valid = false;               // the window ring missed this push: rebuilt on the next view
+    if (push) { h->obsm_valid = false; h->obsr_valid = false; }   // the fp32 rings missed this push: rebuilt on their next use
     return FP_OK;
 }
 
@@ -650,6 +660,7 @@ int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, i
         ObsParams p; fill_obs_params(h, p, nullptr, 1);
         CUDA_TRY(h, launch_obs_push(p, h->d_obsm, h->obs_q, h->grid_obs, st));
         h->launches++;
+        h->obsr_valid = false;
     }
     *d_view = h->d_obsm + (int64_t)(h->obs_q - H + 1) * 6;    // slots w-H+1 .. w: oldest .. newest
     if (env_pitch) *env_pitch = (int64_t)na * 3 * H * 6;
@@ -657,28 +668,93 @@ int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, i
     return FP_OK;
 }
 
-/* step + the pushing get_obs that follows it in the rollout loop, as ONE launch where the kernel supports it */
+/* step + the pushing get_obs that follows it in the rollout loop, dense-view form: two launches (the one-launch
+ * form pushes into the env-minor ring, fp_step_ring) */
 int fp_step_obs(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done, double* d_info,
                 const uint8_t* d_mask, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream) {
     if (!h || !d_view) return FP_EINVAL;
-    if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_obs: call fp_load_profiles first");
-    // fused for the built-in feeder shape (the run-time-table kernels keep the two-launch form)
+    int rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, d_mask, stream);
+    if (rc != FP_OK) return rc;
+    return fp_get_obs_view(h, 1, d_view, env_pitch, agent_pitch, stream);
+}
+
+// Env-minor ring bookkeeping: allocate / rebuild from the fp64 history ring; for a push, advance the slot.
+static int obs_envminor_prepare(FpHandle* h, bool push, cudaStream_t st) {
+    const int H = h->dc.history, na = h->dc.na;
+    if (!h->d_obsr) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        h->n_pad = (h->n + 31) / 32 * 32;
+        CUDA_TRY(h, cudaMalloc(&h->d_obsr, (size_t)H * na * 6 * h->n_pad * 4));
+        h->obsr_valid = false;
+    }
+    if (!h->obsr_valid) {
+        ObsParams p; fill_obs_params(h, p, nullptr, 1);
+        CUDA_TRY(h, launch_obsr_rebuild(p, h->d_obsr, h->n_pad, st));
+        h->launches++;
+        h->ring_q = H - 1; h->obsr_valid = true;
+    }
+    if (push) h->ring_q = (h->ring_q + 1) % H;
+    return FP_OK;
+}
+
+int fp_obs_ring(FpHandle* h, float** d_ring, int32_t* slot, int64_t* n_pad, void* stream) {
+    if (!h || !d_ring) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_obs_ring: call fp_load_profiles first");
+    int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
+    if (rc != FP_OK) return rc;
+    *d_ring = h->d_obsr;
+    if (slot) *slot = h->ring_q;
+    if (n_pad) *n_pad = h->n_pad;
+    return FP_OK;
+}
+
+int fp_step_ring(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done, double* d_info,
+                 const uint8_t* d_mask, float** d_ring, int32_t* slot, int64_t* n_pad, void* stream) {
+    if (!h || !d_ring) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_ring: call fp_load_profiles first");
+    // one launch for the built-in feeder shape; the run-time-table kernels, the warp variant and masked steps push
+    // through the generic path (fp64 history ring) and rebuild the ring from it: same contents
     const bool fuse = (h->variant == FP_VARIANT_THREAD) && d_mask == nullptr && h->shape == SHAPE_IEEE33;
-    if (!fuse) {                                   // other variants / masked steps: two launches, same result
+    if (!fuse) {
         int rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, d_mask, stream);
         if (rc != FP_OK) return rc;
-        return fp_get_obs_view(h, 1, d_view, env_pitch, agent_pitch, stream);
+        float* view = nullptr;
+        rc = fp_get_obs_view(h, 1, &view, nullptr, nullptr, stream);
+        if (rc != FP_OK) return rc;
+        return fp_obs_ring(h, d_ring, slot, n_pad, stream);
     }
-    int rc = obs_ring_prepare(h, true, (cudaStream_t)stream);
+    int rc = obs_envminor_prepare(h, true, (cudaStream_t)stream);
     if (rc != FP_OK) return rc;
     h->fuse_obs = 1;
     rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, nullptr, stream);
     h->fuse_obs = 0;
     if (rc != FP_OK) return rc;
-    const int H = h->dc.history, na = h->dc.na;
-    *d_view = h->d_obsm + (int64_t)(h->obs_q - H + 1) * 6;
-    if (env_pitch) *env_pitch = (int64_t)na * 3 * H * 6;
-    if (agent_pitch) *agent_pitch = (int64_t)3 * H * 6;
+    h->obsm_valid = false;                         // the env-major window ring missed this push
+    *d_ring = h->d_obsr;
+    if (slot) *slot = h->ring_q;
+    if (n_pad) *n_pad = h->n_pad;
+    return FP_OK;
+}
+
+int fp_obs_ring_reset_push(FpHandle* h, const uint8_t* d_mask, void* stream) {
+    if (!h) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_obs_ring_reset_push: call fp_load_profiles first");
+    int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
+    if (rc != FP_OK) return rc;
+    ObsParams p; fill_obs_params(h, p, nullptr, 1);
+    CUDA_TRY(h, launch_obsr_reset_push(p, h->d_obsr, h->n_pad, h->ring_q, d_mask, (cudaStream_t)stream));
+    h->launches++;
+    h->obsm_valid = false;
+    return FP_OK;
+}
+
+int fp_obs_ring_gather(FpHandle* h, float* d_out, void* stream) {
+    if (!h || !d_out) return FP_EINVAL;
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_obs_ring_gather: call fp_load_profiles first");
+    int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
+    if (rc != FP_OK) return rc;
+    CUDA_TRY(h, launch_obsr_gather(h->d_obsr, d_out, h->n, h->n_pad, h->dc.na, h->dc.history, h->ring_q, (cudaStream_t)stream));
+    h->launches++;
     return FP_OK;
 }
 

@@ -447,6 +447,97 @@ __global__ void k_obsm_rebuild(const ObsParams prm, float* __restrict__ obsm) {
     }
 }
 
+// ------------------------------------------------------------------------ env-minor observation ring
+// The native layout of the observation history for the on-device rollout loop: obsr[H][na][6][n_pad] fp32, n_pad =
+// N rounded up to 32.  One push writes, for every (agent, feature), the values of 32 consecutive envs as ONE aligned
+// 128-byte line (the env-major window ring writes 24 bytes per agent row: a partial 32-byte sector, which DRAM with ECC
+// turns into a read-modify-write), at ring slot q = push number mod H -- one number for the whole batch, because all
+// envs push together.  The window of an env is slots q-H+1 .. q (mod H), oldest first; a reset zeroes the env's column,
+// which restarts its zero padding (:393-396).  The consumer is the device policy kernel (policy.cu), which reads a
+// [144 x 128 envs] block per agent with one TMA box and walks the slots in ring order against permuted weight rows;
+// k_obsr_gather materialises the reference's dense [N, na, 6 H] layout for everybody else.
+__global__ void k_obsr_rebuild(const ObsParams prm, float* __restrict__ obsr, int64_t n_pad) {
+    // from the fp64 history ring (the source of truth): window position s (oldest first) -> ring slot s, i.e. the state
+    // after a push at q = H - 1
+    const DevCfg& c = prm.c;
+    const int na = c.na, H = c.history;
+    const int64_t total = (int64_t)H * na * 6 * n_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rr = i / n_pad, e = i - rr * n_pad;
+        const int sl = (int)(rr / (na * 6)), af = (int)(rr - (int64_t)sl * (na * 6));
+        float x = 0.f;
+        if (e < prm.n) {
+            const int32_t cnt = (int32_t)(uint32_t)prm.rec[e * FP_REC_STRIDE + FP_REC_HIST];
+            const int k = cnt - H + sl;
+            if (k >= 0) x = (float)prm.hist[e * (int64_t)(H * FP_HIST_SLOT) + (k % H) * FP_HIST_SLOT + af];
+        }
+        obsr[i] = x;
+    }
+}
+
+// Zero the columns of the envs a reset touches (mask == nullptr: all).  A thread owns an env: the 32 envs of a warp
+// write whole lines when they are reset together (the usual case: episodes of a batch end together).
+__global__ void k_obsr_clear(float* __restrict__ obsr, const uint8_t* __restrict__ mask, int64_t n, int64_t n_pad, int rows) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        if (mask != nullptr && mask[e] == 0) continue;
+        for (int r = 0; r < rows; ++r) obsr[(int64_t)r * n_pad + e] = 0.f;
+    }
+}
+
+// The get_obs call at the end of reset() (:155) for the envs a (masked) reset touched, in ring form: the env's column
+// is zeroed and its post-reset 6-vectors OVERWRITE the newest slot q -- the terminal observation of the episode that
+// just ended, which the rollout loop has consumed -- so that its window reads [0, ..., 0, x_reset] while every other
+// env keeps its slot phase (q stays one number for the batch).  Also pushes the fp64 history ring (cnt 0 -> 1).
+__global__ void k_obsr_reset_push(const ObsParams prm, float* __restrict__ obsr, int64_t n_pad, int q, const uint8_t* __restrict__ mask) {
+    const DevCfg& c = prm.c;
+    const int na = c.na, H = c.history;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < prm.n; e += (int64_t)gridDim.x * blockDim.x) {
+        if (mask != nullptr && mask[e] == 0) continue;
+        uint64_t* rec = prm.rec + e * FP_REC_STRIDE;
+        const uint64_t tm = rec[FP_REC_TIME], hh = rec[FP_REC_HIST];
+        const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32), cnt = (int32_t)(uint32_t)hh;
+        const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);
+        const double* orow = prm.OBSROW + row * FP_OBS_STRIDE;
+        double* hslot = prm.hist + e * (int64_t)(H * FP_HIST_SLOT) + (cnt % H) * FP_HIST_SLOT;
+        for (int sl = 0; sl < H; ++sl) {
+            if (sl == q) continue;
+            for (int af = 0; af < na * 6; ++af) obsr[((int64_t)sl * na * 6 + af) * n_pad + e] = 0.f;
+        }
+        const double price = __ldg(orow + FP_OBS_PRICE);
+        for (int i = 0; i < na; ++i) {
+            const double x[6] = {__ldg(orow + FP_OBS_P + i), __ldg(orow + FP_OBS_Q + i), __ldg(orow + FP_OBS_PV + i),
+                                 prm.V[e * c.nb + prm.agent_col[i] + 1], price, __longlong_as_double((long long)rec[FP_REC_E_CUR + i])};
+            for (int f = 0; f < 6; ++f) {
+                hslot[i * 6 + f] = x[f];
+                obsr[((int64_t)(q * na + i) * 6 + f) * n_pad + e] = (float)x[f];
+            }
+        }
+        for (int k = na * 6; k < FP_HIST_SLOT; ++k) hslot[k] = 0.0;
+        rec[FP_REC_HIST] = (hh & 0xffffffff00000000ull) | (uint32_t)(cnt + 1);
+    }
+}
+
+// Dense view of the ring: out[e][a][s * 6 + f] = obsr[(q - H + 1 + s) mod H][a][f][e]  (the reference's get_obs layout,
+// :387-401).  A CTA transposes a block of 32 envs through shared memory: coalesced on both sides.
+__global__ void __launch_bounds__(256) k_obsr_gather(const float* __restrict__ obsr, float* __restrict__ out, int64_t n, int64_t n_pad,
+                                                     int na, int H, int q) {
+    extern __shared__ float tile[];                // [rows = H * na * 6][33]
+    const int rows = H * na * 6, W = H * 6;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t e0 = (int64_t)blockIdx.x * 32; e0 < n; e0 += (int64_t)gridDim.x * 32) {
+        for (int r = warp; r < rows; r += 8) tile[r * 33 + lane] = (e0 + lane < n_pad) ? obsr[(int64_t)r * n_pad + e0 + lane] : 0.f;
+        __syncthreads();
+        const int64_t ne = (n - e0 < 32) ? (n - e0) : 32;
+        for (int64_t o = threadIdx.x; o < ne * na * W; o += 256) {
+            const int j = (int)(o / (na * W)), r = (int)(o - (int64_t)j * (na * W));
+            const int a = r / W, k = r - a * W, sl = k / 6, f = k - 6 * sl;
+            const int slot = (q + 1 + sl) % H;     // q - H + 1 + sl (mod H)
+            out[(e0 + j) * (int64_t)(na * W) + r] = tile[((slot * na + a) * 6 + f) * 33 + j];
+        }
+        __syncthreads();
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(FP_CTA_THREADS) k_state(const ObsParams prm) {
     const DevCfg& c = prm.c;
@@ -570,6 +661,37 @@ cudaError_t launch_obsm_compact(float* obsm, int64_t rows, int H, cudaStream_t s
 
 cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st) {
     k_obsm_rebuild<<<148 * 16, 256, 0, st>>>(prm, obsm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad, cudaStream_t st) {
+    k_obsr_rebuild<<<148 * 16, 256, 0, st>>>(prm, obsr, n_pad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obsr_clear(float* obsr, const uint8_t* mask, int64_t n, int64_t n_pad, int rows, cudaStream_t st) {
+    const int64_t ctas = (n + 255) / 256;
+    k_obsr_clear<<<(unsigned)(ctas < 148 * 8 ? ctas : 148 * 8), 256, 0, st>>>(obsr, mask, n, n_pad, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obsr_reset_push(const ObsParams& prm, float* obsr, int64_t n_pad, int q, const uint8_t* mask, cudaStream_t st) {
+    const int64_t ctas = (prm.n + 127) / 128;
+    k_obsr_reset_push<<<(unsigned)(ctas < 148 * 16 ? ctas : 148 * 16), 128, 0, st>>>(prm, obsr, n_pad, q, mask);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obsr_gather(const float* obsr, float* out, int64_t n, int64_t n_pad, int na, int H, int q, cudaStream_t st) {
+    const size_t bytes = (size_t)H * na * 6 * 33 * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_obsr_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (bytes > 200 * 1024) return cudaErrorInvalidValue;
+    const int64_t ctas = (n + 31) / 32;
+    k_obsr_gather<<<(unsigned)(ctas < 148 * 2 ? ctas : 148 * 2), 256, bytes, st>>>(obsr, out, n, n_pad, na, H, q);
     return cudaGetLastError();
 }
 

@@ -29,9 +29,9 @@ struct EnvParams {
     const double* PQD;
     // what get_obs reads per row, packed: P and Q at the agent buses, PV, price -- one 128-byte row
     const double* OBSROW;
-    // fused observation push of step(..., return_obs) (thread kernels): fp64 history ring, fp32 mirror ring,
-    // ring slot of this push (obs_push == 0: off)
-    double* hist; float* obsm; int32_t obs_push; int32_t obs_q;   // hist: [N][H][FP_HIST_SLOT] doubles
+    // fused observation push of step(..., return_obs="ring") (thread kernels): fp64 history ring, env-minor fp32 ring
+    // obsr[H][na][6][n_pad], ring slot of this push (obs_push == 0: off)
+    double* hist; float* obsr; int64_t n_pad; int32_t obs_push; int32_t obs_q;   // hist: [N][H][FP_HIST_SLOT] doubles
     // per-env state
     uint64_t* rec; double* V; double* setp;
     double* pfl; double* qfl; double* isq;       // optional line-flow dump (nullptr = off)
@@ -87,6 +87,10 @@ cudaError_t launch_obs_push(const ObsParams& prm, float* obsm, int q, int grid, 
 cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int floats_per_env, cudaStream_t st);
 cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st);
 cudaError_t launch_obsm_compact(float* obsm, int64_t rows, int H, cudaStream_t st);
+cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad, cudaStream_t st);
+cudaError_t launch_obsr_clear(float* obsr, const uint8_t* mask, int64_t n, int64_t n_pad, int rows, cudaStream_t st);
+cudaError_t launch_obsr_reset_push(const ObsParams& prm, float* obsr, int64_t n_pad, int q, const uint8_t* mask, cudaStream_t st);
+cudaError_t launch_obsr_gather(const float* obsr, float* out, int64_t n, int64_t n_pad, int na, int H, int q, cudaStream_t st);
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st);
 cudaError_t launch_pack_obsrow(const double* P, const double* Q, const double* pvp, const int32_t* agent_col, int na, int nl,
                                int64_t T, double* out, cudaStream_t st);

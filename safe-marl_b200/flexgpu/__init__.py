@@ -11,6 +11,7 @@ from .network import Network, create_network
 from .profiles import Profiles, load_csv_profiles, synthetic_profiles
 from ._lib import FlexGpuError, INFO_KEYS, STAT_KEYS
 from .util import prep_obs, translate_action
+from .env import ObsRing
 from . import sharding
 
 

@@ -257,6 +257,9 @@ class BatchedFlexProvisionEnv:
             if lo < 0 or hi >= self.max_start():
                 raise ValueError("start_index out of range for the loaded profiles")
             self._check(self._lib.fp_reset(self._h, _ptr(s), _ptr(e), _ptr(a), _ptr(m), _stream()), "fp_reset")
+        if return_obs == "ring":                                        # reset()'s get_obs (:155) for the reset envs, ring form
+            self._check(self._lib.fp_obs_ring_reset_push(self._h, _ptr(m), _stream()), "fp_obs_ring_reset_push")
+            return self.obs_ring()
         if return_obs:
             return self.get_obs(), self.get_state()                     # :155
         return None
@@ -264,7 +267,8 @@ class BatchedFlexProvisionEnv:
     def step(self, actions, mask=None, want_info=True, translate=False, return_obs=False):
         """Replaces step() (:241-356).  actions: [N, na, 4] (or [N, na*4]) fp32 or fp64 tensor.
         return_obs=True appends the next observation (one pushing get_obs, as model.py:223 does right
-        after the step) to the returned tuple: (reward, done, info, obs).
+        after the step) to the returned tuple: (reward, done, info, obs).  return_obs="ring" does the same in ONE
+        launch and returns the history in its native device layout (ObsRing) -- what the device policy consumes.
         translate=True: `actions` are the policy's raw fp32 outputs and translate_action
         (utils/util.py:121-129: clamp to [action_low, action_high], then 0.5 (x + 1)(high - low) + low,
         all in fp32 -- quirk Q5) is applied inside the step kernel, as model.py:218-220 does on the host."""
@@ -279,7 +283,13 @@ class BatchedFlexProvisionEnv:
             raise ValueError("actions must have n_envs * n_agents * 4 elements")         # :260
         m = self._dev(mask, torch.uint8)
         dt = _lib.FP_F32_POLICY if translate else (_lib.FP_F64 if actions.dtype == torch.float64 else _lib.FP_F32)
-        if return_obs:                               # step + pushing get_obs in one launch (fp_step_obs)
+        if return_obs == "ring":                     # step + pushing get_obs in ONE launch, native env-minor ring
+            p, sl, npad = C.c_void_p(), C.c_int32(), C.c_int64()
+            self._check(self._lib.fp_step_ring(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
+                                               _ptr(self._info) if want_info else None, _ptr(m), C.byref(p), C.byref(sl),
+                                               C.byref(npad), _stream()), "fp_step_ring")
+            obs = self._ring(p.value, sl.value, npad.value)
+        elif return_obs:                             # step + pushing get_obs, dense strided view (fp_step_obs)
             p, ep, ap = C.c_void_p(), C.c_int64(), C.c_int64()
             self._check(self._lib.fp_step_obs(self._h, _ptr(actions), dt, _ptr(self._reward), _ptr(self._done),
                                               _ptr(self._info) if want_info else None, _ptr(m), C.byref(p), C.byref(ep),
@@ -340,6 +350,20 @@ class BatchedFlexProvisionEnv:
         dt = _lib.FP_F64 if dtype == torch.float64 else _lib.FP_F32
         self._check(self._lib.fp_get_obs(self._h, _ptr(buf), dt, 1 if push else 0, _stream()), "fp_get_obs")
         return buf
+
+    def obs_ring(self):
+        """The observation history in its native device layout (fp_obs_ring): ObsRing, no push."""
+        p, sl, npad = C.c_void_p(), C.c_int32(), C.c_int64()
+        self._check(self._lib.fp_obs_ring(self._h, C.byref(p), C.byref(sl), C.byref(npad), _stream()), "fp_obs_ring")
+        return self._ring(p.value, sl.value, npad.value)
+
+    def _ring(self, ptr, slot, n_pad):
+        t = self._obs_views.get(("ring", ptr))
+        if t is None:
+            holder = _ExternalCudaBuffer(ptr, self.history * self.n_agents * 6 * n_pad * 4, self.device.index or 0)
+            t = torch.as_tensor(holder, device=self.device).view(torch.float32).view(self.history, self.n_agents, 6, n_pad)
+            self._obs_views[("ring", ptr)] = t
+        return ObsRing(self, t, slot)
 
     def _obs_view(self, ptr, env_pitch, agent_pitch):
         view = self._obs_views.get(ptr)                              # one cached tensor per ring position
@@ -420,6 +444,23 @@ class BatchedFlexProvisionEnv:
 
     def launch_count(self):
         return int(self._lib.fp_launch_count(self._h))
+
+
+class ObsRing:
+    """The observation history where the device policy reads it: `ring` [history, n_agents, 6, n_pad] fp32 (env-minor:
+    one push writes whole 128-byte lines), `slot` = ring slot of the newest push.  The window of env e / agent a is
+    ring[(slot - history + 1 + s) % history, a, :, e] for s = 0 .. history-1 (oldest first); dense() materialises the
+    reference's [N, n_agents, 6 * history] layout (get_obs, :387-401)."""
+
+    def __init__(self, env, ring, slot):
+        self.env, self.ring, self.slot = env, ring, int(slot)
+
+    def dense(self, out=None):
+        env = self.env
+        if out is None:
+            out = torch.empty(env.n_envs, env.n_agents, env.obs_size, dtype=torch.float32, device=env.device)
+        env._check(env._lib.fp_obs_ring_gather(env._h, _ptr(out), _stream()), "fp_obs_ring_gather")
+        return out
 
 
 class _ExternalCudaBuffer:

@@ -42,12 +42,12 @@ for combo in itertools.product(*knobs.values()):
     for k in range(12):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); env.step(acts[k % 4], want_info=True, return_obs=True); b.record(); torch.cuda.synchronize()
+        a.record(); env.step(acts[k % 4], want_info=True, return_obs="ring"); b.record(); torch.cuda.synchronize()
         if k >= 4:
             to.append(a.elapsed_time(b) * 1e3)
     it = env.pf_iterations.float()
     us = float(np.median(ts))
     print(json.dumps({**cfg, "envs": E, "passes_mean": round(float(it.mean()), 3), "passes_max": int(it.max()),
                       "us_median": round(us, 2), "env_steps_per_s": round(E / us * 1e6 / 1e9, 4),
-                      "hbm_frac": round(E * 1256 / (us * 1e-6) / 6553.3e9, 4), "step_obs_us": round(float(np.median(to)), 2)}), flush=True)
+                      "hbm_frac": round(E * 1256 / (us * 1e-6) / 6553.3e9, 4), "step_ring_us": round(float(np.median(to)), 2)}), flush=True)
     env.close()
