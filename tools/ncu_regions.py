@@ -4,7 +4,9 @@ import csv, subprocess, sys, collections
 rep = sys.argv[1]; nseg = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]
+nxt = [i for i, r in enumerate(rows) if i > 1 and r and r[0] == 'Kernel Name']      # several launches: the first one
+data = [r for r in rows[2:(nxt[0] if nxt else None)] if len(r) == len(hdr)]
 ix = {h: i for i, h in enumerate(hdr)}
 def iv(r, k):
     try: return int(r[ix[k]] or 0)
