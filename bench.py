@@ -19,14 +19,22 @@ would otherwise sit in the 126 MB L2.  value = total envs * K / max-over-ranks(s
 e2e: the same step through fp_step_host (pinned host actions in, reward+done out, copies and
 the stream sync inside the timed region), wall-clocked.
 
---impl reference: the CPU arm.  The reference's own implementation (Pyomo + IPOPT) is not
-installable here, so this times the oracle port: oracle/c/flex_oracle.c (OpenMP,
-all host cores) on a bounded sample of the same workload, plus the single-core Python
-restatement (oracle/env_ref.py) for scale.
+Beside the headline (N = 1 only unless noted): `config2` (BASELINE config 2: 4096 power-flow-only
+solves, both kernel variants, 776 B/solve), `config3` (65 536 envs), `config4` (predictor -> replay
+ring, 262 144 envs), `config5_strong` (every N: 2^20 envs IN TOTAL split over the N GPUs -- strong
+scaling of config 5), `step_plus_get_obs` (fused step + observation push into the env-minor ring,
+the rollout loop's env cost), `roofline_fp64` (the step kernel against the fp64 pipe).
+
+--impl reference: the CPU arm.  The reference's own implementation (Pyomo + IPOPT) is probed for
+(`import pyomo`, `which ipopt`: utils/pf.py:101) but is not installable here, so this
+times the oracle port: oracle/c/flex_oracle.c (OpenMP, all host cores) on the same workload (same
+envs per step, same steps and warm-up), plus the single-core Python restatement (oracle/env_ref.py)
+for scale.
 """
 import argparse
 import json
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -113,7 +121,7 @@ def cpu_port_rate(prof, n_envs, budget_s, seed=5):
     import numpy as np
     from oracle import c_mirror
     cores = c_mirror.use_all_cores()
-    n = min(n_envs, 65536)
+    n = n_envs
     mb = make_mirror(n, prof, seed)
     rng = np.random.default_rng(0)
     acts = rng.uniform(0, 1, (4, n, 20)).astype(np.float32)
@@ -144,15 +152,19 @@ def python_restatement_rate(prof, budget_s=5.0):
     return k / (time.perf_counter() - t0)
 
 
-def ncu_traffic(envs_per_gpu):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_env_t<STEP> launch from the committed
-    `ncu --set full` capture (profiles/r1_step_kernel_traffic.json), if it was taken at this launch size."""
+def ncu_capture(envs_per_gpu):
+    """Counters of one k_env_t<STEP> launch from the committed `ncu --set full` capture
+    (profiles/r2_step_kernel_traffic.json), if it was taken at this launch size: DRAM bytes
+    (dram__bytes_read.sum + dram__bytes_write.sum) and fp64 / fp32 lane-operations."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_kernel_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_step_kernel_traffic.json")) as f:
             d = json.load(f)
-        return float(d["dram_bytes_per_launch"]) if int(d["envs"]) == int(envs_per_gpu) else None
+        return d if int(d["envs"]) == int(envs_per_gpu) else None
     except (OSError, ValueError, KeyError):
         return None
+
+
+FP64_PEAK_LANE_OPS_PER_CLK_SM = 59.0    # measured on B200 (profiles/r1_ubench_fp64_b200.txt; nominal 64)
 
 
 def workload_name(envs_per_gpu):
@@ -160,8 +172,30 @@ def workload_name(envs_per_gpu):
             f"N=8 is config 5)")
 
 
+def make_config(args, world, auto_reset):
+    """The `config` object: identical for the GPU arm and the reference arm of the same command line."""
+    c = {"workload": workload_name(args.envs_per_gpu), "envs_per_gpu": args.envs_per_gpu,
+         "total_envs": args.envs_per_gpu * world, "profile_rows": args.rows,
+         "actions": "fp32 uniform(0,1), one [envs, 5, 4] array per step",
+         "episode": "Philox reset before the warm-up; 95-step episodes (quirk Q1)"}
+    if auto_reset:
+        c["auto_reset_every"] = EPISODE_STEPS
+    return c
+
+
+def probe_reference_solver():
+    """is the reference's own power flow (Pyomo + the ipopt binary, utils/pf.py:101) runnable here?"""
+    try:
+        import pyomo  # noqa: F401
+        have_pyomo = True
+    except Exception:
+        have_pyomo = False
+    return {"pyomo": have_pyomo, "ipopt": shutil.which("ipopt") is not None}
+
+
 def run_reference(args):
-    """--impl reference: the CPU arm (rank 0 only)."""
+    """--impl reference: the CPU arm (rank 0 only) on the GPU arm's workload: the same number of envs per step
+    (all N GPUs' shards), the same steps and warm-up."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -170,32 +204,44 @@ def run_reference(args):
     prof = synthetic_profiles(network, 5, T=args.rows, seed=0)
     import numpy as np
     from oracle import c_mirror
+    probe = probe_reference_solver()
     cores = c_mirror.use_all_cores()                             # torchrun exports OMP_NUM_THREADS=1
-    n = min(args.envs_per_gpu, 65536)
+    W = max(args.warmup, 3); K = args.steps
+    total = args.envs_per_gpu * args.gpus
+    # bounded: at most ~1.5e9 env-steps of CPU work (a few minutes on 16 cores); otherwise step a sample of the envs
+    n = total if total * (K + W) <= 1.5e9 else max(1024, int(1.5e9 / (K + W)) // 32 * 32)
     mb = make_mirror(n, prof, 5)
     rng = np.random.default_rng(0)
     acts = rng.uniform(0, 1, (4, n, 20)).astype(np.float32)
-    steps = max(1, min(args.steps, 60)); warm = max(1, min(args.warmup, 3))
-    for w in range(warm):
-        mb.step(acts[w % 4])
+    t_in_ep = 0
+    resets = 0
+    def one(k):
+        nonlocal t_in_ep, resets
+        if t_in_ep == EPISODE_STEPS:
+            mb.reset_random(5); t_in_ep = 0; resets += 1        # same Philox key, next episode counter
+        mb.step(acts[k % 4]); t_in_ep += 1
+    for w in range(W):
+        one(w)
+    resets = 0
     t0 = time.perf_counter()
-    for k in range(steps):
-        mb.step(acts[k % 4])
+    for k in range(K):
+        one(W + k)
     el = time.perf_counter() - t0
-    value = n * steps / el
+    value = n * K / el
     py = python_restatement_rate(prof, 5.0)
+    kind = "port"                                                # the true reference needs pyomo + ipopt AND /root/reference
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * el / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.envs_per_gpu), "envs_per_gpu": args.envs_per_gpu,
-                   "total_envs": args.envs_per_gpu * args.gpus, "profile_rows": args.rows,
-                   "actions": "fp32 uniform(0,1), host memory",
-                   "sample": f"each step = {n} envs of that workload (bounded CPU sample), rank 0 only"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} envs x {steps} steps, C port of the step (oracle/c/flex_oracle.c, OpenMP); "
-                                   f"the reference itself (Pyomo+IPOPT per step) is not installable; "
-                                   f"single-core Python restatement: {py:.0f} env-steps/s"},
+        "config": make_config(args, args.gpus, resets > 0),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n} envs per step x {K} steps (+{W} warm-up) of the C port of the step (oracle/c/flex_oracle.c, "
+                                   f"OpenMP, {cores} threads)" + ("" if n == total else f" -- a sample of the {total} envs") +
+                                   f"; single-core Python restatement: {py:.0f} env-steps/s",
+                         "reference_solver_probe": probe,
+                         "note": "the reference's own step is Pyomo + an ipopt subprocess per env-step; neither is installed "
+                                 "(and /root/reference does not exist on the GPU box), so the arm runs the port"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,6 +261,9 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostics only)")
     ap.add_argument("--no-config4", action="store_true", help="skip the extra predictor (config 4) measurement at N=1")
     ap.add_argument("--no-obs", action="store_true", help="skip the extra step+get_obs measurement (rollout-loop cost)")
+    ap.add_argument("--no-config2", action="store_true", help="skip the extra power-flow-only (config 2) measurement at N=1")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra strong-scaling (2^20 envs in total) measurement")
+    ap.add_argument("--no-rollout", action="store_true", help="skip the extra device-rollout measurement (policy + step + get_obs [+ Transition writes])")
     ap.add_argument("--variant", default="thread", choices=["thread", "warp"], help="kernel variant (see include/flexgpu.h)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -253,12 +302,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    state = {"t": 0}
+    state = {"t": 0, "timed_resets": 0}
 
     def one_step(k, timed):
         if state["t"] == EPISODE_STEPS:
             env.reset(return_obs=False)                       # Philox auto-reset, one launch
             state["t"] = 0
+            state["timed_resets"] += 1 if timed else 0
         env.step(acts[k % n_act], want_info=True)
         state["t"] += 1
 
@@ -308,15 +358,103 @@ def main():
 
     obs_extra = None
     if not args.no_obs:
-        env.reset(return_obs=False)
-        for k in range(3):                                        # warm-up: allocates the observation window ring
-            env.step(acts[k % n_act], want_info=False, return_obs=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier(); e0.record(stream)
-        for k in range(60):
-            env.step(acts[k % n_act], want_info=False, return_obs=True)
-        e1.record(stream); barrier()
-        obs_extra = E * world * 60 / (e0.elapsed_time(e1) * 1e-3)
+        # the rollout loop's env cost: step + pushing get_obs (model.py:220-223) in ONE launch, observation
+        # history in its native env-minor ring (what the device policy reads)
+        env.reset(return_obs="ring")
+        for k in range(3):
+            env.step(acts[k % n_act], want_info=False, return_obs="ring")
+        Ko = 40
+        evo = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Ko)]
+        barrier()
+        for k in range(Ko):
+            if not args.no_flush:
+                flush.zero_()
+            evo[k][0].record(stream); env.step(acts[k % n_act], want_info=False, return_obs="ring"); evo[k][1].record(stream)
+        barrier()
+        obs_ms = sum(a.elapsed_time(b) for a, b in evo)
+        obs_extra = (E * Ko, obs_ms)
+
+    # ---- the rollout loop on the device (model.py:213-254): tcgen05 policy -> fused translate_action + step + get_obs
+    #      [-> Transition fields into the device replay ring]; nothing crosses PCIe (only the statistics, afterwards)
+    rollout = None
+    if not args.no_rollout and args.variant == "thread":
+        from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS
+        from flexgpu.predictor import DeviceReplayBuffer
+        rngp = np.random.default_rng(7)
+        sd = {"fc1.weight": rngp.normal(0, 0.1, (64, 149)), "fc1.bias": rngp.uniform(-0.08, 0.08, 64), "layernorm.weight": np.ones(64),
+              "layernorm.bias": np.zeros(64), "rnn.weight_ih": rngp.uniform(-0.125, 0.125, (192, 64)),
+              "rnn.weight_hh": rngp.uniform(-0.125, 0.125, (192, 64)), "rnn.bias_ih": rngp.uniform(-0.125, 0.125, 192),
+              "rnn.bias_hh": rngp.uniform(-0.125, 0.125, 192), "fc2.weight": rngp.normal(0, 0.1, (4, 64)), "fc2.bias": rngp.uniform(-0.125, 0.125, 4)}
+        pol = DevicePolicy(sd, device=dev, std=1.0, seed=11 + rank)
+        rollout = {}
+        for label, rec in (("acting", 0), ("recording", E)):
+            buf = DeviceReplayBuffer(2 * E, TRANSITION_FIELDS, device=dev) if rec else None
+            ro = DeviceRollout(env, pol, replay=buf, record_envs=rec)
+            ro.reset()
+            for k in range(3):
+                ro.step()
+            Kr = 30
+            evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kr)]
+            l0 = env.launch_count() + pol.launch_count()
+            barrier()
+            for k in range(Kr):
+                if not args.no_flush:
+                    flush.zero_()
+                evr[k][0].record(stream); ro.step(); evr[k][1].record(stream)
+            barrier()
+            rollout[label] = (E * Kr, sum(a.elapsed_time(b) for a, b in evr), (env.launch_count() + pol.launch_count() - l0) / Kr)
+            if buf is not None:
+                buf.close()
+        pol.close()
+
+    # ---- strong scaling of BASELINE config 5: 2^20 envs IN TOTAL, split over the ranks (every N)
+    strong = None
+    if not args.no_strong:
+        Es = (1 << 20) // world
+        envs = BatchedFlexProvisionEnv({"kernel_variant": args.variant}, n_envs=Es, device=dev, profiles=prof, seed=5,
+                                       env_offset=rank * Es)
+        envs.reset(return_obs=False)
+        acts_s = torch.rand(2, Es, 5, 4, device=dev, dtype=torch.float32, generator=g)
+        Ks = 20
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Ks)]
+        for k in range(3):
+            flush.zero_(); envs.step(acts_s[k % 2], want_info=True)
+        barrier()
+        for k in range(Ks):
+            flush.zero_()
+            evs[k][0].record(stream); envs.step(acts_s[k % 2], want_info=True); evs[k][1].record(stream)
+        barrier()
+        strong = (Es, Ks, sum(a.elapsed_time(b) for a, b in evs))
+        envs.close(); del acts_s
+
+    # ---- BASELINE config 2 (4096 independent power-flow-only solves, utils/pf.py:115-192), both variants, N = 1 only
+    config2 = None
+    if world == 1 and not args.no_config2:
+        n2 = 4096
+        rng2 = np.random.default_rng(0)
+        p2 = torch.from_numpy(network.base_p[None, 1:] * rng2.uniform(0.7, 1.3, (n2, 32))).to(dev)      # data_generation.py:27-36
+        q2 = torch.from_numpy(network.base_q[None, 1:] * rng2.uniform(0.7, 1.3, (n2, 32))).to(dev)
+        config2 = {"workload": "power_flow_only_4096_solves (BASELINE config 2: run_pf.py-style batched solve, V out)",
+                   "unit": "solves/s", "bytes_per_solve": 776, "variants": {}}
+        for var in ("thread", "warp"):
+            e2 = env if var == args.variant else BatchedFlexProvisionEnv({"kernel_variant": var}, n_envs=32, device=dev,
+                                                                         profiles=synthetic_profiles(network, 5, T=2000, seed=0), seed=5)
+            for k in range(5):
+                e2.power_flow(p2, q2, want_flows=False)
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(40)]
+            for k in range(40):
+                flush.zero_()
+                ev2[k][0].record(stream); out2 = e2.power_flow(p2, q2, want_flows=False); ev2[k][1].record(stream)
+            torch.cuda.synchronize()
+            ms2 = statistics.median(a.elapsed_time(b) for a, b in ev2)
+            config2["variants"][var] = {"value": n2 / (ms2 * 1e-3), "kernel_ms_median": ms2,
+                                        "roofline_frac": 776 * n2 / (ms2 * 1e-3) / 1e9 / peaks()[0],
+                                        "passes_max": int(out2["iters"].max()), "failed": int(out2["failed"].sum())}
+            if e2 is not env:
+                e2.close()
+        best = max(config2["variants"], key=lambda v: config2["variants"][v]["value"])
+        config2["value"] = config2["variants"][best]["value"]; config2["best_variant"] = best
+        config2["note"] = "4096 solves are 128 tiles of 32 on 148 SMs: one launch latency, not a bandwidth measurement"
 
     # ---- BASELINE config 3 (65 536 envs on one B200), same method, N = 1 only
     config3 = None
@@ -368,10 +506,12 @@ def main():
                    "bytes_per_env": b4, "roofline_frac": b4 * E4 / (ms4 * 1e-3) / 1e9 / peaks()[0], "steps": K4}
         ring.close()
 
-    t = torch.tensor([dev_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, kern_ms, obs_extra[1] if obs_extra else 0.0, strong[2] if strong else 0.0,
+                      rollout["acting"][1] if rollout else 0.0, rollout["recording"][1] if rollout else 0.0],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, kern_ms = (float(x) for x in t)
+    dev_ms, e2e_s, kern_ms, obs_ms, strong_ms, roll_ms, rollrec_ms = (float(x) for x in t)
     stats = env.episode_stats(reduce=True)                     # the one NCCL collective (16 doubles)
     total_envs = E * world
     value = total_envs * K / (dev_ms * 1e-3)
@@ -380,38 +520,67 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         achieved = B_ALG * E / (kern_ms * 1e-3) / 1e9
+        cap = ncu_capture(E) if args.variant == "thread" else None
+        cfg = make_config(args, world, state["timed_resets"] > 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(E),
-                       "kernel_variant": args.variant, "envs_per_gpu": E, "total_envs": total_envs, "profile_rows": args.rows,
-                       "actions": "fp32 uniform(0,1), resident in HBM", "auto_reset_every": EPISODE_STEPS,
+            "config": cfg,
+            "method": {"kernel_variant": args.variant, "actions": "resident in HBM (8 arrays cycled)",
                        "l2": "flushed before every timed step (256 MiB memset, untimed)" if not args.no_flush else "NOT flushed",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks",
-                       "wall_s_incl_flush": t_wall},
+                       "auto_resets_in_timed_region": state["timed_resets"], "wall_s_incl_flush": t_wall},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": E * 20 * 4, "d2h_bytes_per_step": E * 9,
                     "steps": Ke, "api": "BatchedFlexProvisionEnv.step_host -> fp_step_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(E), "kernel": {"thread": "k_env_t<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
+                         "traffic": float(cap["dram_bytes_per_launch"]) if cap else None,
+                         "kernel": {"thread": "k_env_t<STEP>", "warp": "k_env<STEP>"}[args.variant], "bytes_per_env_step": B_ALG,
                          "kernel_ms_median": kern_ms, "peak_source": peak_src,
-                         "note": "not HBM-bound: 17 fp64 ops x 32 lines x ~6 one-pass sweeps (a warp runs the maximum of its 32 envs; mean 5.2) + the final pass + the setpoint "
-                                 "arithmetic = ~4400 fp64 lane-ops per env-step, which cap the kernel at ~3.9e9 env-steps/s "
-                                 "on the fp64 pipe (59 lane-ops/clk/SM measured), i.e. 75 % of this HBM roofline at best; "
-                                 "see DESIGN.md section 3"},
+                         "note": "latency-bound per warp, not HBM- or pipe-bound: see roofline_fp64 and DESIGN.md section 3"},
             "stats": {k: float(v) for k, v in stats.items()},
         }
+        if cap is not None and clocks and clocks.get("sm_mhz"):
+            # the same kernel against the fp64 pipe: lane-operations (DFMA/DADD/DMUL, one each) per launch from the ncu capture
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            pk = FP64_PEAK_LANE_OPS_PER_CLK_SM * sms * clocks["sm_mhz"] * 1e6
+            ach = cap["fp64_lane_ops_per_launch"] / (kern_ms * 1e-3)
+            line["roofline_fp64"] = {"bound": "fp64 pipe", "achieved_lane_ops": ach, "peak": pk, "unit": "lane-ops/s", "frac": ach / pk,
+                                     "lane_ops_per_env_step": cap["fp64_lane_ops_per_env_step"],
+                                     "fp32_lane_ops_per_env_step": cap["fp32_lane_ops_per_env_step"],
+                                     "peak_source": f"{FP64_PEAK_LANE_OPS_PER_CLK_SM} lane-ops/clk/SM measured (profiles/r1_ubench_fp64_b200.txt) x {sms} SMs x sampled SM clock",
+                                     "counts_source": "profiles/r2_step_kernel_traffic.json (ncu --set full)"}
         if obs_extra is not None:
-            line["step_plus_get_obs_env_steps_per_s"] = obs_extra
+            line["step_plus_get_obs_env_steps_per_s"] = obs_extra[0] * world / (obs_ms * 1e-3)
+            line["step_plus_get_obs"] = {"api": "step(..., return_obs='ring') -> fp_step_ring (one launch)", "steps": 40,
+                                         "ms_per_step": obs_ms / 40, "l2": "flushed before every step"}
+        if rollout is not None:
+            line["rollout_env_steps_per_s"] = rollout["acting"][0] * world / (roll_ms * 1e-3)
+            line["rollout"] = {"loop": "k_policy (RNNAgent fc1-LayerNorm-ReLU-GRUCell-fc2 + tanh-Normal sampling, tcgen05) -> fp_step_ring "
+                                       "(translate_action + step + get_obs push): model.py:213-254 with zero PCIe bytes per step",
+                               "ms_per_step": roll_ms / 30, "launches_per_step": rollout["acting"][2], "steps": 30,
+                               "with_transition_writes": {"env_steps_per_s": rollout["recording"][0] * world / (rollrec_ms * 1e-3),
+                                                          "ms_per_step": rollrec_ms / 30, "launches_per_step": rollout["recording"][2],
+                                                          "bytes_per_transition": 4 * sum(TRANSITION_FIELDS.values()),
+                                                          "recorded_envs_per_step": E},
+                               "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "l2": "flushed before every step"}
+        if strong is not None:
+            line["config5_strong"] = {"workload": "fused_env_step_2^20_envs_total (BASELINE config 5, strong scaling: split over the run's GPUs)",
+                                      "value": strong[0] * world * strong[1] / (strong_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                                      "envs_per_gpu": strong[0], "steps": strong[1], "ms_per_step": strong_ms / strong[1],
+                                      "roofline_frac_per_gpu": B_ALG * strong[0] * strong[1] / (strong_ms * 1e-3) / 1e9 / peak}
+        if config2 is not None:
+            line["config2"] = config2
         if config3 is not None:
             line["config3"] = config3
         if config4 is not None:
             line["config4"] = config4
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_rate(prof, E, budget_s=12.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "reference_solver_probe": probe_reference_solver()}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:

@@ -290,6 +290,52 @@ int fp_predictor_load(FpHandle* h, int32_t n_in, int32_t n_out, const double* h_
 int fp_predict(FpHandle* h, int64_t n, const float* d_X, float* d_vhat, double* d_penalty, FpReplay* sink,
                int32_t f_vhat, int32_t f_penalty, int64_t pos, void* stream);
 
+/* -- acting policy of the rollout loop, transitions, learner feed ---- */
+
+/* The shared-parameter RNNAgent (madrl/agents/rnn_agent.py:8-32: fc1(144 obs + 5 agent-id -> 64) -> LayerNorm ->
+ * ReLU -> GRUCell(64) -> fc2(64 -> 4)) evaluated for n_envs x 5 agents per call on tcgen05 tensor cores, reading the
+ * observation ring of fp_step_ring / fp_obs_ring directly, followed by select_action (utils/util.py:50-64, continuous,
+ * action_enforcebound) -- i.e. the device form of model.py:215-216 (prep_obs -> get_actions).  Weights are held as
+ * TF32; activations keep fp32 accuracy (two-term split).  The handle is independent of FpHandle (one per GPU). */
+typedef struct FpPolicy FpPolicy;
+int fp_policy_create(int device, FpPolicy** out);
+int fp_policy_destroy(FpPolicy* p);
+const char* fp_policy_last_error(const FpPolicy* p);    /* p may be NULL: last fp_policy_create error */
+int64_t fp_policy_launch_count(const FpPolicy* p);
+/* HOST fp32 arrays in torch's state_dict layouts: fc1.weight [64][149], fc1.bias [64], layernorm.weight/.bias [64],
+ * rnn.weight_ih / weight_hh [192][64] (rows r | z | n), rnn.bias_ih / bias_hh [192], fc2.weight [4][64], fc2.bias [4]. */
+int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const float* ln_g, const float* ln_b,
+                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                   const float* fc2_w, const float* fc2_b);
+/* One acting step.  d_ring / slot / n_pad: the observation ring.  d_hid_in (NULL = zeros) / d_hid_out: [n_envs][5][64]
+ * hidden states (last_hid / hid of the Transition); d_reset (may be NULL): envs whose hidden state restarts at zero
+ * (init_hidden, model.py:211).  Outputs [n_envs][5][4] fp32: d_mean (may be NULL), d_action = tanh(mean + std eps)
+ * (what translate_action receives: feed it to fp_step* with FP_F32_POLICY), d_logp (may be NULL).  explore = 1: status
+ * 'train' with exploration, eps from d_eps (caller-supplied standard-normal draws, [n_envs][5][4]) or, if NULL, from
+ * Philox4x32-10 keyed by (seed; row, step); explore = 0: status 'test' (action = tanh(mean)).  std = fixed_policy_std. */
+int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_hid_in,
+                  const uint8_t* d_reset, float* d_hid_out, float* d_mean, float* d_action, float* d_logp,
+                  const float* d_eps, uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream);
+/* Transition fields (madrl/models/model.py:19, :230-242) straight into a replay ring: field rows (row0 + e) mod cap.
+ *   fp_policy_gather_windows   state / next_state: the dense get_obs windows [5][144] of envs [0, n) from the ring
+ *                              (pitch = floats per destination row, >= 720; row0 = 0, cap >= n: a dense tensor)
+ *   fp_policy_rows_to_ring     any dense [n][width] fp32 array (action, log_prob_a, last_hid, hid, value ...)
+ *   fp_policy_scalars_to_ring  reward repeated per agent (model.py:221), done, last_step (= done, or every env when
+ *                              last_step_all: t == max_steps - 1, model.py:229), all-ones action_avail; NULL fields skipped */
+int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n, float* d_out,
+                             int64_t pitch, int64_t row0, int64_t cap, void* stream);
+int fp_policy_rows_to_ring(FpPolicy* p, const float* d_src, int64_t n, int32_t width, float* d_field, int64_t row0,
+                           int64_t cap, void* stream);
+int fp_policy_scalars_to_ring(FpPolicy* p, const double* d_reward, const uint8_t* d_done, int64_t n, int32_t last_step_all,
+                              float* f_reward, float* f_done, float* f_last, float* f_avail, int64_t row0, int64_t cap,
+                              void* stream);
+/* Learner feed: the device part of unpack_data (model.py:308-323) on a batch sampled with fp_replay_sample.
+ * d_critic_in [batch * 5][745] = the MADDPG critic's input rows (maddpg.py:29-66: all agents' observations, one-hot
+ * agent id, all agents' actions); d_reward_norm [batch][5] = reward_normalisation (BatchNorm1d over the batch, training
+ * mode, initial affine parameters; model.py:321-322).  Either output may be NULL. */
+int fp_learner_feed(FpPolicy* p, const float* d_state, const float* d_action, const float* d_reward, int64_t batch,
+                    float* d_critic_in, float* d_reward_norm, void* stream);
+
 /* -- episode statistics (the only cross-GPU reduction; madrl/models/model.py:247-265) ----- */
 
 /* Every fp_step adds, per stepped env, to a device vector of FP_NSTATS doubles:

@@ -1,0 +1,741 @@
+// policy.cu -- the acting policy of the rollout loop on tcgen05 tensor cores.
+//
+//   fp_policy_load / fp_policy_act   replace, for N envs x 5 agents at once, what train_process does per step
+//       (madrl/models/model.py:215-216): prep_obs -> Model.policy (model.py:102-140: agent-id one-hot appended,
+//       shared parameters) -> RNNAgent.forward (madrl/agents/rnn_agent.py:24-32: fc1 -> LayerNorm -> ReLU ->
+//       GRUCell -> fc2) -> select_action (utils/util.py:50-64, continuous / action_enforcebound: x = mean + std eps,
+//       action = tanh(x), log_prob = Normal(mean, std).log_prob(x) - log(1 - action^2 + 1e-6); status 'test':
+//       action = tanh(mean)).
+//
+// Input is the env-minor observation ring the step kernel pushes into (fp_step_ring: ring[24][5][6][n_pad] fp32):
+// a tile is (one agent, 128 consecutive envs), and its 144 x 128 input block -- row k = (ring slot, feature),
+// 128 contiguous envs -- arrives with coalesced 16-byte LDGSTS copies; nothing is re-materialised.  The rotation of
+// the ring (the newest slot moves every step) is absorbed by the WEIGHTS: fc1 is linear in the observation, so the
+// loader prepares the 24 column rotations of W1 once and the kernel stages the one that matches the step's slot.
+// The one-hot agent id only selects a column of W1: it is folded into a per-agent bias.
+//
+// Kernel k_policy: one persistent CTA per SM, 8 worker warps (two threads per (env, agent) row: column halves) + one
+// MMA warp; all weights (139 KB as TF32, UMMA K-major layout) stay in shared memory for the lifetime of the CTA.
+// Per tile, three GEMM phases on tcgen05.mma kind::tf32, M = 128, A OPERAND IN TMEM (a thread owns a row and a TMEM
+// lane is a row, so tcgen05.st.32x32b writes the operand without touching shared memory), fp32 accumulators in TMEM:
+//     P0  workers: 2xTF32 split of the observation block (x = hi + lo, hi TF32-exact)          -> TMEM cols [0, 288)
+//     M1  fc1:  acc1[128][64]  = (Xhi + Xlo) W1^T                  36 MMAs, K = 144                  cols [288, 352)
+//     E1  workers: + bias(agent), LayerNorm (two-thread reduction), ReLU, split -> A2; h_in split -> A3   [0, 256)
+//     M2  GRU:  rz[128][128] = A2 Wih_rz^T + A3 Whh_rz^T;  gi_n = A2 Wih_n^T;  gh_n = A3 Whh_n^T   64 MMAs  [256, 512)
+//     E2  workers: r, z = sigmoid, n = tanh(gi_n + r gh_n), h' = (1 - z) n + z h  -> global, split -> A4   [0, 128)
+//     M3  fc2:  mean[128][16] = A4 W2^T                            16 MMAs                              [128, 144)
+//     E3  workers: + bias, tanh-Normal sampling (Philox4x32-10 + Box-Muller, or caller-supplied eps), outputs
+// Precision: activations keep fp32 accuracy through the two-term split (hi + lo, both products accumulated in fp32);
+// the WEIGHTS are held as TF32 (round-to-nearest, 10-bit mantissa): against torch fp32 with the same rounded weights
+// the means agree to ~1e-6, with arbitrary fp32 weights to ~3e-4 (tests/test_gpu_policy.py states both).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flex_common.cuh"
+
+namespace {
+
+constexpr int POL_M = 128;                 // rows per tile = envs of one agent
+constexpr int POL_OBS = 144, POL_HID = 64, POL_ACT = 4, POL_NA = 5, POL_H = 24, POL_F = 6;
+constexpr int N_WORKERS = 256;             // two threads per row
+constexpr int POL_THREADS = N_WORKERS + 32;
+constexpr uint32_t W1_BYTES = POL_OBS * POL_HID * 4;                       // 36 864: [36 kc][64 n][4]
+constexpr uint32_t WG_RZ_BYTES = POL_HID * 128 * 4, WG_N_BYTES = POL_HID * 64 * 4;   // [16 kc][N][4]
+constexpr uint32_t WG_BYTES = 2 * WG_RZ_BYTES + 2 * WG_N_BYTES;            // 98 304: rz_ih, rz_hh, n_ih, n_hh
+constexpr uint32_t W2_BYTES = POL_HID * 16 * 4;                            // 4 096: [16 kc][16 n][4] (4 outputs, padded)
+// small vectors (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (b_ih + b_hh), b_in[64], b_hn[64], b2[4] (+12 pad)
+constexpr int V_B1A = 0, V_LNG = 320, V_LNB = 384, V_BRZ = 448, V_BIN = 576, V_BHN = 640, V_B2 = 704, V_FLOATS = 720;
+constexpr uint32_t OFF_W1 = 0, OFF_WG = OFF_W1 + W1_BYTES, OFF_W2 = OFF_WG + WG_BYTES, OFF_VEC = OFF_W2 + W2_BYTES;
+constexpr uint32_t OFF_STAGE = OFF_VEC + V_FLOATS * 4;                     // [144][128] fp32 = 73 728
+constexpr uint32_t OFF_LN = OFF_STAGE + POL_OBS * POL_M * 4;               // [2 halves][128 rows] float2 (sum, sum of squares)
+constexpr uint32_t OFF_BAR = OFF_LN + 2 * POL_M * 8;                       // a_ready, mma_done, weights
+constexpr uint32_t OFF_TMEM = OFF_BAR + 32;
+constexpr uint32_t POL_SMEM = OFF_TMEM + 16;
+static_assert(POL_SMEM <= 227 * 1024, "policy kernel exceeds the shared memory of one SM");
+static_assert(OFF_STAGE % 16 == 0 && OFF_WG % 128 == 0 && OFF_W2 % 128 == 0, "operand alignment");
+// TMEM columns (512 = the whole TMEM: one CTA per SM)
+constexpr uint32_t C_XHI = 0, C_XLO = 144, C_ACC1 = 288;
+constexpr uint32_t C_A2HI = 0, C_A2LO = 64, C_A3HI = 128, C_A3LO = 192, C_RZ = 256, C_GIN = 384, C_GHN = 448;
+constexpr uint32_t C_A4HI = 0, C_A4LO = 64, C_ACC3 = 128;
+
+struct PolParams {
+    const float* ring; int64_t n_pad; int64_t n; int32_t slot;       // observation ring, newest slot
+    const float* W1rot; const float* Wg; const float* W2; const float* vec;
+    const float* hid_in; const uint8_t* reset; float* hid_out;        // [n][5][64]; reset: h_in = 0 for these envs
+    float* mean; float* action; float* logp;                          // [n][5][4]
+    const float* eps;                                                 // optional caller-supplied N(0,1) draws [n][5][4]
+    uint64_t seed; uint64_t step; float std_; float log_std; int32_t explore;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol mistake must surface as a trap, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int ID, int THREADS>
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(p));
+    return p != 0u;
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle: [k-chunk of 4 tf32][n][4]; LBO = bytes between the two
+// 16-byte K chunks of one MMA (= N * 16), SBO = bytes between 8-row groups (128); version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// Instruction descriptor: D fp32, A/B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t idesc_n(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(POL_M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem: lane = row, one 32-bit column per k] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
+    r[0] = __uint_as_float(a); r[1] = __uint_as_float(b); r[2] = __uint_as_float(c); r[3] = __uint_as_float(d);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// hi/lo split of four values into the TMEM A operand at columns col (hi part) and col + lo_off (lo part)
+__device__ __forceinline__ void split_st4(uint32_t lane_base, uint32_t col_hi, uint32_t col_lo, float a, float b, float c, float d) {
+    const float ha = tf32_hi(a), hb = tf32_hi(b), hc = tf32_hi(c), hd = tf32_hi(d);
+    tmem_st4(lane_base + col_hi, ha, hb, hc, hd);
+    tmem_st4(lane_base + col_lo, __fsub_rn(a, ha), __fsub_rn(b, hb), __fsub_rn(c, hc), __fsub_rn(d, hd));
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
+    float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
+    float2* lnp = reinterpret_cast<float2*>(smem + OFF_LN);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+    const int row = tid & (POL_M - 1), half = (tid >> 7) & 1;
+    const int64_t n_blocks = (prm.n + POL_M - 1) / POL_M, n_tiles = n_blocks * POL_NA;
+
+    // this tile's observation block: 144 rows (ring slot s, feature f) x 128 envs, each row 512 contiguous bytes
+    auto request = [&](int64_t tile) {
+        const int a = (int)(tile % POL_NA);
+        const int64_t e0 = (tile / POL_NA) * POL_M;
+        for (int ch = tid; ch < POL_OBS * 32; ch += N_WORKERS) {          // 16-byte chunks: 32 per row
+            const int k = ch >> 5, c4 = (ch & 31) * 4;
+            const int s = k / POL_F, f = k - s * POL_F;
+            float* dst = stage + k * POL_M + c4;
+            if (e0 + c4 + 4 <= prm.n_pad) cp_async16(dst, prm.ring + ((int64_t)(s * POL_NA + a) * POL_F + f) * prm.n_pad + e0 + c4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+
+    if (tid == 0) {
+        mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, W1_BYTES + WG_BYTES + W2_BYTES + V_FLOATS * 4);      // weights: four bulk copies, one barrier
+        tma_load_1d(smem_u32(smem + OFF_W1), prm.W1rot + (size_t)prm.slot * (W1_BYTES / 4), W1_BYTES, bar_w);
+        tma_load_1d(smem_u32(smem + OFF_WG), prm.Wg, WG_BYTES, bar_w);
+        tma_load_1d(smem_u32(smem + OFF_W2), prm.W2, W2_BYTES, bar_w);
+        tma_load_1d(smem_u32(smem + OFF_VEC), prm.vec, V_FLOATS * 4, bar_w);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < N_WORKERS && (int64_t)blockIdx.x < n_tiles) request(blockIdx.x);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == N_WORKERS / 32) {
+        // =============================================================== MMA warp
+        const uint32_t w1 = smem_u32(smem + OFF_W1), wg = smem_u32(smem + OFF_WG), w2 = smem_u32(smem + OFF_W2);
+        const uint32_t b_rz_ih = wg, b_rz_hh = wg + WG_RZ_BYTES, b_n_ih = wg + 2 * WG_RZ_BYTES, b_n_hh = b_n_ih + WG_N_BYTES;
+        uint32_t pa = 0;
+        bool first = true;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // ---- M1: fc1
+            mbar_wait(bar_a, pa); pa ^= 1u;
+            if (first) { mbar_wait(bar_w, 0u); first = false; }
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < POL_OBS / 8; ++ks) {
+                    const uint64_t db = umma_desc(w1 + ks * 2 * (64 * 16), 64 * 16, 128);
+                    umma_tf32_ts(tmem_base + C_ACC1, tmem_base + C_XHI + 8 * ks, db, idesc_n(64), ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + C_ACC1, tmem_base + C_XLO + 8 * ks, db, idesc_n(64), 1u);
+                }
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+            // ---- M2: GRU gates
+            mbar_wait(bar_a, pa); pa ^= 1u;
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < POL_HID / 8; ++ks) {
+                    const uint64_t d_rz_i = umma_desc(b_rz_ih + ks * 2 * (128 * 16), 128 * 16, 128);
+                    const uint64_t d_rz_h = umma_desc(b_rz_hh + ks * 2 * (128 * 16), 128 * 16, 128);
+                    const uint64_t d_n_i = umma_desc(b_n_ih + ks * 2 * (64 * 16), 64 * 16, 128);
+                    const uint64_t d_n_h = umma_desc(b_n_hh + ks * 2 * (64 * 16), 64 * 16, 128);
+                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A2HI + 8 * ks, d_rz_i, idesc_n(128), ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A2LO + 8 * ks, d_rz_i, idesc_n(128), 1u);
+                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A3HI + 8 * ks, d_rz_h, idesc_n(128), 1u);
+                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A3LO + 8 * ks, d_rz_h, idesc_n(128), 1u);
+                    umma_tf32_ts(tmem_base + C_GIN, tmem_base + C_A2HI + 8 * ks, d_n_i, idesc_n(64), ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + C_GIN, tmem_base + C_A2LO + 8 * ks, d_n_i, idesc_n(64), 1u);
+                    umma_tf32_ts(tmem_base + C_GHN, tmem_base + C_A3HI + 8 * ks, d_n_h, idesc_n(64), ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + C_GHN, tmem_base + C_A3LO + 8 * ks, d_n_h, idesc_n(64), 1u);
+                }
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+            // ---- M3: fc2
+            mbar_wait(bar_a, pa); pa ^= 1u;
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < POL_HID / 8; ++ks) {
+                    const uint64_t db = umma_desc(w2 + ks * 2 * (16 * 16), 16 * 16, 128);
+                    umma_tf32_ts(tmem_base + C_ACC3, tmem_base + C_A4HI + 8 * ks, db, idesc_n(16), ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + C_ACC3, tmem_base + C_A4LO + 8 * ks, db, idesc_n(16), 1u);
+                }
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =============================================================== workers: two threads per row (column halves)
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t pm = 0;
+        bool first = true;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int a = (int)(tile % POL_NA);
+            const int64_t e = (tile / POL_NA) * POL_M + row;
+            const bool live = e < prm.n;
+            const int64_t r_glob = e * POL_NA + a;                              // row of the reference's (b, n, .) tensors
+
+            // ---- P0: observation block -> TMEM (this thread: 72 of the row's 144 inputs)
+            cp_async_wait_all();
+            group_sync<1, N_WORKERS>();                                         // the block has landed; TMEM of the previous tile is drained
+#pragma unroll
+            for (int c = 0; c < 18; ++c) {
+                const int k0 = 72 * half + 4 * c;
+                split_st4(lane_base, C_XHI + k0, C_XLO + k0, stage[(k0 + 0) * POL_M + row], stage[(k0 + 1) * POL_M + row],
+                          stage[(k0 + 2) * POL_M + row], stage[(k0 + 3) * POL_M + row]);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+            group_sync<1, N_WORKERS>();                                         // every thread has read the staging block
+            if (tile + gridDim.x < n_tiles) request(tile + gridDim.x);          // the next block travels during the three GEMM phases
+            // the previous hidden state of this thread's 32 units (issued now, consumed after fc1)
+            float h[32];
+            {
+                const bool zero = !live || prm.hid_in == nullptr || (prm.reset != nullptr && prm.reset[e] != 0);
+                const float4* hp = reinterpret_cast<const float4*>(prm.hid_in + (zero ? 0 : r_glob) * POL_HID + 32 * half);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 t = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(hp + i);
+                    h[4 * i] = t.x; h[4 * i + 1] = t.y; h[4 * i + 2] = t.z; h[4 * i + 3] = t.w;
+                }
+            }
+            if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small vectors have landed
+
+            // ---- E1: fc1 epilogue: bias(agent), LayerNorm, ReLU -> A2; h -> A3
+            mbar_wait(bar_m, pm); pm ^= 1u;
+            tc_fence_after();
+            {
+                float v[32];
+                tmem_ld32(lane_base + C_ACC1 + 32 * half, v);
+                tmem_wait_ld();
+                float s = 0.0f, ss = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v[i] = __fadd_rn(v[i], vec[V_B1A + a * POL_HID + 32 * half + i]); s = __fadd_rn(s, v[i]); }
+                lnp[half * POL_M + row] = make_float2(s, 0.0f);
+                group_sync<1, N_WORKERS>();
+                const float mean = __fmul_rn(__fadd_rn(lnp[row].x, lnp[POL_M + row].x), 1.0f / POL_HID);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v[i] = __fsub_rn(v[i], mean); ss = fmaf(v[i], v[i], ss); }
+                group_sync<1, N_WORKERS>();                                     // the sums have been read: the cells are reused
+                lnp[half * POL_M + row] = make_float2(ss, 0.0f);
+                group_sync<1, N_WORKERS>();
+                const float var = __fmul_rn(__fadd_rn(lnp[row].x, lnp[POL_M + row].x), 1.0f / POL_HID);   // biased, as torch
+                const float rstd = rsqrtf(__fadd_rn(var, 1e-5f));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float y = fmaf(__fmul_rn(v[i], rstd), vec[V_LNG + 32 * half + i], vec[V_LNB + 32 * half + i]);
+                    v[i] = fmaxf(y, 0.0f);                                       // hid_activation = relu
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    split_st4(lane_base, C_A2HI + 32 * half + 4 * c, C_A2LO + 32 * half + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    split_st4(lane_base, C_A3HI + 32 * half + 4 * c, C_A3LO + 32 * half + 4 * c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+                }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+
+            // ---- E2: GRU cell (torch.nn.GRUCell: r, z, n gate order) -> h', A4
+            mbar_wait(bar_m, pm); pm ^= 1u;
+            tc_fence_after();
+            {
+                float g[32], hn[32];
+                tmem_ld32(lane_base + C_RZ + 64 + 32 * half, g);                 // z pre-activations
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) g[i] = sigmoidf_acc(__fadd_rn(g[i], vec[V_BRZ + 64 + 32 * half + i]));    // z
+                {
+                    float rp[32], gi[32];
+                    tmem_ld32(lane_base + C_RZ + 32 * half, rp);
+                    tmem_ld32(lane_base + C_GIN + 32 * half, gi);
+                    tmem_ld32(lane_base + C_GHN + 32 * half, hn);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float r = sigmoidf_acc(__fadd_rn(rp[i], vec[V_BRZ + 32 * half + i]));
+                        const float nn = tanhf(fmaf(r, __fadd_rn(hn[i], vec[V_BHN + 32 * half + i]), __fadd_rn(gi[i], vec[V_BIN + 32 * half + i])));
+                        hn[i] = fmaf(g[i], __fsub_rn(h[i], nn), nn);              // (1 - z) n + z h
+                    }
+                }
+                if (live) {
+                    float4* ho = reinterpret_cast<float4*>(prm.hid_out + r_glob * POL_HID + 32 * half);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ho[i] = make_float4(hn[4 * i], hn[4 * i + 1], hn[4 * i + 2], hn[4 * i + 3]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    split_st4(lane_base, C_A4HI + 32 * half + 4 * c, C_A4LO + 32 * half + 4 * c, hn[4 * c], hn[4 * c + 1], hn[4 * c + 2], hn[4 * c + 3]);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+
+            // ---- E3: fc2 epilogue + select_action (utils/util.py:50-64)
+            mbar_wait(bar_m, pm); pm ^= 1u;
+            tc_fence_after();
+            if (half == 0) {
+                float m[4];
+                tmem_ld4(lane_base + C_ACC3, m);
+                tmem_wait_ld();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) m[i] = __fadd_rn(m[i], vec[V_B2 + i]);
+                    if (prm.mean != nullptr) reinterpret_cast<float4*>(prm.mean)[r_glob] = make_float4(m[0], m[1], m[2], m[3]);
+                    float act[4], lp[4];
+                    if (prm.explore) {
+                        float z[4];
+                        if (prm.eps != nullptr) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(prm.eps) + r_glob);
+                            z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+                        } else {                                                 // Philox4x32-10 keyed by the seed, counter = (row, step)
+                            U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
+                            ctr.z = (uint32_t)prm.step; ctr.w = (uint32_t)(prm.step >> 32);
+                            const U4 rr = philox4x32_10(ctr, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+                            // Box-Muller on (0, 1] uniforms
+                            const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
+                            const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
+                            const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+                            float s0, c0, s1, c1;
+                            sincosf(6.283185307179586f * u1, &s0, &c0);
+                            sincosf(6.283185307179586f * u3, &s1, &c1);
+                            z[0] = ra * c0; z[1] = ra * s0; z[2] = rb * c1; z[3] = rb * s1;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x = fmaf(prm.std_, z[i], m[i]);          // Normal(mean, std).rsample()
+                            const float y = tanhf(x);
+                            // Normal.log_prob(x) = -(x - mean)^2 / (2 var) - log(std) - log(sqrt(2 pi)), then the tanh correction
+                            const float d = __fsub_rn(x, m[i]);
+                            float l = -__fdividef(__fmul_rn(d, d), __fmul_rn(2.0f, __fmul_rn(prm.std_, prm.std_)));
+                            l = __fsub_rn(__fsub_rn(l, prm.log_std), 0.9189385332046727f);
+                            lp[i] = __fsub_rn(l, logf(__fadd_rn(__fsub_rn(1.0f, __fmul_rn(y, y)), 1e-6f)));
+                            act[i] = y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { act[i] = tanhf(m[i]); lp[i] = 0.0f; }       // status == 'test' (util.py:82-85)
+                    }
+                    reinterpret_cast<float4*>(prm.action)[r_glob] = make_float4(act[0], act[1], act[2], act[3]);
+                    if (prm.logp != nullptr) reinterpret_cast<float4*>(prm.logp)[r_glob] = make_float4(lp[0], lp[1], lp[2], lp[3]);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------- transitions -> replay ring, learner feed
+// Pure data movement.
+//   k_window_gather   dense observation windows [n][5][144] (oldest entry first: get_obs, :387-401) of envs [0, n) from
+//                     the env-minor ring into rows of pitch `pitch` floats (a replay field, or a dense tensor)
+__global__ void __launch_bounds__(256) k_window_gather(const float* __restrict__ ring, int64_t n_pad, int slot, int64_t n,
+                                                       float* __restrict__ out, int64_t pitch, int64_t row0, int64_t cap) {
+    // block = (32 envs, one agent): the 144 x 32 block is read row by row (128-byte lines), transposed through shared
+    // memory and written as 32 rows of 144 contiguous floats (whole 32-byte sectors: a 24-byte scatter per history
+    // entry would cost a DRAM read-modify-write per store)
+    __shared__ float t[POL_OBS][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n_blk = (n + 31) >> 5;
+    for (int64_t blk = blockIdx.x; blk < n_blk * POL_NA; blk += gridDim.x) {
+        const int a = (int)(blk % POL_NA);
+        const int64_t e0 = (blk / POL_NA) << 5;
+        for (int k = w; k < POL_OBS; k += 8) {                    // k = r * 6 + f: r-th oldest entry lives in ring slot (slot + 1 + r) mod 24
+            const int r = k / POL_F, f = k - r * POL_F;
+            const int s = (slot + 1 + r) % POL_H;
+            t[k][lane] = (e0 + lane < n) ? ring[((int64_t)(s * POL_NA + a) * POL_F + f) * n_pad + e0 + lane] : 0.0f;
+        }
+        __syncthreads();
+        for (int j = w; j < 32; j += 8) {
+            if (e0 + j < n) {
+                int64_t orow = row0 + e0 + j; orow = orow >= cap ? orow - cap : orow;
+                float* dst = out + orow * pitch + a * POL_OBS;
+                for (int k = lane; k < POL_OBS; k += 32) dst[k] = t[k][j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// rows of `width` floats from a dense [n][width] source into ring rows (row0 + e) mod cap of pitch `width`
+__global__ void k_rows_to_ring(const float* __restrict__ src, int64_t n, int width, float* __restrict__ dst, int64_t row0, int64_t cap) {
+    const int64_t total = n * width, ring = cap * width, base = row0 * width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = base + i; o = o >= ring ? o - ring : o;
+        dst[o] = src[i];
+    }
+}
+
+// reward (fp64, one per env) repeated for the agents (model.py:221), done / last_step flags, all-ones availability
+__global__ void k_scalars_to_ring(const double* __restrict__ reward, const uint8_t* __restrict__ done, int64_t n, int last_step_all,
+                                  float* __restrict__ f_reward, float* __restrict__ f_done, float* __restrict__ f_last,
+                                  float* __restrict__ f_avail, int64_t row0, int64_t cap) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = row0 + e; o = o >= cap ? o - cap : o;
+        const float r = (float)reward[e];
+        const float d = done[e] ? 1.0f : 0.0f;
+        if (f_reward) {
+#pragma unroll
+            for (int a = 0; a < POL_NA; ++a) f_reward[o * POL_NA + a] = r;
+        }
+        if (f_done) f_done[o] = d;
+        if (f_last) f_last[o] = (done[e] || last_step_all) ? 1.0f : 0.0f;      // done_ = done or t == max_steps - 1 (model.py:229)
+        if (f_avail) {
+#pragma unroll
+            for (int j = 0; j < POL_NA * POL_ACT; ++j) f_avail[o * (POL_NA * POL_ACT) + j] = 1.0f;
+        }
+    }
+}
+
+// MADDPG critic input (madrl/models/maddpg.py:29-66, shared parameters, agent_id): for batch row b and agent i
+//   [ obs of all agents (5 x 144) | one-hot(i) (5) | actions of all agents (5 x 4) ]   = 745 floats
+__global__ void k_critic_input(const float* __restrict__ state, const float* __restrict__ action, int64_t batch, float* __restrict__ out) {
+    constexpr int W = POL_NA * POL_OBS + POL_NA + POL_NA * POL_ACT;
+    const int64_t total = batch * POL_NA * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % W);
+        const int64_t bi = i / W;
+        const int ag = (int)(bi % POL_NA);
+        const int64_t b = bi / POL_NA;
+        float v;
+        if (c < POL_NA * POL_OBS) v = state[b * (POL_NA * POL_OBS) + c];
+        else if (c < POL_NA * POL_OBS + POL_NA) v = (c - POL_NA * POL_OBS == ag) ? 1.0f : 0.0f;
+        else v = action[b * (POL_NA * POL_ACT) + (c - POL_NA * POL_OBS - POL_NA)];
+        out[i] = v;
+    }
+}
+
+// reward_normalisation (model.py:321-322): nn.BatchNorm1d(n_agents) in training mode with its initial affine
+// parameters (weight 1, bias 0: the module is in no optimiser): per agent column, (x - mean) / sqrt(var_biased + 1e-5)
+__global__ void k_reward_batchnorm(const float* __restrict__ reward, int64_t batch, float* __restrict__ out) {
+    const int a = blockIdx.x;                                       // one block per agent column
+    __shared__ double sh[2][256];
+    double s = 0.0, ss = 0.0;
+    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) { const double x = reward[b * POL_NA + a]; s += x; }
+    sh[0][threadIdx.x] = s; __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) { if ((int)threadIdx.x < d) sh[0][threadIdx.x] += sh[0][threadIdx.x + d]; __syncthreads(); }
+    const double mean = sh[0][0] / (double)batch;
+    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) { const double x = reward[b * POL_NA + a] - mean; ss += x * x; }
+    sh[1][threadIdx.x] = ss; __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) { if ((int)threadIdx.x < d) sh[1][threadIdx.x] += sh[1][threadIdx.x + d]; __syncthreads(); }
+    const double var = sh[1][0] / (double)batch;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5)), meanf = (float)mean;
+    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) out[b * POL_NA + a] = (reward[b * POL_NA + a] - meanf) * rstd;
+}
+
+int grid_for(int64_t total) {
+    int64_t g = (total + 255) / 256;
+    if (g < 1) g = 1;
+    return (int)(g > 148 * 16 ? 148 * 16 : g);
+}
+
+float round_tf32(float x) {                    // round to nearest even on the 13 dropped mantissa bits
+    uint32_t u; std::memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u += 0x00000FFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float y; std::memcpy(&y, &u, 4);
+    return y;
+}
+
+}  // namespace
+
+struct FpPolicy {
+    int device = 0;
+    int loaded = 0;
+    float* d_W1rot = nullptr; float* d_Wg = nullptr; float* d_W2 = nullptr; float* d_vec = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+thread_local std::string g_policy_err;
+int pfail(FpPolicy* p, int code, const std::string& msg) {
+    if (p) p->err = msg; else g_policy_err = msg;
+    return code;
+}
+}  // namespace
+
+extern "C" {
+
+int fp_policy_create(int device, FpPolicy** out) {
+    if (!out) return FP_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return pfail(nullptr, FP_ECUDA, "fp_policy_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return pfail(nullptr, FP_EINVAL, "fp_policy_create: bad device index");
+    FpPolicy* p = new FpPolicy();
+    p->device = device;
+    *out = p;
+    return FP_OK;
+}
+
+int fp_policy_destroy(FpPolicy* p) {
+    if (!p) return FP_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_W2); cudaFree(p->d_vec);
+    delete p;
+    return FP_OK;
+}
+
+const char* fp_policy_last_error(const FpPolicy* p) { return p ? p->err.c_str() : g_policy_err.c_str(); }
+int64_t fp_policy_launch_count(const FpPolicy* p) { return p ? p->launches : 0; }
+
+// Host weights in torch's layouts (state_dict of RNNAgent, madrl/agents/rnn_agent.py:11-16):
+//   fc1.weight [64][149] (144 observation columns + 5 agent-id columns), fc1.bias [64], layernorm.weight / .bias [64],
+//   rnn.weight_ih / weight_hh [192][64] (rows r | z | n), rnn.bias_ih / bias_hh [192], fc2.weight [4][64], fc2.bias [4]
+int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const float* ln_g, const float* ln_b, const float* w_ih,
+                   const float* w_hh, const float* b_ih, const float* b_hh, const float* fc2_w, const float* fc2_b) {
+    if (!p) return FP_EINVAL;
+    if (!fc1_w || !fc1_b || !ln_g || !ln_b || !w_ih || !w_hh || !b_ih || !b_hh || !fc2_w || !fc2_b)
+        return pfail(p, FP_EINVAL, "fp_policy_load: null weight array");
+    cudaSetDevice(p->device);
+    const int KIN = POL_OBS + POL_NA;
+    // fc1: 24 column rotations, UMMA K-major layout [kc][n][4]; ring slot s holds history entry r = (s - q - 1) mod 24
+    // when the newest slot is q, i.e. K index s * 6 + f must carry weight column r * 6 + f
+    std::vector<float> W1((size_t)POL_H * POL_OBS * POL_HID, 0.0f);
+    for (int q = 0; q < POL_H; ++q)
+        for (int s = 0; s < POL_H; ++s) {
+            const int r = ((s - q - 1) % POL_H + POL_H) % POL_H;
+            for (int f = 0; f < POL_F; ++f) {
+                const int k = s * POL_F + f, src = r * POL_F + f;
+                for (int n = 0; n < POL_HID; ++n)
+                    W1[(size_t)q * POL_OBS * POL_HID + ((size_t)(k >> 2) * POL_HID + n) * 4 + (k & 3)] = round_tf32(fc1_w[(size_t)n * KIN + src]);
+            }
+        }
+    auto pack = [](std::vector<float>& dst, size_t off, const float* w, int row0, int rows, int npad) {   // w [.][64] rows row0 .. row0 + rows
+        for (int n = 0; n < rows; ++n)
+            for (int k = 0; k < POL_HID; ++k)
+                dst[off + ((size_t)(k >> 2) * npad + n) * 4 + (k & 3)] = round_tf32(w[(size_t)(row0 + n) * POL_HID + k]);
+    };
+    std::vector<float> Wg(WG_BYTES / 4, 0.0f), W2(W2_BYTES / 4, 0.0f), vec(V_FLOATS, 0.0f);
+    pack(Wg, 0, w_ih, 0, 128, 128);
+    pack(Wg, WG_RZ_BYTES / 4, w_hh, 0, 128, 128);
+    pack(Wg, 2 * WG_RZ_BYTES / 4, w_ih, 128, 64, 64);
+    pack(Wg, 2 * WG_RZ_BYTES / 4 + WG_N_BYTES / 4, w_hh, 128, 64, 64);
+    pack(W2, 0, fc2_w, 0, POL_ACT, 16);
+    for (int a = 0; a < POL_NA; ++a)
+        for (int n = 0; n < POL_HID; ++n) vec[V_B1A + a * POL_HID + n] = fc1_b[n] + fc1_w[(size_t)n * KIN + POL_OBS + a];   // one-hot column folded in
+    for (int n = 0; n < POL_HID; ++n) { vec[V_LNG + n] = ln_g[n]; vec[V_LNB + n] = ln_b[n]; vec[V_BIN + n] = b_ih[128 + n]; vec[V_BHN + n] = b_hh[128 + n]; }
+    for (int n = 0; n < 128; ++n) vec[V_BRZ + n] = b_ih[n] + b_hh[n];
+    for (int n = 0; n < POL_ACT; ++n) vec[V_B2 + n] = fc2_b[n];
+    cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_W2); cudaFree(p->d_vec);
+    p->d_W1rot = p->d_Wg = p->d_W2 = p->d_vec = nullptr;
+    if (cudaMalloc(&p->d_W1rot, W1.size() * 4) != cudaSuccess || cudaMalloc(&p->d_Wg, Wg.size() * 4) != cudaSuccess ||
+        cudaMalloc(&p->d_W2, W2.size() * 4) != cudaSuccess || cudaMalloc(&p->d_vec, vec.size() * 4) != cudaSuccess)
+        return pfail(p, FP_ENOMEM, "fp_policy_load: cudaMalloc failed");
+    cudaMemcpy(p->d_W1rot, W1.data(), W1.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_Wg, Wg.data(), Wg.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_W2, W2.data(), W2.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_vec, vec.data(), vec.size() * 4, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaFuncSetAttribute(k_policy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->loaded = 1;
+    return FP_OK;
+}
+
+// One acting step for n_envs x 5 agents.  d_ring / slot / n_pad: the observation ring (fp_obs_ring, fp_step_ring).
+// d_hid_in (may be null = zeros) / d_hid_out: [n_envs][5][64]; d_reset (may be null): envs whose hidden state restarts
+// at zero (init_hidden, model.py:211).  d_mean, d_logp may be null.  explore = 1: status 'train' with exploration
+// (d_eps = caller-supplied standard-normal draws [n_envs][5][4], or null: Philox keyed by (seed, row, step));
+// explore = 0: status 'test'.  std = fixed_policy_std (default.yaml: 1.0).
+int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_hid_in,
+                  const uint8_t* d_reset, float* d_hid_out, float* d_mean, float* d_action, float* d_logp, const float* d_eps,
+                  uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!p->loaded) return pfail(p, FP_ESTATE, "fp_policy_act: call fp_policy_load first");
+    if (!d_ring || !d_hid_out || !d_action || n_envs < 1 || slot < 0 || slot >= POL_H || n_pad < n_envs || (n_pad & 3))
+        return pfail(p, FP_EINVAL, "fp_policy_act: bad arguments");
+    if (!(std_ > 0.0f)) return pfail(p, FP_EINVAL, "fp_policy_act: std must be positive");
+    cudaSetDevice(p->device);
+    PolParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.ring = d_ring; prm.n_pad = n_pad; prm.n = n_envs; prm.slot = slot;
+    prm.W1rot = p->d_W1rot; prm.Wg = p->d_Wg; prm.W2 = p->d_W2; prm.vec = p->d_vec;
+    prm.hid_in = d_hid_in; prm.reset = d_reset; prm.hid_out = d_hid_out;
+    prm.mean = d_mean; prm.action = d_action; prm.logp = d_logp; prm.eps = d_eps;
+    prm.seed = seed; prm.step = step; prm.std_ = std_; prm.log_std = std::log(std_); prm.explore = explore;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const int64_t tiles = (n_envs + POL_M - 1) / POL_M * POL_NA;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    k_policy<<<grid, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(prm);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+// Dense observation windows of envs [0, n) (get_obs layout [n][5][144], oldest entry first) from the ring into rows
+// (row0 + e) mod cap of pitch `pitch` floats: a replay field (state / next_state of the Transition, model.py:230-237)
+// or, with row0 = 0 and cap >= n, a dense tensor.
+int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n, float* d_out, int64_t pitch,
+                             int64_t row0, int64_t cap, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!d_ring || !d_out || n < 1 || pitch < POL_NA * POL_OBS || row0 < 0 || cap < n || row0 >= cap || slot < 0 || slot >= POL_H)
+        return pfail(p, FP_EINVAL, "fp_policy_gather_windows: bad arguments");
+    cudaSetDevice(p->device);
+    k_window_gather<<<grid_for(((n + 31) / 32) * POL_NA * 256), 256, 0, (cudaStream_t)stream>>>(d_ring, n_pad, slot, n, d_out, pitch, row0, cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+int fp_policy_rows_to_ring(FpPolicy* p, const float* d_src, int64_t n, int32_t width, float* d_field, int64_t row0, int64_t cap, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!d_src || !d_field || n < 1 || width < 1 || row0 < 0 || cap < n || row0 >= cap) return pfail(p, FP_EINVAL, "fp_policy_rows_to_ring: bad arguments");
+    cudaSetDevice(p->device);
+    k_rows_to_ring<<<grid_for(n * width), 256, 0, (cudaStream_t)stream>>>(d_src, n, width, d_field, row0, cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+int fp_policy_scalars_to_ring(FpPolicy* p, const double* d_reward, const uint8_t* d_done, int64_t n, int32_t last_step_all,
+                              float* f_reward, float* f_done, float* f_last, float* f_avail, int64_t row0, int64_t cap, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!d_reward || !d_done || n < 1 || row0 < 0 || cap < n || row0 >= cap) return pfail(p, FP_EINVAL, "fp_policy_scalars_to_ring: bad arguments");
+    cudaSetDevice(p->device);
+    k_scalars_to_ring<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(d_reward, d_done, n, last_step_all, f_reward, f_done, f_last, f_avail, row0, cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+// Learner feed (unpack_data, madrl/models/model.py:308-323, on a sampled batch already on the device):
+//   d_critic_in [batch * 5][745]: the MADDPG critic's input rows (maddpg.py:29-66); d_reward_norm [batch][5]: the
+//   reward after reward_normalisation (BatchNorm1d over the batch, training mode).  Either may be null.
+int fp_learner_feed(FpPolicy* p, const float* d_state, const float* d_action, const float* d_reward, int64_t batch,
+                    float* d_critic_in, float* d_reward_norm, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (batch < 1 || (d_critic_in && (!d_state || !d_action)) || (d_reward_norm && !d_reward)) return pfail(p, FP_EINVAL, "fp_learner_feed: bad arguments");
+    cudaSetDevice(p->device);
+    if (d_critic_in) {
+        k_critic_input<<<grid_for(batch * POL_NA * 745), 256, 0, (cudaStream_t)stream>>>(d_state, d_action, batch, d_critic_in);
+        p->launches++;
+    }
+    if (d_reward_norm) {
+        k_reward_batchnorm<<<POL_NA, 256, 0, (cudaStream_t)stream>>>(d_reward, batch, d_reward_norm);
+        p->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    return FP_OK;
+}
+
+}  // extern "C"

@@ -92,6 +92,17 @@ _PROTOS = {
     "fp_replay_field_ptr": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     "fp_predictor_load": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double]),
     "fp_predict": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "fp_policy_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "fp_policy_destroy": (C.c_int, [_P]),
+    "fp_policy_last_error": (C.c_char_p, [_P]),
+    "fp_policy_launch_count": (C.c_int64, [_P]),
+    "fp_policy_load": (C.c_int, [_P] * 11),
+    "fp_policy_act": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64,
+                                C.c_float, C.c_int32, _P]),
+    "fp_policy_gather_windows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "fp_policy_rows_to_ring": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int64, _P]),
+    "fp_policy_scalars_to_ring": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "fp_learner_feed": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS.keys())

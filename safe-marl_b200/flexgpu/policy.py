@@ -1,0 +1,230 @@
+"""The rollout loop on the device: acting policy, Transition writes, learner feed.
+
+DevicePolicy    the shared-parameter RNNAgent (madrl/agents/rnn_agent.py:8-32) + select_action
+                (utils/util.py:50-64) for N envs x 5 agents per call, through fp_policy_act (tcgen05), reading the
+                env's observation ring directly.
+DeviceRollout   the body of train_process (madrl/models/model.py:213-254) with nothing crossing PCIe:
+                policy -> fused translate_action + step + get_obs -> Transition fields into a DeviceReplayBuffer.
+learner_batch   unpack_data (model.py:308-323) on a sampled window: the 12 batch tensors + the MADDPG critic input.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .predictor import DeviceReplayBuffer
+
+N_AGENTS, OBS, HID, ACT = 5, 144, 64, 4
+# Transition (model.py:19) as fp32 replay fields, widths per transition (one env-step)
+TRANSITION_FIELDS = {"state": N_AGENTS * OBS, "action": N_AGENTS * ACT, "log_prob_a": N_AGENTS * ACT, "value": N_AGENTS,
+                     "next_value": N_AGENTS, "reward": N_AGENTS, "next_state": N_AGENTS * OBS, "done": 1, "last_step": 1,
+                     "action_avail": N_AGENTS * ACT, "last_hid": N_AGENTS * HID, "hid": N_AGENTS * HID}
+_WEIGHT_KEYS = ("fc1.weight", "fc1.bias", "layernorm.weight", "layernorm.bias", "rnn.weight_ih", "rnn.weight_hh",
+                "rnn.bias_ih", "rnn.bias_hh", "fc2.weight", "fc2.bias")
+_WEIGHT_SHAPES = ((HID, OBS + N_AGENTS), (HID,), (HID,), (HID,), (3 * HID, HID), (3 * HID, HID), (3 * HID,), (3 * HID,),
+                  (ACT, HID), (ACT,))
+
+
+def _ptr(t):
+    if t is None or isinstance(t, C.c_void_p):
+        return t
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_tf32(w):
+    """Round-to-nearest-even to TF32 (10-bit mantissa): how fp_policy_load holds the weights."""
+    u = np.ascontiguousarray(w, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x0FFF + ((u >> 13) & 1)) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(w))
+
+
+class DevicePolicy:
+    def __init__(self, state_dict=None, device="cuda:0", std=1.0, seed=0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.FlexGpuError("DevicePolicy needs a CUDA device; there is no CPU fallback")
+        self._lib = _lib.lib()
+        self._p = C.c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        rc = self._lib.fp_policy_create(idx, C.byref(self._p))
+        if rc != 0:
+            raise _lib.FlexGpuError(f"fp_policy_create failed ({rc}): {self._lib.fp_policy_last_error(None).decode()}")
+        self.std = float(std)                       # fixed_policy_std (default.yaml: 1.0; gaussian_policy False)
+        self.seed = int(seed)
+        self._bufs = {}
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise _lib.FlexGpuError(f"{what} failed ({rc}): {self._lib.fp_policy_last_error(self._p).decode()}")
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self._lib.fp_policy_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd):
+        """sd: RNNAgent.state_dict() (torch tensors) or a dict of arrays with the same keys."""
+        arrs = []
+        for k, shape in zip(_WEIGHT_KEYS, _WEIGHT_SHAPES):
+            v = sd[k]
+            a = np.ascontiguousarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+            if a.shape != shape:
+                raise ValueError(f"{k}: expected {shape}, got {a.shape} (hid_size 64, obs 144 + 5 agent ids, 4 actions)")
+            arrs.append(a)
+        self._check(self._lib.fp_policy_load(self._p, *[a.ctypes.data_as(C.c_void_p) for a in arrs]), "fp_policy_load")
+
+    def launch_count(self):
+        return int(self._lib.fp_policy_launch_count(self._p))
+
+    def _buf(self, name, shape):
+        b = self._bufs.get(name)
+        if b is None or b.shape != shape:
+            b = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._bufs[name] = b
+        return b
+
+    def act(self, ring, slot=None, n_envs=None, hid_in=None, reset=None, explore=True, eps=None, step=0, hid_out=None,
+            want_mean=False, want_logp=True):
+        """ring: an ObsRing (env.obs_ring() / step(..., return_obs='ring')) or a raw [24, 5, 6, n_pad] fp32 tensor with
+        `slot` / `n_envs`.  Returns (action [N,5,4], log_prob [N,5,4] or None, hid [N,5,64], mean or None); the output
+        tensors are reused by the next call unless hid_out is given."""
+        if hasattr(ring, "ring"):
+            slot, n_envs, ring = ring.slot, ring.env.n_envs, ring.ring
+        n_pad = ring.shape[-1]
+        N = int(n_envs)
+        action = self._buf("action", (N, N_AGENTS, ACT))
+        logp = self._buf("logp", (N, N_AGENTS, ACT)) if want_logp else None
+        mean = self._buf("mean", (N, N_AGENTS, ACT)) if want_mean else None
+        if hid_out is None:
+            hid_out = self._buf("hid", (N, N_AGENTS, HID))
+        if hid_in is not None and hid_in.data_ptr() == hid_out.data_ptr():
+            raise ValueError("hid_in and hid_out must be different buffers")
+        r = None if reset is None else reset.to(device=self.device, dtype=torch.uint8).contiguous()
+        e = None if eps is None else eps.to(device=self.device, dtype=torch.float32).contiguous()
+        self._check(self._lib.fp_policy_act(self._p, _ptr(ring), int(slot), int(n_pad), N, _ptr(hid_in), _ptr(r), _ptr(hid_out),
+                                            _ptr(mean), _ptr(action), _ptr(logp), _ptr(e), self.seed, int(step), self.std,
+                                            1 if explore else 0, _stream()), "fp_policy_act")
+        return action, logp, hid_out, mean
+
+    def gather_windows(self, ring, n, out, pitch, row0=0, cap=None):
+        slot, ringt = ring.slot, ring.ring
+        self._check(self._lib.fp_policy_gather_windows(self._p, _ptr(ringt), int(slot), int(ringt.shape[-1]), int(n), _ptr(out),
+                                                       int(pitch), int(row0), int(cap if cap is not None else n), _stream()),
+                    "fp_policy_gather_windows")
+
+
+class DeviceRollout:
+    """train_process (model.py:198-267) for N envs at once.  Per step: k_policy (act on the ring + last_hid) ->
+    fp_step_ring with FP_F32_POLICY actions (translate_action + step + pushing get_obs, one launch) -> Transition
+    fields of the first `record_envs` envs into `replay` (a DeviceReplayBuffer with TRANSITION_FIELDS).  value /
+    next_value are stored as zeros: MADDPG's losses recompute both from the critic (maddpg.py:104-107) and never read
+    them.  Episodes end together (95 steps, quirk Q1): the finished envs are reset from their Philox streams and their
+    hidden state restarts at zero (init_hidden, model.py:211)."""
+
+    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240):
+        self.env, self.policy, self.replay = env, policy, replay
+        self.N = env.n_envs
+        self.R = 0 if replay is None else int(self.N if record_envs is None else min(record_envs, self.N))
+        if replay is not None and (dict(replay.fields) != TRANSITION_FIELDS or self.R > replay.size):
+            raise ValueError("replay must be a DeviceReplayBuffer(TRANSITION_FIELDS) holding at least record_envs rows")
+        self.max_steps = int(max_steps)
+        dev = env.device
+        self._hid = [torch.zeros(self.N, N_AGENTS, HID, device=dev), torch.zeros(self.N, N_AGENTS, HID, device=dev)]
+        self._cur = 0
+        self._reset_mask = None
+        self.t = 0                                  # step within the episode
+        self.total_steps = 0
+        self.ring = None
+        self._fptr = {}
+        if replay is not None:
+            for i, k in enumerate(replay.names):
+                p = C.c_void_p()
+                replay._check(replay._lib.fp_replay_field_ptr(replay._r, i, C.byref(p)), "fp_replay_field_ptr")
+                self._fptr[k] = p
+            self._zeros = torch.zeros(self.R, N_AGENTS, device=dev)
+
+    def reset(self):
+        self.ring = self.env.reset(return_obs="ring")              # state, _ = env.reset() (model.py:208)
+        self._hid[self._cur].zero_()                                # init_hidden (model.py:211)
+        self._reset_mask = None
+        self.t = 0
+        return self.ring
+
+    def _rows(self, name, src, pos):
+        pol = self.policy
+        w = TRANSITION_FIELDS[name]
+        pol._check(pol._lib.fp_policy_rows_to_ring(pol._p, _ptr(src), self.R, w, self._fptr[name], pos, self.replay.size,
+                                                   _stream()), "fp_policy_rows_to_ring")
+
+    def step(self, explore=True, eps=None):
+        if self.ring is None:
+            self.reset()
+        env, pol = self.env, self.policy
+        last_hid, hid = self._hid[self._cur], self._hid[1 - self._cur]
+        action, logp, hid, _ = pol.act(self.ring, hid_in=last_hid, reset=self._reset_mask, explore=explore, eps=eps,
+                                       step=self.total_steps, hid_out=hid)                         # model.py:215-216
+        pos = None
+        if self.R:
+            pos = self.replay.reserve(self.R)
+            pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
+            if self._reset_mask is not None:       # a restarted env's last_hid is the zero state it acted from
+                last_hid = torch.where(self._reset_mask[:, None, None].bool(), torch.zeros_like(last_hid), last_hid)
+            self._rows("last_hid", last_hid, pos)
+        # translate_action (:218) + env.step (:220) + get_obs (:223) in one launch
+        reward, done, info, self.ring = env.step(action, translate=True, want_info=False, return_obs="ring")
+        self.t += 1
+        self.total_steps += 1
+        if self.R:
+            pol.gather_windows(self.ring, self.R, self._fptr["next_state"], TRANSITION_FIELDS["next_state"], pos, self.replay.size)
+            self._rows("action", action, pos); self._rows("log_prob_a", logp, pos); self._rows("hid", hid, pos)
+            self._rows("value", self._zeros, pos); self._rows("next_value", self._zeros, pos)
+            pol._check(pol._lib.fp_policy_scalars_to_ring(
+                pol._p, _ptr(reward), _ptr(done), self.R, 1 if self.t == self.max_steps else 0, self._fptr["reward"],
+                self._fptr["done"], self._fptr["last_step"], self._fptr["action_avail"], pos, self.replay.size, _stream()),
+                "fp_policy_scalars_to_ring")
+        self._cur = 1 - self._cur
+        self._reset_mask = None
+        if self.t >= env.episode_limit - 1 or self.t >= self.max_steps:        # every env of the batch has terminated (Q1)
+            mask = done.to(torch.uint8) if self.t < self.max_steps else torch.ones_like(done, dtype=torch.uint8)
+            self.ring = env.reset(mask=mask, return_obs="ring")
+            self._reset_mask = mask.clone()
+            self.t = 0
+        return reward, done
+
+
+def learner_batch(policy, replay, batch_size, start=None, reward_normalisation=True, critic_input=True):
+    """unpack_data (model.py:308-323) on `batch_size` consecutive transitions (get_batch, replay_buffer.py:14-21):
+    the reference's 12 tensors in its shapes -- including its quirk log_prob_a = action (:313) -- plus, for MADDPG,
+    `critic_in` [batch * 5, 745] (maddpg.py:29-66).  Everything stays on the device."""
+    b = replay.get_batch(batch_size, start=start)
+    B = batch_size
+    out = {
+        "state": b["state"].view(B, N_AGENTS, OBS), "action": b["action"].view(B, N_AGENTS, ACT),
+        "log_prob_a": b["action"].view(B, N_AGENTS, ACT),                     # sic: model.py:313 concatenates batch.action
+        "value": b["value"].view(B, N_AGENTS, 1), "next_value": b["next_value"].view(B, N_AGENTS, 1),
+        "reward": b["reward"], "next_state": b["next_state"].view(B, N_AGENTS, OBS), "done": b["done"].view(B, 1),
+        "last_step": b["last_step"].view(B, 1), "action_avail": b["action_avail"].view(B, N_AGENTS, ACT),
+        "last_hid": b["last_hid"].view(B, N_AGENTS, HID), "hid": b["hid"].view(B, N_AGENTS, HID),
+    }
+    crit = torch.empty(B * N_AGENTS, N_AGENTS * OBS + N_AGENTS + N_AGENTS * ACT, device=replay.device) if critic_input else None
+    rn = torch.empty(B, N_AGENTS, device=replay.device) if reward_normalisation else None
+    policy._check(policy._lib.fp_learner_feed(policy._p, _ptr(b["state"]), _ptr(b["action"]), _ptr(b["reward"]), B, _ptr(crit),
+                                              _ptr(rn), _stream()), "fp_learner_feed")
+    if reward_normalisation:
+        out["reward"] = rn
+    if critic_input:
+        out["critic_in"] = crit
+    return out

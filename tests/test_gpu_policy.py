@@ -1,0 +1,200 @@
+"""GPU parity of the device rollout path through the C ABI:
+
+  * fp_policy_act (tcgen05) against the reference's own RNNAgent + Model.policy + select_action run on CPU torch
+    (tests/golden/ref_policy.npz, written by tests/golden/make_ref_policy_golden.py from /root/reference).
+    Tolerances (fp32 arithmetic, stated): the device holds the weight MATRICES as TF32 and keeps activations at fp32
+    accuracy, so against the reference evaluated with the same TF32-rounded matrices means / hidden states / actions
+    agree to 2e-5 (observed ~2e-6) and log-probabilities to 2e-4 (the tanh correction log(1 - a^2 + 1e-6) amplifies
+    rounding near |a| = 1); against the reference with its unrounded fp32 initialisation the bound is 5e-4.
+  * Transition fields written by DeviceRollout against the env's own dense observations / rewards and the policy outputs
+    (bit-exact: pure data movement).
+  * learner_batch against the reference's TransReplayBuffer.get_batch + Model.unpack_data + MADDPG.value's critic input."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_policy.npz")
+KEYS = ("fc1.weight", "fc1.bias", "layernorm.weight", "layernorm.bias", "rnn.weight_ih", "rnn.weight_hh", "rnn.bias_ih",
+        "rnn.bias_hh", "fc2.weight", "fc2.bias")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def make_ring(obs, slot, cuda, n_pad=None):
+    """[n, 5, 144] windows (oldest entry first) -> the env-minor ring [24, 5, 6, n_pad] with its newest entry in `slot`."""
+    n = obs.shape[0]
+    n_pad = n_pad or (n + 31) // 32 * 32
+    w = torch.from_numpy(obs).view(n, 5, 24, 6)
+    ring = torch.zeros(24, 5, 6, n_pad)
+    for r in range(24):
+        ring[(slot + 1 + r) % 24, :, :, :n] = w[:, :, r, :].permute(1, 2, 0)
+    return ring.to(cuda).contiguous()
+
+
+@pytest.mark.parametrize("tag,tol,tol_lp", [("t_", 2e-5, 2e-4), ("", 5e-4, 5e-3)])
+def test_policy_matches_reference_rnn_agent(gold, cuda, tag, tol, tol_lp):
+    from flexgpu.policy import DevicePolicy
+    prefix = "wt_" if tag == "t_" else "w_"
+    pol = DevicePolicy({k: gold[prefix + k] for k in KEYS}, device=cuda, std=1.0)
+    n = gold["obs0"].shape[0]
+    hid = None
+    worst = {}
+    for t, slot in enumerate((7, 23, 0)):                       # three recurrent steps, three rotations of the ring
+        ring = make_ring(gold[f"obs{t}"], slot, cuda)
+        hid_out = torch.empty(n, 5, 64, device=cuda)
+        act, logp, hid_new, mean = pol.act(ring, slot=slot, n_envs=n, hid_in=hid, explore=True, eps=torch.from_numpy(gold[f"eps{t}"]),
+                                           hid_out=hid_out, want_mean=True)
+        for name, got, bound in (("mean", mean, tol), ("hid", hid_new, tol), ("action", act, tol), ("logp", logp, tol_lp)):
+            err = float(np.max(np.abs(got.cpu().numpy() - gold[f"{tag}{name}{t}"])))
+            worst[name] = max(worst.get(name, 0.0), err)
+            assert err < bound, (name, t, err)
+        act_t, lp_t, _, _ = pol.act(ring, slot=slot, n_envs=n, hid_in=hid, explore=False, hid_out=torch.empty_like(hid_out))
+        assert np.max(np.abs(act_t.cpu().numpy() - gold[f"{tag}action_test{t}"])) < tol          # status 'test': tanh(mean)
+        hid = hid_new
+    print("max abs errors vs reference", tag or "fp32-weights", worst)
+    pol.close()
+
+
+def test_policy_rows_are_independent_and_ragged_sizes(gold, cuda):
+    """Any n (tail blocks, n not a multiple of 128 or 32): every row depends on its own inputs only."""
+    from flexgpu.policy import DevicePolicy
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda)
+    obs = gold["obs1"]
+    full = None
+    for n in (160, 129, 128, 33, 1):
+        ring = make_ring(obs[:n], 5, cuda)
+        h_in = torch.from_numpy(gold["t_hid0"][:n]).to(cuda).contiguous()
+        act, _, hid, mean = pol.act(ring, slot=5, n_envs=n, hid_in=h_in, explore=False, want_mean=True, hid_out=torch.empty(n, 5, 64, device=cuda))
+        got = (mean.cpu().numpy().copy(), hid.cpu().numpy().copy())
+        if full is None:
+            full = got
+        else:
+            assert np.array_equal(got[0], full[0][:n]) and np.array_equal(got[1], full[1][:n])
+    # reset mask: the masked envs act from a zero hidden state
+    n = 160
+    ring = make_ring(obs, 5, cuda)
+    h_in = torch.from_numpy(gold["t_hid0"]).to(cuda).contiguous()
+    mask = torch.zeros(n, dtype=torch.uint8, device=cuda); mask[::3] = 1
+    _, _, hid_m, mean_m = pol.act(ring, slot=5, n_envs=n, hid_in=h_in, reset=mask, explore=False, want_mean=True, hid_out=torch.empty(n, 5, 64, device=cuda))
+    mean_m = mean_m.cpu().numpy().copy()
+    _, _, _, mean_z = pol.act(ring, slot=5, n_envs=n, hid_in=None, explore=False, want_mean=True, hid_out=torch.empty(n, 5, 64, device=cuda))
+    mean_z = mean_z.cpu().numpy()
+    assert np.array_equal(mean_m[::3], mean_z[::3]) and np.array_equal(np.delete(mean_m, np.s_[::3], 0), np.delete(full[0], np.s_[::3], 0))
+    pol.close()
+
+
+def test_policy_philox_sampling(gold, cuda):
+    """Device-side exploration noise: N(0, 1) draws keyed by (seed, row, step) -- reproducible, step-dependent."""
+    from flexgpu.policy import DevicePolicy
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda, std=1.0, seed=1234)
+    n = 4096
+    obs = np.tile(gold["obs0"], (26, 1, 1))[:n]
+    ring = make_ring(obs, 3, cuda)
+    a1, lp1, _, m1 = pol.act(ring, slot=3, n_envs=n, explore=True, step=7, want_mean=True)
+    a1, lp1, m1 = a1.double().cpu().numpy().copy(), lp1.cpu().numpy().copy(), m1.double().cpu().numpy().copy()
+    a2, _, _, _ = pol.act(ring, slot=3, n_envs=n, explore=True, step=7)
+    assert np.array_equal(a1, a2.double().cpu().numpy())
+    a3, _, _, _ = pol.act(ring, slot=3, n_envs=n, explore=True, step=8)
+    assert not np.array_equal(a1, a3.double().cpu().numpy())
+    ok = np.abs(a1) < 0.999
+    z = (np.arctanh(np.where(ok, a1, 0.0)) - m1)[ok]
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.03 and abs(np.mean(z ** 3)) < 0.08
+    # log_prob consistent with the draws (utils/util.py:56-61)
+    want = -0.5 * z ** 2 - 0.9189385332046727 - np.log(1.0 - a1[ok] ** 2 + 1e-6)
+    assert np.max(np.abs(lp1[ok] - want)) < 2e-2 and np.median(np.abs(lp1[ok] - want)) < 1e-5
+    pol.close()
+
+
+@pytest.fixture()
+def small_env(cuda, profiles):
+    from flexgpu import BatchedFlexProvisionEnv
+    e = BatchedFlexProvisionEnv(None, n_envs=300, device=cuda, profiles=profiles, seed=3)
+    yield e
+    e.close()
+
+
+def test_rollout_writes_the_transition_fields(gold, cuda, small_env):
+    """DeviceRollout = train_process's loop body (model.py:213-254): what lands in the replay ring is exactly what the
+    env and the policy produced at that step."""
+    from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS
+    from flexgpu.predictor import DeviceReplayBuffer
+    env = small_env
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda, seed=9)
+    R = 200
+    buf = DeviceReplayBuffer(3 * R + 50, TRANSITION_FIELDS, device=cuda)
+    ro = DeviceRollout(env, pol, replay=buf, record_envs=R)
+    ro.reset()
+    steps = []
+    for t in range(4):                                          # the fourth step wraps the FIFO
+        pre = ro.ring.dense().clone()
+        last_hid = ro._hid[ro._cur].clone()
+        reward, done = ro.step()
+        steps.append(dict(state=pre[:R].reshape(R, -1), next_state=ro.ring.dense()[:R].reshape(R, -1).clone(),
+                          last_hid=last_hid[:R].reshape(R, -1), hid=ro._hid[ro._cur][:R].reshape(R, -1).clone(),
+                          action=pol._bufs["action"][:R].reshape(R, -1).clone(), log_prob_a=pol._bufs["logp"][:R].reshape(R, -1).clone(),
+                          reward=reward[:R, None].float().repeat(1, 5).clone(), done=done[:R, None].float().clone()))
+    assert len(buf) == 3 * R + 50
+    got = buf.get_batch(3 * R + 50, start=0)                    # oldest first: the last 50 rows of step 0, then steps 1..3
+    want = {k: torch.cat([steps[0][k][R - 50:]] + [s[k] for s in steps[1:]]) for k in steps[0]}
+    for k, w in want.items():
+        assert torch.equal(got[k], w), k
+    assert torch.equal(got["last_step"], got["done"]) and bool((got["action_avail"] == 1).all())
+    assert bool((got["value"] == 0).all()) and bool((got["next_value"] == 0).all())
+    # the hidden state is carried: last_hid of step t + 1 is hid of step t
+    assert torch.equal(steps[2]["last_hid"], steps[1]["hid"])
+    pol.close(); buf.close()
+
+
+def test_rollout_episode_boundary_resets_hidden_state(gold, cuda, profiles):
+    from flexgpu import BatchedFlexProvisionEnv
+    from flexgpu.policy import DevicePolicy, DeviceRollout
+    env = BatchedFlexProvisionEnv(None, n_envs=64, device=cuda, profiles=profiles, seed=4)
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda, seed=2)
+    ro = DeviceRollout(env, pol)
+    ro.reset()
+    for t in range(95):
+        reward, done = ro.step()
+    assert bool(done.all()) and ro.t == 0 and ro._reset_mask is not None       # 95 steps: every env terminated and was reset
+    assert int(env.steps.min()) == 1 and int(env.steps.max()) == 1
+    # the first action of the new episode comes from a zero hidden state
+    ring = ro.ring
+    _, _, _, mean_z = pol.act(ring, hid_in=None, explore=False, want_mean=True, hid_out=torch.empty(64, 5, 64, device=cuda))
+    mean_z = mean_z.cpu().numpy().copy()
+    _, _, _, mean_r = pol.act(ring, hid_in=ro._hid[ro._cur], reset=ro._reset_mask, explore=False, want_mean=True,
+                              hid_out=torch.empty(64, 5, 64, device=cuda))
+    assert np.array_equal(mean_z, mean_r.cpu().numpy())
+    stats = env.episode_stats()
+    assert float(stats["env_steps"]) == 64 * 95 and float(stats["episodes"]) == 64
+    pol.close(); env.close()
+
+
+def test_learner_batch_matches_reference_unpack_data(gold, cuda):
+    """TransReplayBuffer(64) fed 80 transitions, get_batch(32) with the reference's np.random draw, Model.unpack_data
+    and the critic input MADDPG.value builds -- against DeviceReplayBuffer + learner_batch on the same transitions."""
+    from flexgpu.policy import DevicePolicy, TRANSITION_FIELDS, learner_batch
+    from flexgpu.predictor import DeviceReplayBuffer
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda)
+    buf = DeviceReplayBuffer(64, TRANSITION_FIELDS, device=cuda)
+    n_tr = gold["tr_state"].shape[0]
+    for lo in range(0, n_tr, 7):                                 # add_experience in uneven chunks
+        hi = min(n_tr, lo + 7)
+        buf.add_experience({k: torch.from_numpy(gold["tr_" + k][lo:hi]).to(cuda) for k in TRANSITION_FIELDS})
+    assert len(buf) == 64
+    out = learner_batch(pol, buf, 32, start=int(gold["batch_start"]))
+    for k in ("state", "action", "log_prob_a", "value", "next_value", "next_state", "done", "last_step", "action_avail", "last_hid", "hid"):
+        want = gold["up_" + k]
+        assert tuple(out[k].shape) == want.shape, k
+        assert np.array_equal(out[k].cpu().numpy(), want.astype(np.float32)), k
+    assert np.array_equal(out["log_prob_a"].cpu().numpy(), gold["up_action"])            # the reference's quirk (model.py:313)
+    assert np.max(np.abs(out["reward"].cpu().numpy() - gold["up_reward"])) < 1e-5        # BatchNorm1d over the batch
+    assert tuple(out["critic_in"].shape) == gold["critic_in"].shape == (160, 745)
+    assert np.array_equal(out["critic_in"].cpu().numpy(), gold["critic_in"])
+    raw = learner_batch(pol, buf, 32, start=int(gold["batch_start"]), reward_normalisation=False, critic_input=False)
+    assert "critic_in" not in raw and float(raw["reward"].abs().max()) > 0
+    pol.close(); buf.close()
