@@ -14,20 +14,24 @@
 // loader prepares the 24 column rotations of W1 once and the kernel stages the one that matches the step's slot.
 // The one-hot agent id only selects a column of W1: it is folded into a per-agent bias.
 //
-// Kernel k_policy: one persistent CTA per SM, 8 worker warps (two threads per (env, agent) row: column halves) + one
-// MMA warp; all weights (139 KB as TF32, UMMA K-major layout) stay in shared memory for the lifetime of the CTA.
-// Per tile, three GEMM phases on tcgen05.mma kind::tf32, M = 128, A OPERAND IN TMEM (a thread owns a row and a TMEM
+// Kernel k_policy: one persistent CTA per SM, 16 worker warps (FOUR threads per (env, agent) row: column quarters) + one
+// MMA warp; the matrices (135 KB as TF32, UMMA K-major layout) stay in shared memory for the lifetime of the CTA.
+// Per tile, two GEMM phases on tcgen05.mma kind::tf32, M = 128, A OPERAND IN TMEM (a thread owns a row and a TMEM
 // lane is a row, so tcgen05.st.32x32b writes the operand without touching shared memory), fp32 accumulators in TMEM:
 //     P0  workers: 2xTF32 split of the observation block (x = hi + lo, hi TF32-exact)          -> TMEM cols [0, 288)
 //     M1  fc1:  acc1[128][64]  = (Xhi + Xlo) W1^T                  36 MMAs, K = 144                  cols [288, 352)
-//     E1  workers: + bias(agent), LayerNorm (two-thread reduction), ReLU, split -> A2; h_in split -> A3   [0, 256)
+//     E1  workers: + bias(agent), LayerNorm (four-thread reduction), ReLU, split -> A2; h_in split -> A3  [0, 256)
 //     M2  GRU:  rz[128][128] = A2 Wih_rz^T + A3 Whh_rz^T;  gi_n = A2 Wih_n^T;  gh_n = A3 Whh_n^T   64 MMAs  [256, 512)
-//     E2  workers: r, z = sigmoid, n = tanh(gi_n + r gh_n), h' = (1 - z) n + z h  -> global, split -> A4   [0, 128)
-//     M3  fc2:  mean[128][16] = A4 W2^T                            16 MMAs                              [128, 144)
-//     E3  workers: + bias, tanh-Normal sampling (Philox4x32-10 + Box-Muller, or caller-supplied eps), outputs
+//     E2  workers: r, z = sigmoid, n = tanh(gi_n + r gh_n), h' = (1 - z) n + z h -> global; fc2 (64 -> 4: 256 FMAs per
+//         row, on the CUDA cores in fp32 with the unrounded weights -- cheaper than a third tensor-core round trip),
+//         four-thread reduction, + bias, tanh-Normal sampling (Philox4x32-10 + Box-Muller, or caller-supplied eps)
+// The workers' phases and the MMA phases of one tile are serial (one tile fills the 512 TMEM columns: the split
+// doubles every A operand); the next tile's observation block travels (LDGSTS) underneath.
 // Precision: activations keep fp32 accuracy through the two-term split (hi + lo, both products accumulated in fp32);
-// the WEIGHTS are held as TF32 (round-to-nearest, 10-bit mantissa): against torch fp32 with the same rounded weights
-// the means agree to ~1e-6, with arbitrary fp32 weights to ~3e-4 (tests/test_gpu_policy.py states both).
+// the fc1 / GRU MATRICES are held as TF32 (round-to-nearest, 10-bit mantissa): against torch fp32 with the same
+// rounded matrices the means agree to ~1e-6, with arbitrary fp32 weights to ~3e-4 (tests/test_gpu_policy.py states both).
+#include <cuda.h>
+
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -39,34 +43,37 @@ namespace {
 
 constexpr int POL_M = 128;                 // rows per tile = envs of one agent
 constexpr int POL_OBS = 144, POL_HID = 64, POL_ACT = 4, POL_NA = 5, POL_H = 24, POL_F = 6;
-constexpr int N_WORKERS = 256;             // two threads per row
+constexpr int TPR = 4;                     // worker threads per row (column quarters)
+constexpr int N_WORKERS = TPR * POL_M;     // 512
 constexpr int POL_THREADS = N_WORKERS + 32;
+constexpr int CPT = POL_HID / TPR;         // hidden columns per thread: 16
+constexpr int KPT = POL_OBS / TPR;         // observation inputs per thread: 36
 constexpr uint32_t W1_BYTES = POL_OBS * POL_HID * 4;                       // 36 864: [36 kc][64 n][4]
 constexpr uint32_t WG_RZ_BYTES = POL_HID * 128 * 4, WG_N_BYTES = POL_HID * 64 * 4;   // [16 kc][N][4]
 constexpr uint32_t WG_BYTES = 2 * WG_RZ_BYTES + 2 * WG_N_BYTES;            // 98 304: rz_ih, rz_hh, n_ih, n_hh
-constexpr uint32_t W2_BYTES = POL_HID * 16 * 4;                            // 4 096: [16 kc][16 n][4] (4 outputs, padded)
-// small vectors (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (b_ih + b_hh), b_in[64], b_hn[64], b2[4] (+12 pad)
-constexpr int V_B1A = 0, V_LNG = 320, V_LNB = 384, V_BRZ = 448, V_BIN = 576, V_BHN = 640, V_B2 = 704, V_FLOATS = 720;
-constexpr uint32_t OFF_W1 = 0, OFF_WG = OFF_W1 + W1_BYTES, OFF_W2 = OFF_WG + WG_BYTES, OFF_VEC = OFF_W2 + W2_BYTES;
+// small arrays (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (b_ih + b_hh), b_in[64], b_hn[64], W2[4][64] (fp32), b2[4] (+12 pad)
+constexpr int V_B1A = 0, V_LNG = 320, V_LNB = 384, V_BRZ = 448, V_BIN = 576, V_BHN = 640, V_W2 = 704, V_B2 = 960, V_FLOATS = 992;
+constexpr uint32_t OFF_W1 = 0, OFF_WG = OFF_W1 + W1_BYTES, OFF_VEC = OFF_WG + WG_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_VEC + V_FLOATS * 4;                     // [144][128] fp32 = 73 728
-constexpr uint32_t OFF_LN = OFF_STAGE + POL_OBS * POL_M * 4;               // [2 halves][128 rows] float2 (sum, sum of squares)
-constexpr uint32_t OFF_BAR = OFF_LN + 2 * POL_M * 8;                       // a_ready, mma_done, weights
+constexpr uint32_t OFF_LN = OFF_STAGE + POL_OBS * POL_M * 4;               // [TPR][128 rows] float2 (sum, sum of squares)
+constexpr uint32_t OFF_FC = OFF_LN + TPR * POL_M * 8;                      // [TPR][128 rows] float4: fc2 partial sums
+constexpr uint32_t OFF_BAR = OFF_FC + TPR * POL_M * 16;                    // a_ready, mma_done, weights, x_full
 constexpr uint32_t OFF_TMEM = OFF_BAR + 32;
 constexpr uint32_t POL_SMEM = OFF_TMEM + 16;
 static_assert(POL_SMEM <= 227 * 1024, "policy kernel exceeds the shared memory of one SM");
-static_assert(OFF_STAGE % 16 == 0 && OFF_WG % 128 == 0 && OFF_W2 % 128 == 0, "operand alignment");
+static_assert(OFF_STAGE % 128 == 0 && OFF_WG % 128 == 0 && OFF_VEC % 16 == 0 && (V_FLOATS * 4) % 16 == 0, "operand alignment");
 // TMEM columns (512 = the whole TMEM: one CTA per SM)
 constexpr uint32_t C_XHI = 0, C_XLO = 144, C_ACC1 = 288;
 constexpr uint32_t C_A2HI = 0, C_A2LO = 64, C_A3HI = 128, C_A3LO = 192, C_RZ = 256, C_GIN = 384, C_GHN = 448;
-constexpr uint32_t C_A4HI = 0, C_A4LO = 64, C_ACC3 = 128;
 
 struct PolParams {
     const float* ring; int64_t n_pad; int64_t n; int32_t slot;       // observation ring, newest slot
-    const float* W1rot; const float* Wg; const float* W2; const float* vec;
+    const float* W1rot; const float* Wg; const float* vec;
     const float* hid_in; const uint8_t* reset; float* hid_out;        // [n][5][64]; reset: h_in = 0 for these envs
     float* mean; float* action; float* logp;                          // [n][5][4]
     const float* eps;                                                 // optional caller-supplied N(0,1) draws [n][5][4]
     uint64_t seed; uint64_t step; float std_; float log_std; int32_t explore;
+    int32_t use_tma;                                                  // observation blocks by one 3-D TMA box copy per tile
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +101,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// One box of the 3-D ring view [24 slots][30 = agent x feature][n_pad envs]: 24 x 6 x 128 floats -> [144][128] in shared memory
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, int32_t c_env, int32_t c_row, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c_env), "r"(c_row), "r"(0), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -153,6 +165,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -165,47 +194,64 @@ __device__ __forceinline__ void split_st4(uint32_t lane_base, uint32_t col_hi, u
     tmem_st4(lane_base + col_lo, __fsub_rn(a, ha), __fsub_rn(b, hb), __fsub_rn(c, hc), __fsub_rn(d, hd));
 }
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+// Gate non-linearities from the SFU exponential (ex2.approx, 2 ulp) and reciprocal: absolute error ~2e-7 on (0, 1) /
+// (-1, 1), i.e. fp32 rounding level -- the accurate library tanhf / expf cost 4x the instructions, and the gates are
+// 96 evaluations per thread and tile.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x))); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float ax = fminf(fabsf(x), 15.0f);                       // tanh(15) == 1 in fp32; keeps e^{2x} finite
+    const float t = __fsub_rn(1.0f, __fdividef(2.0f, __fadd_rn(__expf(__fmul_rn(2.0f, ax)), 1.0f)));
+    return copysignf(t, x);
+}
 
-__global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm) {
+__global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
     float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
     float2* lnp = reinterpret_cast<float2*>(smem + OFF_LN);
+    float4* fcp = reinterpret_cast<float4*>(smem + OFF_FC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16;
+    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
-    const int row = tid & (POL_M - 1), half = (tid >> 7) & 1;
+    const int row = tid & (POL_M - 1), qt = (tid >> 7) & (TPR - 1);        // row of the tile, column quarter
     const int64_t n_blocks = (prm.n + POL_M - 1) / POL_M, n_tiles = n_blocks * POL_NA;
 
-    // this tile's observation block: 144 rows (ring slot s, feature f) x 128 envs, each row 512 contiguous bytes
+    // this tile's observation block: 144 rows (ring slot s, feature f) x 128 envs, each row 512 contiguous bytes.
+    // One TMA box copy by the MMA warp (tma_request); rings narrower than a tile take coalesced LDGSTS by the workers.
+    auto tma_request = [&](int64_t tile) {                                   // one thread
+        mbar_expect_tx(bar_x, POL_OBS * POL_M * 4);
+        tma_load_box(smem_u32(stage), &tmap, (int32_t)((tile / POL_NA) * POL_M), (int32_t)(tile % POL_NA) * POL_F, bar_x);
+    };
     auto request = [&](int64_t tile) {
         const int a = (int)(tile % POL_NA);
         const int64_t e0 = (tile / POL_NA) * POL_M;
-        for (int ch = tid; ch < POL_OBS * 32; ch += N_WORKERS) {          // 16-byte chunks: 32 per row
-            const int k = ch >> 5, c4 = (ch & 31) * 4;
+        const int c4 = (tid & 31) * 4;
+        const bool inside = e0 + c4 + 4 <= prm.n_pad;
+#pragma unroll
+        for (int i = 0; i < POL_OBS * 32 / N_WORKERS; ++i) {               // 16-byte chunks: 32 per row, one row per warp and trip
+            const int k = (tid >> 5) + (N_WORKERS / 32) * i;
             const int s = k / POL_F, f = k - s * POL_F;
             float* dst = stage + k * POL_M + c4;
-            if (e0 + c4 + 4 <= prm.n_pad) cp_async16(dst, prm.ring + ((int64_t)(s * POL_NA + a) * POL_F + f) * prm.n_pad + e0 + c4);
+            if (inside) cp_async16(dst, prm.ring + ((int64_t)(s * POL_NA + a) * POL_F + f) * prm.n_pad + e0 + c4);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         cp_async_commit();
     };
 
     if (tid == 0) {
-        mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1);
+        mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1); mbar_init(bar_x, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_w, W1_BYTES + WG_BYTES + W2_BYTES + V_FLOATS * 4);      // weights: four bulk copies, one barrier
+        if (prm.use_tma && (int64_t)blockIdx.x < n_tiles) tma_request(blockIdx.x);
+        mbar_expect_tx(bar_w, W1_BYTES + WG_BYTES + V_FLOATS * 4);          // weights: three bulk copies, one barrier
         tma_load_1d(smem_u32(smem + OFF_W1), prm.W1rot + (size_t)prm.slot * (W1_BYTES / 4), W1_BYTES, bar_w);
         tma_load_1d(smem_u32(smem + OFF_WG), prm.Wg, WG_BYTES, bar_w);
-        tma_load_1d(smem_u32(smem + OFF_W2), prm.W2, W2_BYTES, bar_w);
         tma_load_1d(smem_u32(smem + OFF_VEC), prm.vec, V_FLOATS * 4, bar_w);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid < N_WORKERS && (int64_t)blockIdx.x < n_tiles) request(blockIdx.x);
+    if (!prm.use_tma && tid < N_WORKERS && (int64_t)blockIdx.x < n_tiles) request(blockIdx.x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -213,7 +259,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm) 
 
     if (warp == N_WORKERS / 32) {
         // =============================================================== MMA warp
-        const uint32_t w1 = smem_u32(smem + OFF_W1), wg = smem_u32(smem + OFF_WG), w2 = smem_u32(smem + OFF_W2);
+        const uint32_t w1 = smem_u32(smem + OFF_W1), wg = smem_u32(smem + OFF_WG);
         const uint32_t b_rz_ih = wg, b_rz_hh = wg + WG_RZ_BYTES, b_n_ih = wg + 2 * WG_RZ_BYTES, b_n_hh = b_n_ih + WG_N_BYTES;
         uint32_t pa = 0;
         bool first = true;
@@ -224,6 +270,8 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm) 
             tc_fence_after();
             __syncwarp();
             if (elect_one()) {
+                // every worker has read the staging block (P0): the next tile's block travels during the GEMM phases
+                if (prm.use_tma && tile + gridDim.x < n_tiles) tma_request(tile + gridDim.x);
 #pragma unroll
                 for (int ks = 0; ks < POL_OBS / 8; ++ks) {
                     const uint64_t db = umma_desc(w1 + ks * 2 * (64 * 16), 64 * 16, 128);
@@ -256,25 +304,12 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm) 
                 umma_commit(bar_m);
             }
             __syncwarp();
-            // ---- M3: fc2
-            mbar_wait(bar_a, pa); pa ^= 1u;
-            tc_fence_after();
-            __syncwarp();
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < POL_HID / 8; ++ks) {
-                    const uint64_t db = umma_desc(w2 + ks * 2 * (16 * 16), 16 * 16, 128);
-                    umma_tf32_ts(tmem_base + C_ACC3, tmem_base + C_A4HI + 8 * ks, db, idesc_n(16), ks > 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_base + C_ACC3, tmem_base + C_A4LO + 8 * ks, db, idesc_n(16), 1u);
-                }
-                umma_commit(bar_m);
-            }
-            __syncwarp();
         }
     } else {
-        // =============================================================== workers: two threads per row (column halves)
+        // =============================================================== workers: four threads per row (column quarters)
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t pm = 0;
+        const int c0 = CPT * qt;                                               // this thread's 16 hidden columns
+        uint32_t pm = 0, px = 0;
         bool first = true;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int a = (int)(tile % POL_NA);
@@ -282,153 +317,152 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm) 
             const bool live = e < prm.n;
             const int64_t r_glob = e * POL_NA + a;                              // row of the reference's (b, n, .) tensors
 
-            // ---- P0: observation block -> TMEM (this thread: 72 of the row's 144 inputs)
-            cp_async_wait_all();
+            // ---- P0: observation block -> TMEM (this thread: 36 of the row's 144 inputs)
+            if (prm.use_tma) { mbar_wait(bar_x, px); px ^= 1u; }
+            else cp_async_wait_all();
             group_sync<1, N_WORKERS>();                                         // the block has landed; TMEM of the previous tile is drained
 #pragma unroll
-            for (int c = 0; c < 18; ++c) {
-                const int k0 = 72 * half + 4 * c;
+            for (int c = 0; c < KPT / 4; ++c) {
+                const int k0 = KPT * qt + 4 * c;
                 split_st4(lane_base, C_XHI + k0, C_XLO + k0, stage[(k0 + 0) * POL_M + row], stage[(k0 + 1) * POL_M + row],
                           stage[(k0 + 2) * POL_M + row], stage[(k0 + 3) * POL_M + row]);
             }
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_a);
-            group_sync<1, N_WORKERS>();                                         // every thread has read the staging block
-            if (tile + gridDim.x < n_tiles) request(tile + gridDim.x);          // the next block travels during the three GEMM phases
-            // the previous hidden state of this thread's 32 units (issued now, consumed after fc1)
-            float h[32];
+            if (!prm.use_tma) {
+                group_sync<1, N_WORKERS>();                                     // every thread has read the staging block
+                if (tile + gridDim.x < n_tiles) request(tile + gridDim.x);
+            }
+            // the previous hidden state of this thread's 16 units (issued now, consumed after fc1)
+            float h[CPT];
             {
                 const bool zero = !live || prm.hid_in == nullptr || (prm.reset != nullptr && prm.reset[e] != 0);
-                const float4* hp = reinterpret_cast<const float4*>(prm.hid_in + (zero ? 0 : r_glob) * POL_HID + 32 * half);
+                const float4* hp = reinterpret_cast<const float4*>(prm.hid_in + (zero ? 0 : r_glob) * POL_HID + c0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < CPT / 4; ++i) {
                     const float4 t = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(hp + i);
                     h[4 * i] = t.x; h[4 * i + 1] = t.y; h[4 * i + 2] = t.z; h[4 * i + 3] = t.w;
                 }
             }
-            if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small vectors have landed
+            if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small arrays have landed
 
             // ---- E1: fc1 epilogue: bias(agent), LayerNorm, ReLU -> A2; h -> A3
             mbar_wait(bar_m, pm); pm ^= 1u;
             tc_fence_after();
             {
-                float v[32];
-                tmem_ld32(lane_base + C_ACC1 + 32 * half, v);
+                float v[CPT];
+                tmem_ld16(lane_base + C_ACC1 + c0, v);
                 tmem_wait_ld();
                 float s = 0.0f, ss = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { v[i] = __fadd_rn(v[i], vec[V_B1A + a * POL_HID + 32 * half + i]); s = __fadd_rn(s, v[i]); }
-                lnp[half * POL_M + row] = make_float2(s, 0.0f);
+                for (int i = 0; i < CPT; ++i) { v[i] = __fadd_rn(v[i], vec[V_B1A + a * POL_HID + c0 + i]); s = __fadd_rn(s, v[i]); ss = fmaf(v[i], v[i], ss); }
+                lnp[qt * POL_M + row] = make_float2(s, ss);
                 group_sync<1, N_WORKERS>();
-                const float mean = __fmul_rn(__fadd_rn(lnp[row].x, lnp[POL_M + row].x), 1.0f / POL_HID);
+                float S = 0.0f, SS = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { v[i] = __fsub_rn(v[i], mean); ss = fmaf(v[i], v[i], ss); }
-                group_sync<1, N_WORKERS>();                                     // the sums have been read: the cells are reused
-                lnp[half * POL_M + row] = make_float2(ss, 0.0f);
-                group_sync<1, N_WORKERS>();
-                const float var = __fmul_rn(__fadd_rn(lnp[row].x, lnp[POL_M + row].x), 1.0f / POL_HID);   // biased, as torch
+                for (int j = 0; j < TPR; ++j) { const float2 t = lnp[j * POL_M + row]; S = __fadd_rn(S, t.x); SS = __fadd_rn(SS, t.y); }
+                const float mean = __fmul_rn(S, 1.0f / POL_HID);
+                const float var = fmaxf(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
                 const float rstd = rsqrtf(__fadd_rn(var, 1e-5f));
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float y = fmaf(__fmul_rn(v[i], rstd), vec[V_LNG + 32 * half + i], vec[V_LNB + 32 * half + i]);
+                for (int i = 0; i < CPT; ++i) {
+                    const float y = fmaf(__fmul_rn(__fsub_rn(v[i], mean), rstd), vec[V_LNG + c0 + i], vec[V_LNB + c0 + i]);
                     v[i] = fmaxf(y, 0.0f);                                       // hid_activation = relu
                 }
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    split_st4(lane_base, C_A2HI + 32 * half + 4 * c, C_A2LO + 32 * half + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    split_st4(lane_base, C_A3HI + 32 * half + 4 * c, C_A3LO + 32 * half + 4 * c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+                for (int c = 0; c < CPT / 4; ++c) {
+                    split_st4(lane_base, C_A2HI + c0 + 4 * c, C_A2LO + c0 + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    split_st4(lane_base, C_A3HI + c0 + 4 * c, C_A3LO + c0 + 4 * c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
                 }
             }
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_a);
 
-            // ---- E2: GRU cell (torch.nn.GRUCell: r, z, n gate order) -> h', A4
+            // ---- E2: GRU cell (torch.nn.GRUCell: r, z, n gate order) -> h'; fc2 partial sums
             mbar_wait(bar_m, pm); pm ^= 1u;
             tc_fence_after();
             {
-                float g[32], hn[32];
-                tmem_ld32(lane_base + C_RZ + 64 + 32 * half, g);                 // z pre-activations
-                tmem_wait_ld();
+                float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) g[i] = sigmoidf_acc(__fadd_rn(g[i], vec[V_BRZ + 64 + 32 * half + i]));    // z
-                {
-                    float rp[32], gi[32];
-                    tmem_ld32(lane_base + C_RZ + 32 * half, rp);
-                    tmem_ld32(lane_base + C_GIN + 32 * half, gi);
-                    tmem_ld32(lane_base + C_GHN + 32 * half, hn);
+                for (int hc = 0; hc < CPT / 8; ++hc) {                          // two chunks of 8 columns: half the live registers
+                    const int cc = c0 + 8 * hc;
+                    float rp[8], zp[8], gi[8], gh[8];
+                    tmem_ld8(lane_base + C_RZ + cc, rp);
+                    tmem_ld8(lane_base + C_RZ + 64 + cc, zp);
+                    tmem_ld8(lane_base + C_GIN + cc, gi);
+                    tmem_ld8(lane_base + C_GHN + cc, gh);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float r = sigmoidf_acc(__fadd_rn(rp[i], vec[V_BRZ + 32 * half + i]));
-                        const float nn = tanhf(fmaf(r, __fadd_rn(hn[i], vec[V_BHN + 32 * half + i]), __fadd_rn(gi[i], vec[V_BIN + 32 * half + i])));
-                        hn[i] = fmaf(g[i], __fsub_rn(h[i], nn), nn);              // (1 - z) n + z h
+                    for (int i = 0; i < 8; ++i) {
+                        const float r = sigmoid_fast(__fadd_rn(rp[i], vec[V_BRZ + cc + i]));
+                        const float z = sigmoid_fast(__fadd_rn(zp[i], vec[V_BRZ + 64 + cc + i]));
+                        const float nn = tanh_fast(fmaf(r, __fadd_rn(gh[i], vec[V_BHN + cc + i]), __fadd_rn(gi[i], vec[V_BIN + cc + i])));
+                        const float hn = fmaf(z, __fsub_rn(h[8 * hc + i], nn), nn);   // (1 - z) n + z h
+                        h[8 * hc + i] = hn;
+                        p0 = fmaf(hn, vec[V_W2 + cc + i], p0); p1 = fmaf(hn, vec[V_W2 + 64 + cc + i], p1);
+                        p2 = fmaf(hn, vec[V_W2 + 128 + cc + i], p2); p3 = fmaf(hn, vec[V_W2 + 192 + cc + i], p3);
                     }
                 }
+                fcp[qt * POL_M + row] = make_float4(p0, p1, p2, p3);
                 if (live) {
-                    float4* ho = reinterpret_cast<float4*>(prm.hid_out + r_glob * POL_HID + 32 * half);
+                    float4* ho = reinterpret_cast<float4*>(prm.hid_out + r_glob * POL_HID + c0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) ho[i] = make_float4(hn[4 * i], hn[4 * i + 1], hn[4 * i + 2], hn[4 * i + 3]);
+                    for (int i = 0; i < CPT / 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
                 }
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    split_st4(lane_base, C_A4HI + 32 * half + 4 * c, C_A4LO + 32 * half + 4 * c, hn[4 * c], hn[4 * c + 1], hn[4 * c + 2], hn[4 * c + 3]);
             }
-            tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_a);
+            group_sync<1, N_WORKERS>();                                         // the partial sums of the row are in place
 
-            // ---- E3: fc2 epilogue + select_action (utils/util.py:50-64)
-            mbar_wait(bar_m, pm); pm ^= 1u;
-            tc_fence_after();
-            if (half == 0) {
+            // ---- fc2 bias + select_action (utils/util.py:50-64)
+            if (qt == 0 && live) {
                 float m[4];
-                tmem_ld4(lane_base + C_ACC3, m);
-                tmem_wait_ld();
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) m[i] = __fadd_rn(m[i], vec[V_B2 + i]);
-                    if (prm.mean != nullptr) reinterpret_cast<float4*>(prm.mean)[r_glob] = make_float4(m[0], m[1], m[2], m[3]);
-                    float act[4], lp[4];
-                    if (prm.explore) {
-                        float z[4];
-                        if (prm.eps != nullptr) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(prm.eps) + r_glob);
-                            z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-                        } else {                                                 // Philox4x32-10 keyed by the seed, counter = (row, step)
-                            U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
-                            ctr.z = (uint32_t)prm.step; ctr.w = (uint32_t)(prm.step >> 32);
-                            const U4 rr = philox4x32_10(ctr, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
-                            // Box-Muller on (0, 1] uniforms
-                            const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
-                            const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
-                            const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
-                            float s0, c0, s1, c1;
-                            sincosf(6.283185307179586f * u1, &s0, &c0);
-                            sincosf(6.283185307179586f * u3, &s1, &c1);
-                            z[0] = ra * c0; z[1] = ra * s0; z[2] = rb * c1; z[3] = rb * s1;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float x = fmaf(prm.std_, z[i], m[i]);          // Normal(mean, std).rsample()
-                            const float y = tanhf(x);
-                            // Normal.log_prob(x) = -(x - mean)^2 / (2 var) - log(std) - log(sqrt(2 pi)), then the tanh correction
-                            const float d = __fsub_rn(x, m[i]);
-                            float l = -__fdividef(__fmul_rn(d, d), __fmul_rn(2.0f, __fmul_rn(prm.std_, prm.std_)));
-                            l = __fsub_rn(__fsub_rn(l, prm.log_std), 0.9189385332046727f);
-                            lp[i] = __fsub_rn(l, logf(__fadd_rn(__fsub_rn(1.0f, __fmul_rn(y, y)), 1e-6f)));
-                            act[i] = y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { act[i] = tanhf(m[i]); lp[i] = 0.0f; }       // status == 'test' (util.py:82-85)
-                    }
-                    reinterpret_cast<float4*>(prm.action)[r_glob] = make_float4(act[0], act[1], act[2], act[3]);
-                    if (prm.logp != nullptr) reinterpret_cast<float4*>(prm.logp)[r_glob] = make_float4(lp[0], lp[1], lp[2], lp[3]);
+                {
+                    const float4 t0 = fcp[row], t1 = fcp[POL_M + row], t2 = fcp[2 * POL_M + row], t3 = fcp[3 * POL_M + row];
+                    m[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0.x, t1.x), t2.x), t3.x), vec[V_B2 + 0]);
+                    m[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0.y, t1.y), t2.y), t3.y), vec[V_B2 + 1]);
+                    m[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0.z, t1.z), t2.z), t3.z), vec[V_B2 + 2]);
+                    m[3] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0.w, t1.w), t2.w), t3.w), vec[V_B2 + 3]);
                 }
+                if (prm.mean != nullptr) reinterpret_cast<float4*>(prm.mean)[r_glob] = make_float4(m[0], m[1], m[2], m[3]);
+                float act[4], lp[4];
+                if (prm.explore) {
+                    float z[4];
+                    if (prm.eps != nullptr) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(prm.eps) + r_glob);
+                        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+                    } else {                                                 // Philox4x32-10 keyed by the seed, counter = (row, step)
+                        U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
+                        ctr.z = (uint32_t)prm.step; ctr.w = (uint32_t)(prm.step >> 32);
+                        const U4 rr = philox4x32_10(ctr, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+                        // Box-Muller on (0, 1] x [0, 1) uniforms
+                        const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
+                        const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
+                        const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+                        float s0, cs0, s1, cs1;
+                        __sincosf(6.283185307179586f * u1, &s0, &cs0);
+                        __sincosf(6.283185307179586f * u3, &s1, &cs1);
+                        z[0] = ra * cs0; z[1] = ra * s0; z[2] = rb * cs1; z[3] = rb * s1;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = fmaf(prm.std_, z[i], m[i]);          // Normal(mean, std).rsample()
+                        const float y = tanh_fast(x);
+                        // Normal.log_prob(x) = -(x - mean)^2 / (2 var) - log(std) - log(sqrt(2 pi)), then the tanh correction
+                        const float d = __fsub_rn(x, m[i]);
+                        float l = -__fdividef(__fmul_rn(d, d), __fmul_rn(2.0f, __fmul_rn(prm.std_, prm.std_)));
+                        l = __fsub_rn(__fsub_rn(l, prm.log_std), 0.9189385332046727f);
+                        lp[i] = __fsub_rn(l, __logf(__fadd_rn(__fsub_rn(1.0f, __fmul_rn(y, y)), 1e-6f)));
+                        act[i] = y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { act[i] = tanh_fast(m[i]); lp[i] = 0.0f; }   // status == 'test' (util.py:82-85)
+                }
+                reinterpret_cast<float4*>(prm.action)[r_glob] = make_float4(act[0], act[1], act[2], act[3]);
+                if (prm.logp != nullptr) reinterpret_cast<float4*>(prm.logp)[r_glob] = make_float4(lp[0], lp[1], lp[2], lp[3]);
             }
-            tc_fence_before();
         }
     }
 
@@ -556,12 +590,25 @@ float round_tf32(float x) {                    // round to nearest even on the 1
 struct FpPolicy {
     int device = 0;
     int loaded = 0;
-    float* d_W1rot = nullptr; float* d_Wg = nullptr; float* d_W2 = nullptr; float* d_vec = nullptr;
+    float* d_W1rot = nullptr; float* d_Wg = nullptr; float* d_vec = nullptr;
     int64_t launches = 0;
     std::string err;
 };
 
 namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {                  // the driver entry point, without linking libcuda
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
 thread_local std::string g_policy_err;
 int pfail(FpPolicy* p, int code, const std::string& msg) {
     if (p) p->err = msg; else g_policy_err = msg;
@@ -585,7 +632,7 @@ int fp_policy_create(int device, FpPolicy** out) {
 int fp_policy_destroy(FpPolicy* p) {
     if (!p) return FP_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_W2); cudaFree(p->d_vec);
+    cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_vec);
     delete p;
     return FP_OK;
 }
@@ -620,25 +667,25 @@ int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const fl
             for (int k = 0; k < POL_HID; ++k)
                 dst[off + ((size_t)(k >> 2) * npad + n) * 4 + (k & 3)] = round_tf32(w[(size_t)(row0 + n) * POL_HID + k]);
     };
-    std::vector<float> Wg(WG_BYTES / 4, 0.0f), W2(W2_BYTES / 4, 0.0f), vec(V_FLOATS, 0.0f);
+    std::vector<float> Wg(WG_BYTES / 4, 0.0f), vec(V_FLOATS, 0.0f);
     pack(Wg, 0, w_ih, 0, 128, 128);
     pack(Wg, WG_RZ_BYTES / 4, w_hh, 0, 128, 128);
     pack(Wg, 2 * WG_RZ_BYTES / 4, w_ih, 128, 64, 64);
     pack(Wg, 2 * WG_RZ_BYTES / 4 + WG_N_BYTES / 4, w_hh, 128, 64, 64);
-    pack(W2, 0, fc2_w, 0, POL_ACT, 16);
+    for (int o = 0; o < POL_ACT; ++o)
+        for (int k = 0; k < POL_HID; ++k) vec[V_W2 + o * POL_HID + k] = fc2_w[(size_t)o * POL_HID + k];      // fc2 runs in fp32: unrounded
     for (int a = 0; a < POL_NA; ++a)
         for (int n = 0; n < POL_HID; ++n) vec[V_B1A + a * POL_HID + n] = fc1_b[n] + fc1_w[(size_t)n * KIN + POL_OBS + a];   // one-hot column folded in
     for (int n = 0; n < POL_HID; ++n) { vec[V_LNG + n] = ln_g[n]; vec[V_LNB + n] = ln_b[n]; vec[V_BIN + n] = b_ih[128 + n]; vec[V_BHN + n] = b_hh[128 + n]; }
     for (int n = 0; n < 128; ++n) vec[V_BRZ + n] = b_ih[n] + b_hh[n];
     for (int n = 0; n < POL_ACT; ++n) vec[V_B2 + n] = fc2_b[n];
-    cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_W2); cudaFree(p->d_vec);
-    p->d_W1rot = p->d_Wg = p->d_W2 = p->d_vec = nullptr;
+    cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_vec);
+    p->d_W1rot = p->d_Wg = p->d_vec = nullptr;
     if (cudaMalloc(&p->d_W1rot, W1.size() * 4) != cudaSuccess || cudaMalloc(&p->d_Wg, Wg.size() * 4) != cudaSuccess ||
-        cudaMalloc(&p->d_W2, W2.size() * 4) != cudaSuccess || cudaMalloc(&p->d_vec, vec.size() * 4) != cudaSuccess)
+        cudaMalloc(&p->d_vec, vec.size() * 4) != cudaSuccess)
         return pfail(p, FP_ENOMEM, "fp_policy_load: cudaMalloc failed");
     cudaMemcpy(p->d_W1rot, W1.data(), W1.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_Wg, Wg.data(), Wg.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(p->d_W2, W2.data(), W2.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_vec, vec.data(), vec.size() * 4, cudaMemcpyHostToDevice);
     cudaError_t e = cudaFuncSetAttribute(k_policy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
@@ -663,15 +710,32 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
     PolParams prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.ring = d_ring; prm.n_pad = n_pad; prm.n = n_envs; prm.slot = slot;
-    prm.W1rot = p->d_W1rot; prm.Wg = p->d_Wg; prm.W2 = p->d_W2; prm.vec = p->d_vec;
+    prm.W1rot = p->d_W1rot; prm.Wg = p->d_Wg; prm.vec = p->d_vec;
     prm.hid_in = d_hid_in; prm.reset = d_reset; prm.hid_out = d_hid_out;
     prm.mean = d_mean; prm.action = d_action; prm.logp = d_logp; prm.eps = d_eps;
     prm.seed = seed; prm.step = step; prm.std_ = std_; prm.log_std = std::log(std_); prm.explore = explore;
+    // the ring as a 3-D tensor [24 slots][30 = agent x feature][n_pad envs] (innermost first); a tile is the box
+    // [24][6][128] at (env block, agent * 6, 0); envs past n_pad read as zeros
+    alignas(64) CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    prm.use_tma = 0;
+    if (n_pad >= POL_M && ((uintptr_t)d_ring & 15) == 0) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return pfail(p, FP_ECUDA, "fp_policy_act: cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t gdim[3] = {(cuuint64_t)n_pad, (cuuint64_t)(POL_NA * POL_F), (cuuint64_t)POL_H};
+        const cuuint64_t gstride[2] = {(cuuint64_t)n_pad * 4, (cuuint64_t)n_pad * 4 * (POL_NA * POL_F)};
+        const cuuint32_t box[3] = {POL_M, POL_F, POL_H}, estr[3] = {1, 1, 1};
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_ring), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return pfail(p, FP_ECUDA, "fp_policy_act: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        prm.use_tma = 1;
+    }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const int64_t tiles = (n_envs + POL_M - 1) / POL_M * POL_NA;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    k_policy<<<grid, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(prm);
+    k_policy<<<grid, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(prm, tmap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;
