@@ -5,8 +5,11 @@ on the GPU; only the episode statistics leave it (one all-reduce when several ra
     python examples/rollout.py --envs 65536 --steps 95
     torchrun --nproc-per-node 8 examples/rollout.py --envs 1048576      # 2^20 envs sharded over 8 GPUs
 
-The policy here is a stand-in (a fixed random affine map of the observation squashed by tanh): the point is
-the env-side API a learner plugs into.
+The policy is the reference's shared-parameter RNNAgent (madrl/agents/rnn_agent.py) evaluated by the tcgen05 policy
+kernel straight from the env's observation ring; pass --weights model.pt (a checkpoint written by train_agent.py:
+{"model_state_dict": ...}, train_agent.py:144-147) or let the script initialise it like the reference does
+(init_std 0.1).  With --record N the Transition fields (model.py:230-242) of the first N envs go into a device replay
+ring, from which `learner_batch` hands the learner the unpack_data tensors.
 """
 import argparse
 import os
@@ -21,11 +24,26 @@ sys.path[:0] = [os.path.join(ROOT, "safe-marl_b200")]
 from flexgpu import BatchedFlexProvisionEnv, sharding  # noqa: E402
 
 
+def reference_init(seed=0):
+    """RNNAgent weights as the reference initialises them: nn.Linear weights ~ N(0, init_std = 0.1) (model.py:185-190),
+    everything else torch's defaults (uniform(-1/sqrt(fan), 1/sqrt(fan)); LayerNorm 1 / 0)."""
+    g = torch.Generator().manual_seed(seed)
+    u = lambda shape, k: (torch.rand(shape, generator=g) * 2 - 1) * k
+    return {"fc1.weight": torch.randn(64, 149, generator=g) * 0.1, "fc1.bias": u((64,), 149 ** -0.5),
+            "layernorm.weight": torch.ones(64), "layernorm.bias": torch.zeros(64),
+            "rnn.weight_ih": u((192, 64), 0.125), "rnn.weight_hh": u((192, 64), 0.125), "rnn.bias_ih": u((192,), 0.125),
+            "rnn.bias_hh": u((192,), 0.125), "fc2.weight": torch.randn(4, 64, generator=g) * 0.1, "fc2.bias": u((4,), 0.125)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=65536, help="total environments over all ranks")
     ap.add_argument("--steps", type=int, default=95)
+    ap.add_argument("--weights", default=None, help="checkpoint with the policy's state_dict (policy_dicts.0.* keys)")
+    ap.add_argument("--record", type=int, default=1024, help="envs per rank whose transitions go into the device replay ring")
     args = ap.parse_args()
+    from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS, learner_batch
+    from flexgpu.predictor import DeviceReplayBuffer
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -34,29 +52,34 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     offset, count = sharding.shard(args.envs, rank, world)             # env index range of this rank
     env = BatchedFlexProvisionEnv(None, n_envs=count, device=dev, seed=0, env_offset=offset)
-    obs, state = env.reset()                                           # [N,5,144] f32, [N,110] f32
-    g = torch.Generator(device=dev).manual_seed(1)
-    Wp = torch.randn(env.obs_size, env.n_actions, device=dev, generator=g) * 0.05
-    noise = 0.1 * torch.randn(8, count * env.n_agents, env.n_actions, device=dev, generator=g)
-    torch.tanh(obs.view(-1, env.obs_size) @ Wp)                        # warm-up: cuBLAS handle, module load
+    if args.weights:
+        sd = torch.load(args.weights, map_location="cpu")
+        sd = sd.get("model_state_dict", sd)
+        sd = {k.split("policy_dicts.0.", 1)[1]: v for k, v in sd.items() if k.startswith("policy_dicts.0.")} or sd
+    else:
+        sd = reference_init()
+    policy = DevicePolicy(sd, device=dev, std=1.0, seed=1 + rank)      # fixed_policy_std 1.0 (default.yaml)
+    rec = min(args.record, count)
+    replay = DeviceReplayBuffer(max(rec * 8, 5000), TRANSITION_FIELDS, device=dev) if rec else None    # replay_buffer_size 5000
+    rollout = DeviceRollout(env, policy, replay=replay, record_envs=rec)
+    rollout.reset()                                                    # env.reset() + init_hidden (model.py:208-211)
+    rollout.step()                                                     # warm-up: allocations, module load
     env.episode_stats(reset=True)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for t in range(args.steps):
-        action = torch.tanh(obs.view(-1, env.obs_size) @ Wp) + noise[t % 8]
-        # translate_action (util.py:121-129) and the pushing get_obs (quirk Q7) are fused into the step kernel
-        reward, done, info, obs = env.step(action, translate=True, want_info=False, return_obs=True)
-        if (t + 1) % (env.episode_limit - 1) == 0:                     # every env of the batch ends after 95 steps (Q1):
-            env.reset(mask=done.to(torch.uint8), return_obs=False)     # auto-reset the finished ones (Philox streams)
-            obs = env.get_obs()
+        reward, done = rollout.step()                                  # policy -> translate_action + step + get_obs -> Transition
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     stats = env.episode_stats()                                        # the one collective (NCCL all-reduce of 16 doubles)
     if rank == 0:
         means = sharding.episode_means(stats)
         print(f"{args.envs} envs x {args.steps} steps on {world} GPU(s): {args.envs * args.steps / dt:.3e} env-steps/s "
-              f"(policy + step + get_obs)")
+              f"(tcgen05 policy + fused step/get_obs" + (f" + {rec} transitions/step/rank" if rec else "") + ")")
         for k in ("mean_train_reward", "mean_train_revenue", "mean_train_voltage_penalty", "mean_train_solver_failed"):
             print(f"  {k:32s} {means[k]: .6f}")
-    env.close()
+        if replay is not None and len(replay) >= 32:
+            batch = learner_batch(policy, replay, 32)                  # replay.get_batch(32) + unpack_data, on the device
+            print("  learner batch:", {k: tuple(v.shape) for k, v in batch.items()})
+    policy.close(); env.close()
     if world > 1:
         dist.destroy_process_group()
 

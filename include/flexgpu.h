@@ -161,6 +161,11 @@ int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const doub
  * on how envs are sharded over GPUs.  Used by throughput rollouts (auto-reset). */
 int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask,
                     void* stream);
+/* fp_reset_random, then up to `retries` more launches for the envs (of d_mask) whose initial power flow failed
+ * (FP_FLAG_RESET_FAILED) -- the reference's `while not solvable` redraw loop (:82-153) without a host round trip: the
+ * retry mask is built on the device.  d_failed (may be NULL): device int32, envs still flagged after the last attempt. */
+int fp_reset_random_retry(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask, int32_t retries,
+                          int32_t* d_failed, void* stream);
 
 /* Replaces step() (:241-356): d_actions[N][na*4] (agent-major, k = P_red, P_esc, P_esd, Q_pv)
  * of dtype act_dtype; outputs d_reward[N] fp64, d_done[N] uint8, d_info[N][FP_INFO_STRIDE]

@@ -43,6 +43,7 @@ struct FpHandle {
     float* d_obsr = nullptr; int ring_q = 0; bool obsr_valid = false; int64_t n_pad = 0;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
+    uint8_t* d_retry_mask = nullptr; void* d_retry_count = nullptr;     // fp_reset_random_retry: device-built retry mask
     int stats_rows = 0, stats_cap = 0;     // rows of one launch's statistics block
     const uint8_t* d_inject = nullptr;
     int keep_flows = 0;
@@ -72,6 +73,13 @@ static int fail(FpHandle* h, int code, const std::string& msg) {
     return code;
 }
 
+// Every entry point runs on the handle's device whatever the caller's current device is (two handles on two
+// GPUs in one process); cudaSetDevice on the current device is a no-op.
+#define USE_DEVICE(h)                                                                            \
+    do {                                                                                         \
+        cudaError_t e_ = cudaSetDevice((h)->device);                                             \
+        if (e_ != cudaSuccess) return fail((h), FP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e_)); \
+    } while (0)
 #define CUDA_TRY(h, expr)                                                              \
     do {                                                                               \
         cudaError_t e_ = (expr);                                                       \
@@ -283,7 +291,7 @@ int fp_destroy(FpHandle* h) {
     predictor_free(&h->pred);
     cudaFree(h->d_topo); cudaFree(h->d_P); cudaFree(h->d_Q); cudaFree(h->d_PVP); cudaFree(h->d_PQD); cudaFree(h->d_OBS);
     cudaFree(h->d_rec); cudaFree(h->d_V); cudaFree(h->d_setp); cudaFree(h->d_hist); cudaFree(h->d_obsm); cudaFree(h->d_obsr);
-    cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial);
+    cudaFree(h->d_pfl); cudaFree(h->d_qfl); cudaFree(h->d_isq); cudaFree(h->d_stats_partial); cudaFree(h->d_retry_mask); cudaFree(h->d_retry_count);
     cudaFree(h->d_act_stage); cudaFree(h->d_act_xlat); cudaFree(h->d_reward_stage); cudaFree(h->d_done_stage); cudaFree(h->d_info_stage);
     for (int i = 0; i < FP_HOST_STREAMS; ++i) {
         if (h->host_streams[i]) cudaStreamDestroy(h->host_streams[i]);
@@ -377,6 +385,7 @@ static cudaError_t launch_env_any(FpHandle* h, int mode, const EnvParams& p, cud
 int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const double* d_a0,
              const uint8_t* d_mask, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_reset: call fp_load_profiles first");
     if (!d_start || !d_e0 || !d_a0) return fail(h, FP_EINVAL, "fp_reset: null input");
     EnvParams p; fill_env_params(h, p);
@@ -395,9 +404,8 @@ int fp_reset(FpHandle* h, const int32_t* d_start, const double* d_e0, const doub
     return FP_OK;
 }
 
-int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask, void* stream) {
-    if (!h) return FP_EINVAL;
-    if (!h->d_P) return fail(h, FP_ESTATE, "fp_reset_random: call fp_load_profiles first");
+// One launch of the random reset for the envs of d_mask (+ the observation rings' restart).
+static int reset_random_once(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask, void* stream) {
     EnvParams p; fill_env_params(h, p);
     p.mask = d_mask; p.random = 1; p.seed = seed; p.env_offset = env_offset;
     p.inject = nullptr;
@@ -414,9 +422,46 @@ int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_
     return FP_OK;
 }
 
+int fp_reset_random(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask, void* stream) {
+    if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_reset_random: call fp_load_profiles first");
+    return reset_random_once(h, seed, env_offset, d_mask, stream);
+}
+
+// The reference redraws until the initial power flow is solvable (`while not solvable`, :82-153).  Here: the random
+// reset, then `retries` more launches for the envs (of d_mask) whose FP_FLAG_RESET_FAILED is set -- the retry mask is
+// built on the device, so nothing synchronises with the host; a launch whose mask is empty costs a few microseconds.
+// Every attempt draws from the env's next Philox episode counter.  d_failed (may be NULL) receives the number of envs
+// still flagged after the last attempt (int32 on the device).
+int fp_reset_random_retry(FpHandle* h, uint64_t seed, int64_t env_offset, const uint8_t* d_mask, int32_t retries,
+                          int32_t* d_failed, void* stream) {
+    if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_reset_random_retry: call fp_load_profiles first");
+    if (retries < 0 || retries > 64) return fail(h, FP_EINVAL, "fp_reset_random_retry: 0 <= retries <= 64");
+    int rc = reset_random_once(h, seed, env_offset, d_mask, stream);
+    if (rc != FP_OK) return rc;
+    if (retries > 0 || d_failed) {
+        if (!h->d_retry_mask) CUDA_TRY(h, cudaMalloc(&h->d_retry_mask, (size_t)h->n + 4));
+        int32_t* cnt = reinterpret_cast<int32_t*>(h->d_retry_count);
+        if (!cnt) { CUDA_TRY(h, cudaMalloc(&h->d_retry_count, 4)); cnt = reinterpret_cast<int32_t*>(h->d_retry_count); }
+        for (int r = 0; r <= retries; ++r) {
+            CUDA_TRY(h, launch_reset_failed_mask(h->d_rec, d_mask, h->n, h->d_retry_mask, cnt, (cudaStream_t)stream));
+            h->launches++;
+            if (r == retries) break;
+            rc = reset_random_once(h, seed, env_offset, h->d_retry_mask, stream);
+            if (rc != FP_OK) return rc;
+        }
+        if (d_failed) CUDA_TRY(h, cudaMemcpyAsync(d_failed, cnt, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return FP_OK;
+}
+
 int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done,
             double* d_info, const uint8_t* d_mask, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step: call fp_load_profiles first");
     if (!d_actions || !d_reward || !d_done) return fail(h, FP_EINVAL, "fp_step: null input/output");
     if (act_dtype != FP_F32 && act_dtype != FP_F64 && act_dtype != FP_F32_POLICY) return fail(h, FP_EINVAL, "fp_step: bad action dtype");
@@ -500,6 +545,7 @@ static int enqueue_host_chunks(FpHandle* h, const void* h_actions, int act_dtype
 int fp_step_host(FpHandle* h, const void* h_actions, int act_dtype, double* h_reward, uint8_t* h_done,
                  double* h_info, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_host: call fp_load_profiles first");
     if (!h_actions || !h_reward || !h_done) return fail(h, FP_EINVAL, "fp_step_host: null buffer");
     if (act_dtype != FP_F32 && act_dtype != FP_F64 && act_dtype != FP_F32_POLICY) return fail(h, FP_EINVAL, "fp_step_host: bad action dtype");
@@ -613,6 +659,7 @@ static void fill_obs_params(FpHandle* h, ObsParams& p, void* out, int push) {
 
 int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_obs: bad arguments");
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
@@ -651,6 +698,7 @@ static int obs_ring_prepare(FpHandle* h, bool push, cudaStream_t st) {
 
 int fp_get_obs_view(FpHandle* h, int push, float** d_view, int64_t* env_pitch, int64_t* agent_pitch, void* stream) {
     if (!h || !d_view) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs_view: call fp_load_profiles first");
     const int H = h->dc.history, na = h->dc.na;
     cudaStream_t st = (cudaStream_t)stream;
@@ -699,6 +747,7 @@ static int obs_envminor_prepare(FpHandle* h, bool push, cudaStream_t st) {
 
 int fp_obs_ring(FpHandle* h, float** d_ring, int32_t* slot, int64_t* n_pad, void* stream) {
     if (!h || !d_ring) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_obs_ring: call fp_load_profiles first");
     int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
     if (rc != FP_OK) return rc;
@@ -711,6 +760,7 @@ int fp_obs_ring(FpHandle* h, float** d_ring, int32_t* slot, int64_t* n_pad, void
 int fp_step_ring(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward, uint8_t* d_done, double* d_info,
                  const uint8_t* d_mask, float** d_ring, int32_t* slot, int64_t* n_pad, void* stream) {
     if (!h || !d_ring) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_step_ring: call fp_load_profiles first");
     // one launch for the built-in feeder shape; the run-time-table kernels, the warp variant and masked steps push
     // through the generic path (fp64 history ring) and rebuild the ring from it: same contents
@@ -738,6 +788,7 @@ int fp_step_ring(FpHandle* h, const void* d_actions, int act_dtype, double* d_re
 
 int fp_obs_ring_reset_push(FpHandle* h, const uint8_t* d_mask, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_obs_ring_reset_push: call fp_load_profiles first");
     int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
     if (rc != FP_OK) return rc;
@@ -750,6 +801,7 @@ int fp_obs_ring_reset_push(FpHandle* h, const uint8_t* d_mask, void* stream) {
 
 int fp_obs_ring_gather(FpHandle* h, float* d_out, void* stream) {
     if (!h || !d_out) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_obs_ring_gather: call fp_load_profiles first");
     int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
     if (rc != FP_OK) return rc;
@@ -760,6 +812,7 @@ int fp_obs_ring_gather(FpHandle* h, float* d_out, void* stream) {
 
 int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_state: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_state: bad arguments");
     ObsParams p; fill_obs_params(h, p, d_out, 0);
@@ -799,6 +852,7 @@ int fp_set_keep_flows(FpHandle* h, int keep) {
 int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, double* d_V, double* d_Pl,
                   double* d_Ql, double* d_Isq, int32_t* d_iters, uint8_t* d_fail, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     if (n < 1 || !d_p || !d_q || !d_V) return fail(h, FP_EINVAL, "fp_power_flow: bad arguments");
     PfParams p;
     p.topo = h->d_topo; p.n = n; p.nl = h->dc.nl; p.max_iter = h->dc.pf_max_iter; p.tol = h->dc.pf_tol; p.n32 = h->dc.pf_f32; p.pad_ = 0;
@@ -817,6 +871,7 @@ int fp_power_flow(FpHandle* h, int64_t n, const double* d_p, const double* d_q, 
 
 int fp_stats_read(FpHandle* h, double* d_out, void* stream) {
     if (!h || !d_out) return FP_EINVAL;
+    USE_DEVICE(h);
     CUDA_TRY(h, launch_stats_fold(h->d_stats_partial, h->stats_rows, d_out, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
@@ -824,6 +879,7 @@ int fp_stats_read(FpHandle* h, double* d_out, void* stream) {
 
 int fp_stats_reset(FpHandle* h, void* stream) {
     if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
     CUDA_TRY(h, cudaMemsetAsync(h->d_stats_partial, 0, (size_t)h->stats_rows * FP_NSTATS * 8, (cudaStream_t)stream));
     return FP_OK;
 }

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_env(const EnvParams prm) {
                 if (lane < na) { a0 = b0; a1 = b1; a2 = b2; a3 = b3; e_init = ee; }
             } else {
                 start = prm.start[e];
+                start = (start < 0) ? 0 : ((start >= prm.start_range) ? prm.start_range - 1 : start);   // a direct C caller's rows stay inside the dataset
                 if (lane < na) {
                     e_init = prm.e0[e * na + lane];
                     const double* a = prm.a0 + (e * na + lane) * 4;
@@ -666,6 +667,27 @@ cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t 
 
 cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad, cudaStream_t st) {
     k_obsr_rebuild<<<148 * 16, 256, 0, st>>>(prm, obsr, n_pad);
+    return cudaGetLastError();
+}
+
+// out[e] = 1 for the envs (of `mask`, if given) whose last reset failed (FP_FLAG_RESET_FAILED); *count = how many
+__global__ void k_reset_failed_mask(const uint64_t* __restrict__ rec, const uint8_t* __restrict__ mask, int64_t n,
+                                    uint8_t* __restrict__ out, int32_t* __restrict__ count) {
+    int local = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t flags = (uint32_t)(rec[e * FP_REC_STRIDE + FP_REC_COUNTS] >> 32);
+        const bool bad = ((flags & FP_FLAG_RESET_FAILED) != 0) && (mask == nullptr || mask[e] != 0);
+        out[e] = bad ? 1 : 0;
+        local += bad ? 1 : 0;
+    }
+    local = __reduce_add_sync(FULL, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+cudaError_t launch_reset_failed_mask(const uint64_t* rec, const uint8_t* mask, int64_t n, uint8_t* out, int32_t* count, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    const int64_t ctas = (n + 255) / 256;
+    k_reset_failed_mask<<<(unsigned)(ctas < 148 * 4 ? ctas : 148 * 4), 256, 0, st>>>(rec, mask, n, out, count);
     return cudaGetLastError();
 }
 

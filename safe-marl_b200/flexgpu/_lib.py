@@ -62,6 +62,7 @@ _PROTOS = {
     "fp_load_profiles": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64]),
     "fp_reset": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "fp_reset_random": (C.c_int, [_P, C.c_uint64, C.c_int64, _P, _P]),
+    "fp_reset_random_retry": (C.c_int, [_P, C.c_uint64, C.c_int64, _P, C.c_int32, _P, _P]),
     "fp_step": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "fp_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "fp_get_obs": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),

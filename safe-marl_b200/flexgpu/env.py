@@ -95,6 +95,7 @@ class BatchedFlexProvisionEnv:
         self._inject = None
         self._host = None
         self._obs_views = {}
+        self._reset_failed = None
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -229,25 +230,27 @@ class BatchedFlexProvisionEnv:
             return x.to(device=self.device, dtype=dtype).contiguous()
         return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
 
-    def reset(self, start_index=None, e0=None, a0=None, mask=None, return_obs=True):
+    RESET_RETRIES = 3        # redraws of an env whose initial power flow fails (the reference loops until solvable, :82-153)
+
+    def reset(self, start_index=None, e0=None, a0=None, mask=None, return_obs=True, check=False):
         """Replaces reset()/manual_reset() (:74-155, :157-239).
 
         With no draws given, each env draws (start row, E0, a0) from its own Philox stream
         keyed by (seed, env_offset + e, episode counter).  Envs whose initial power flow fails
-        are re-drawn (random mode) like the reference's `while not solvable` loop (:82-153).
-        """
+        are re-drawn up to RESET_RETRIES times like the reference's `while not solvable` loop (:82-153) -- on the
+        device, without a host round trip.  An env that still fails keeps FP_FLAG_RESET_FAILED in `flags`
+        (`reset_failed_count()` reads the count); check=True synchronises and raises FlexGpuError instead.
+        A reset restarts the observation history of the envs it resets: a window returned earlier by
+        get_obs() / step(return_obs=...) no longer holds their previous episode -- copy `next_obs` before resetting."""
         m = self._dev(mask, torch.uint8)
         if start_index is None:
-            self._check(self._lib.fp_reset_random(self._h, self.seed, self.env_offset, _ptr(m), _stream()),
-                        "fp_reset_random")
-            for _ in range(8):
-                bad = (self.flags & _lib.FLAG_RESET_FAILED) != 0
-                if m is not None:
-                    bad &= m != 0
-                if not bool(bad.any()):
-                    break
-                self._check(self._lib.fp_reset_random(self._h, self.seed, self.env_offset,
-                                                      _ptr(bad.to(torch.uint8)), _stream()), "fp_reset_random")
+            if self._reset_failed is None:
+                self._reset_failed = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._check(self._lib.fp_reset_random_retry(self._h, self.seed, self.env_offset, _ptr(m), self.RESET_RETRIES,
+                                                        _ptr(self._reset_failed), _stream()), "fp_reset_random_retry")
+            if check and int(self._reset_failed.item()):
+                raise _lib.FlexGpuError(f"{int(self._reset_failed.item())} envs found no solvable initial state in "
+                                        f"{self.RESET_RETRIES + 1} draws")
         else:
             N, na = self.n_envs, self.n_agents
             s = self._dev(start_index, torch.int32).view(N)
@@ -263,6 +266,10 @@ class BatchedFlexProvisionEnv:
         if return_obs:
             return self.get_obs(), self.get_state()                     # :155
         return None
+
+    def reset_failed_count(self):
+        """Envs whose last random reset found no solvable initial state (synchronises)."""
+        return 0 if self._reset_failed is None else int(self._reset_failed.item())
 
     def step(self, actions, mask=None, want_info=True, translate=False, return_obs=False):
         """Replaces step() (:241-356).  actions: [N, na, 4] (or [N, na*4]) fp32 or fp64 tensor.

@@ -157,3 +157,37 @@ def test_reference_power_flow_solver_outputs(env):
                            (np.sqrt(out["Isq"]), g["I"], 1e-7)):
         err = np.max(np.abs(got - want))
         assert err < TOL_PU and err < tol
+
+
+def test_loading_sweep_up_to_voltage_collapse(env, network, tree):
+    """The default pf_tol (1e-5 on the current-row residual) was chosen on the bench workload: sweep the IEEE-33 base
+    case from 0.2x to 3.9x loading (voltage collapse of the feeder: ~3.7x, V_min 0.47 p.u. at 3.6x) and hold the
+    north_star bar -- |dV|, |dP|, |dQ|, |dI| <= 1e-6 p.u. against the dense Newton root -- for EVERY solve the kernel
+    reports as converged, right up to its failure flag; past the collapse point every solve must be flagged."""
+    lam = np.round(np.arange(0.2, 3.9001, 0.05), 2)
+    p = network.base_p[None, 1:] * lam[:, None]
+    q = network.base_q[None, 1:] * lam[:, None]
+    out = _np(env.power_flow(p, q))
+    worst = dict(V=0.0, P=0.0, Q=0.0, I=0.0)
+    solved_newton = np.zeros(len(lam), dtype=bool)
+    for i, l in enumerate(lam):
+        try:
+            sol = pf_ref.solve_newton(tree, np.concatenate(([0.0], p[i])), np.concatenate(([0.0], q[i])), max_iter=60)
+            solved_newton[i] = True
+        except pf_ref.SolverFailure:
+            continue
+        if out["failed"][i]:
+            continue
+        for k, got, want in (("V", out["V"][i], np.sqrt(sol["v"])), ("P", out["P"][i], sol["P"][1:]), ("Q", out["Q"][i], sol["Q"][1:]),
+                             ("I", np.sqrt(out["Isq"][i]), np.sqrt(sol["ell"][1:]))):
+            err = float(np.max(np.abs(got - want)))
+            worst[k] = max(worst[k], err)
+            assert err < TOL_PU, (k, float(l), err)
+    ok = ~out["failed"]
+    assert ok[lam <= 3.0].all(), "the kernel must solve everything up to 3x loading (V_min 0.66 p.u.)"
+    assert not ok[~solved_newton].any(), "past the collapse point every solve must carry the failure flag"
+    # the failure flag is monotone in the loading: once the fixed point stops converging it stays flagged
+    first_fail = int(np.argmax(~ok)) if (~ok).any() else len(lam)
+    assert not ok[first_fail:].any()
+    print(f"loading sweep ({env.variant_name}): solved up to {lam[ok].max():.2f}x (Newton: {lam[solved_newton].max():.2f}x), "
+          f"max errors vs Newton {worst}")
