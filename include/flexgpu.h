@@ -295,6 +295,21 @@ int fp_predictor_load(FpHandle* h, int32_t n_in, int32_t n_out, const double* h_
 int fp_predict(FpHandle* h, int64_t n, const float* d_X, float* d_vhat, double* d_penalty, FpReplay* sink,
                int32_t f_vhat, int32_t f_penalty, int64_t pos, void* stream);
 
+/* -- safety layer as a batched projection ------------------------------- */
+
+/* Replaces SAFEMADDPG.safety_layer_optimization (madrl/models/safemaddpg.py:176-299: a Pyomo QP solved by Gurobi per
+ * get_actions call) for every env at once.  In the form the reference evaluates its voltage predictor (:266,272: the
+ * ROW SUMS of the coefficient blocks coef[:, :33] / coef[:, 33:] times the bus's own P_net / Q_net) the QP separates
+ * per building and has a closed-form optimum (k_safety_project).  fp_safety_load takes the fitted regressor as the
+ * reference reads it (:182-184): h_coef [n_bus][2 n_bus], h_intercept [n_bus] (host, fp64), the voltage limits and the
+ * slack price (1000, :205-206).  fp_safety_project: d_actions [N][na][4] raw policy outputs (FP_F32 / FP_F64) -> parse_actions
+ * (:143-174, the env's own scaling / ESS logic on its current demands, PV and energy) -> projection -> d_adjusted fp32,
+ * either in the reference's return layout [N][x(na) | c(na) | d(na) | g(na)] (type_major = 1, :290-296) or [N][na][4];
+ * d_slack [N][na] (remaining predicted violation, p.u.) and d_intervened [N][na] may be NULL. */
+int fp_safety_load(FpHandle* h, const double* h_coef, const double* h_intercept, double v_min, double v_max, double slack_weight);
+int fp_safety_project(FpHandle* h, const void* d_actions, int act_dtype, float* d_adjusted, int32_t type_major, double* d_slack,
+                      uint8_t* d_intervened, void* stream);
+
 /* -- acting policy of the rollout loop, transitions, learner feed ---- */
 
 /* The shared-parameter RNNAgent (madrl/agents/rnn_agent.py:8-32: fc1(144 obs + 5 agent-id -> 64) -> LayerNorm ->

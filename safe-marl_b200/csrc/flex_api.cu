@@ -43,6 +43,7 @@ struct FpHandle {
     float* d_obsr = nullptr; int ring_q = 0; bool obsr_valid = false; int64_t n_pad = 0;
     double *d_pfl = nullptr, *d_qfl = nullptr, *d_isq = nullptr;
     double* d_stats_partial = nullptr;
+    double safety_sP[8] = {0}, safety_sQ[8] = {0}, safety_b[8] = {0}, safety_vmin = 0, safety_vmax = 0, safety_w = 0; int safety_loaded = 0;
     uint8_t* d_retry_mask = nullptr; void* d_retry_count = nullptr;     // fp_reset_random_retry: device-built retry mask
     int stats_rows = 0, stats_cap = 0;     // rows of one launch's statistics block
     const uint8_t* d_inject = nullptr;
@@ -806,6 +807,42 @@ int fp_obs_ring_gather(FpHandle* h, float* d_out, void* stream) {
     int rc = obs_envminor_prepare(h, false, (cudaStream_t)stream);
     if (rc != FP_OK) return rc;
     CUDA_TRY(h, launch_obsr_gather(h->d_obsr, d_out, h->n, h->n_pad, h->dc.na, h->dc.history, h->ring_q, (cudaStream_t)stream));
+    h->launches++;
+    return FP_OK;
+}
+
+// Safety layer (madrl/models/safemaddpg.py:176-299) as a batched closed-form projection: see k_safety_project.
+int fp_safety_load(FpHandle* h, const double* h_coef, const double* h_intercept, double v_min, double v_max, double slack_weight) {
+    if (!h) return FP_EINVAL;
+    if (!h_coef || !h_intercept) return fail(h, FP_EINVAL, "fp_safety_load: null model");
+    if (!(slack_weight > 0.0) || !(v_min < v_max)) return fail(h, FP_EINVAL, "fp_safety_load: bad limits / weight");
+    const int nb = h->dc.nb, na = h->dc.na;
+    // safemaddpg.py:182-184: W_P = coef[:, :nb], W_Q = coef[:, nb:]; :266,272 multiply their ROW SUMS by the bus's own P_net / Q_net
+    for (int i = 0; i < na; ++i) {
+        const int bus = h->topo.agent_col[i] + 1;                 // bus position of agent i's building
+        double sp = 0.0, sq = 0.0;
+        for (int j = 0; j < nb; ++j) { sp += h_coef[(size_t)bus * 2 * nb + j]; sq += h_coef[(size_t)bus * 2 * nb + nb + j]; }
+        h->safety_sP[i] = sp; h->safety_sQ[i] = sq; h->safety_b[i] = h_intercept[bus];
+    }
+    h->safety_vmin = v_min; h->safety_vmax = v_max; h->safety_w = slack_weight; h->safety_loaded = 1;
+    return FP_OK;
+}
+
+int fp_safety_project(FpHandle* h, const void* d_actions, int act_dtype, float* d_adjusted, int32_t type_major, double* d_slack,
+                      uint8_t* d_intervened, void* stream) {
+    if (!h) return FP_EINVAL;
+    USE_DEVICE(h);
+    if (!h->safety_loaded) return fail(h, FP_ESTATE, "fp_safety_project: call fp_safety_load first");
+    if (!h->d_P) return fail(h, FP_ESTATE, "fp_safety_project: call fp_load_profiles first");
+    if (!d_actions || !d_adjusted || (act_dtype != FP_F32 && act_dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_safety_project: bad arguments");
+    SafetyParams p;
+    std::memset(&p, 0, sizeof(p));
+    fill_obs_params(h, p.o, nullptr, 0);
+    for (int i = 0; i < h->dc.na; ++i) { p.sP[i] = h->safety_sP[i]; p.sQ[i] = h->safety_sQ[i]; p.b[i] = h->safety_b[i]; }
+    p.v_min = h->safety_vmin; p.v_max = h->safety_vmax; p.w = h->safety_w;
+    p.actions = d_actions; p.act_f64 = (act_dtype == FP_F64);
+    p.out = d_adjusted; p.type_major = type_major; p.slack = d_slack; p.intervened = d_intervened;
+    CUDA_TRY(h, launch_safety_project(p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
 }

@@ -670,6 +670,93 @@ cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad
     return cudaGetLastError();
 }
 
+// Safety layer of SAFEMADDPG (madrl/models/safemaddpg.py:176-299) for every env at once.  The reference builds a QP per
+// get_actions call (20 action variables, P_net / Q_net of 33 buses, 66 slacks priced at 1000) and hands it to Gurobi; in
+// the form it evaluates the voltage prediction (:266,272: row sums of the coefficient blocks times the bus's OWN P_net /
+// Q_net) the problem separates per building into
+//     min (x - x0)^2 + (c - c0)^2 + (d - d0)^2 + (g - g0)^2 + w (s_lo + s_up)
+//     s.t. V = sP (Pd (1 - x) + c - d) + sQ (Qd + g) + b,  v_min - s_lo <= V <= v_max + s_up,  x, c, d, s >= 0
+// whose optimum is closed-form: with a = dV / d(x, c, d, g) pointing towards the violated limit and multiplier
+// lam in [0, w], y(lam) = max(y0 + (lam / 2) a, 0) on the bounded variables; the gain a . (y - y0) is concave piecewise
+// linear in lam (<= 3 breakpoints, where a decreasing variable reaches zero) and lam* is the smallest multiplier that
+// closes the deficit, else w (the rest is slack).  One thread per (env, agent); mirrored by oracle/safety_ref.py.
+__global__ void k_safety_project(const SafetyParams prm) {
+    const DevCfg& c = prm.o.c;
+    const int na = c.na;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < prm.o.n * na; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / na;
+        const int i = (int)(t - e * na);
+        // the env's current demands, PV and ESS energy (the row in force, quirk Q1)
+        const uint64_t* rec = prm.o.rec + e * FP_REC_STRIDE;
+        const uint64_t tm = rec[FP_REC_TIME];
+        const int32_t start = (int32_t)(uint32_t)tm, steps = (int32_t)(tm >> 32);
+        const int64_t row = (int64_t)start + ((steps > 1) ? min(steps - 1, c.episode_limit + c.history) : 1);
+        const double* orow = prm.o.OBSROW + row * FP_OBS_STRIDE;
+        const double Pd = __ldg(orow + FP_OBS_P + i), Qd = __ldg(orow + FP_OBS_Q + i), ppv = __ldg(orow + FP_OBS_PV + i);
+        const double e_cur = __longlong_as_double((long long)rec[FP_REC_E_CUR + i]);
+        double a0, a1, a2, a3;
+        if (prm.act_f64) {
+            const double* ap = reinterpret_cast<const double*>(prm.actions) + t * 4;
+            a0 = ap[0]; a1 = ap[1]; a2 = ap[2]; a3 = ap[3];
+        } else {
+            const float4 f = reinterpret_cast<const float4*>(prm.actions)[t];
+            a0 = f.x; a1 = f.y; a2 = f.z; a3 = f.w;
+        }
+        // parse_actions (:143-174) = the env's own scaling / clipping / ESS logic
+        const Setpoint sp = apply_actions_frac(c, true, a0, a1, a2, a3, ppv, e_cur);
+        double y[4] = {sp.pred, sp.ch, sp.dis, sp.qpv};
+        const double sP = prm.sP[i], sQ = prm.sQ[i];
+        const double V0 = fma(sQ, Qd + y[3], sP * ((Pd * (1.0 - y[0]) + y[1]) - y[2])) + prm.b[i];
+        double slack = 0.0;
+        bool moved = false;
+        const bool low = V0 < prm.v_min, high = V0 > prm.v_max;
+        if (low || high) {
+            const double sg = low ? 1.0 : -1.0;
+            const double delta = low ? (prm.v_min - V0) : (V0 - prm.v_max);
+            const double a[4] = {sg * (-sP * Pd), sg * sP, sg * (-sP), sg * sQ};
+            // breakpoints of the bounded variables that move down, sorted (three-element network)
+            double bk[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) bk[k] = (a[k] < 0.0) ? (2.0 * y[k] / -a[k]) : prm.w;
+            if (bk[0] > bk[1]) { const double s_ = bk[0]; bk[0] = bk[1]; bk[1] = s_; }
+            if (bk[1] > bk[2]) { const double s_ = bk[1]; bk[1] = bk[2]; bk[2] = s_; }
+            if (bk[0] > bk[1]) { const double s_ = bk[0]; bk[0] = bk[1]; bk[1] = s_; }
+            double lam = 0.0, gain = 0.0;
+            bool closed = false;
+#pragma unroll
+            for (int seg = 0; seg < 4 && !closed; ++seg) {
+                double nxt = (seg < 3) ? bk[seg] : prm.w;
+                nxt = (nxt < prm.w) ? nxt : prm.w;
+                if (nxt <= lam) continue;
+                double sl = a[3] * a[3] * 0.5;                  // d gain / d lam on (lam, nxt)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (a[k] > 0.0 || (a[k] < 0.0 && lam < 2.0 * y[k] / -a[k])) sl += a[k] * a[k] * 0.5;
+                if (sl > 0.0 && gain + sl * (nxt - lam) >= delta) { lam += (delta - gain) / sl; gain = delta; closed = true; }
+                else { gain += sl * (nxt - lam); lam = nxt; }
+            }
+            slack = (delta - gain > 0.0) ? (delta - gain) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const double v = fma(0.5 * lam, a[k], y[k]); y[k] = (v > 0.0) ? v : 0.0; }
+            y[3] = fma(0.5 * lam, a[3], y[3]);
+            moved = lam > 0.0;
+        }
+        if (prm.type_major) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) prm.out[e * 4 * na + k * na + i] = (float)y[k];    // [x(na) | c(na) | d(na) | g(na)], :290-296
+        } else {
+            reinterpret_cast<float4*>(prm.out)[t] = make_float4((float)y[0], (float)y[1], (float)y[2], (float)y[3]);
+        }
+        if (prm.slack != nullptr) prm.slack[t] = slack;
+        if (prm.intervened != nullptr) prm.intervened[t] = moved ? 1 : 0;
+    }
+}
+cudaError_t launch_safety_project(const SafetyParams& prm, cudaStream_t st) {
+    const int64_t ctas = (prm.o.n * prm.o.c.na + 255) / 256;
+    k_safety_project<<<(unsigned)(ctas < 148 * 16 ? ctas : 148 * 16), 256, 0, st>>>(prm);
+    return cudaGetLastError();
+}
+
 // out[e] = 1 for the envs (of `mask`, if given) whose last reset failed (FP_FLAG_RESET_FAILED); *count = how many
 __global__ void k_reset_failed_mask(const uint64_t* __restrict__ rec, const uint8_t* __restrict__ mask, int64_t n,
                                     uint8_t* __restrict__ out, int32_t* __restrict__ count) {

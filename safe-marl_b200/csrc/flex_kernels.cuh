@@ -91,6 +91,16 @@ cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad
 cudaError_t launch_obsr_clear(float* obsr, const uint8_t* mask, int64_t n, int64_t n_pad, int rows, cudaStream_t st);
 cudaError_t launch_obsr_reset_push(const ObsParams& prm, float* obsr, int64_t n_pad, int q, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_obsr_gather(const float* obsr, float* out, int64_t n, int64_t n_pad, int na, int H, int q, cudaStream_t st);
+// safety layer of SAFEMADDPG as a batched projection (fp_safety_project)
+struct SafetyParams {
+    ObsParams o;                                   // c, n, OBSROW, rec (the env's current demands / PV / ESS energy)
+    double sP[8], sQ[8], b[8];                     // row sums of the predictor's P / Q coefficient blocks and intercept at the agents' buses
+    double v_min, v_max, w;
+    const void* actions; int32_t act_f64;          // proposed raw policy actions [n][na][4]
+    float* out; int32_t type_major;                // adjusted setpoints: [n][4][na] (the reference's return layout) or [n][na][4]
+    double* slack; uint8_t* intervened;            // per (env, agent): remaining slack, 1 if the layer moved the action (may be null)
+};
+cudaError_t launch_safety_project(const SafetyParams& prm, cudaStream_t st);
 cudaError_t launch_reset_failed_mask(const uint64_t* rec, const uint8_t* mask, int64_t n, uint8_t* out, int32_t* count, cudaStream_t st);
 cudaError_t launch_stats_fold(const double* partial, int n_blocks, double* out, cudaStream_t st);
 cudaError_t launch_pack_obsrow(const double* P, const double* Q, const double* pvp, const int32_t* agent_col, int na, int nl,

@@ -93,6 +93,8 @@ _PROTOS = {
     "fp_replay_field_ptr": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     "fp_predictor_load": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double]),
     "fp_predict": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P]),
+    "fp_safety_load": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, C.c_double]),
+    "fp_safety_project": (C.c_int, [_P, _P, C.c_int, _P, C.c_int32, _P, _P, _P]),
     "fp_policy_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "fp_policy_destroy": (C.c_int, [_P]),
     "fp_policy_last_error": (C.c_char_p, [_P]),

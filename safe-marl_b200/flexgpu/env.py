@@ -430,6 +430,33 @@ class BatchedFlexProvisionEnv:
                                             _ptr(Isq), _ptr(iters), _ptr(failed), _stream()), "fp_power_flow")
         return dict(V=V, P=Pl, Q=Ql, Isq=Isq, iters=iters, failed=failed.bool())
 
+    # ------------------------------------------------------------------ safety layer (SAFEMADDPG)
+    def load_safety_model(self, coef, intercept, slack_weight=1000.0):
+        """The fitted voltage regressor as safemaddpg.py:182-184 reads it: coef [n_bus, 2 n_bus], intercept [n_bus]."""
+        coef = np.ascontiguousarray(coef, dtype=np.float64); icpt = np.ascontiguousarray(intercept, dtype=np.float64)
+        if coef.shape != (self.n_bus, 2 * self.n_bus) or icpt.shape != (self.n_bus,):
+            raise ValueError("coef must be [n_bus, 2 n_bus] and intercept [n_bus]")
+        self._check(self._lib.fp_safety_load(self._h, coef.ctypes.data_as(C.c_void_p), icpt.ctypes.data_as(C.c_void_p),
+                                             float(self.args_dict["v_min"]), float(self.args_dict["v_max"]), float(slack_weight)),
+                    "fp_safety_load")
+
+    def safety_project(self, actions, layout="reference", want_info=False):
+        """safety_layer_optimization (safemaddpg.py:176-299) for every env: raw policy actions [N, na, 4] -> adjusted
+        setpoints (fp32).  layout="reference": [N, 4 na] as the reference returns them ([x | c | d | g], :290-296);
+        layout="agent": [N, na, 4].  want_info adds (slack [N, na] f64, intervened [N, na] bool)."""
+        a = actions.to(self.device).contiguous()
+        if a.dtype not in (torch.float32, torch.float64):
+            a = a.to(torch.float64)
+        if a.numel() != self.n_envs * self.n_agents * 4:
+            raise ValueError("actions must have n_envs * n_agents * 4 elements")
+        tm = layout == "reference"
+        out = torch.empty((self.n_envs, 4 * self.n_agents) if tm else (self.n_envs, self.n_agents, 4), dtype=torch.float32, device=self.device)
+        slack = torch.empty(self.n_envs, self.n_agents, dtype=torch.float64, device=self.device) if want_info else None
+        moved = torch.empty(self.n_envs, self.n_agents, dtype=torch.uint8, device=self.device) if want_info else None
+        self._check(self._lib.fp_safety_project(self._h, _ptr(a), _lib.FP_F64 if a.dtype == torch.float64 else _lib.FP_F32, _ptr(out),
+                                                1 if tm else 0, _ptr(slack), _ptr(moved), _stream()), "fp_safety_project")
+        return (out, slack, moved.bool()) if want_info else out
+
     # ------------------------------------------------------------------ statistics
     def episode_stats(self, reduce=True, reset=False):
         """Sums accumulated by every step since the last reset of the statistics (the batched
