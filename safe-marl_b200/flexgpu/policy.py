@@ -228,3 +228,42 @@ def learner_batch(policy, replay, batch_size, start=None, reward_normalisation=T
     if critic_input:
         out["critic_in"] = crit
     return out
+
+
+def smoke(env, device):
+    """Tiny policy + rollout invocation for __graft_entry__.smoke(): k_policy on the env's own observation ring against
+    a plain torch fp32 evaluation of RNNAgent.forward (rnn_agent.py:24-32) with the same (TF32-rounded) matrices."""
+    g = torch.Generator().manual_seed(0)
+    sd = {k: (torch.randn(s, generator=g) * 0.1) for k, s in zip(_WEIGHT_KEYS, _WEIGHT_SHAPES)}
+    sd["layernorm.weight"] = 1.0 + sd["layernorm.weight"]
+    pol = DevicePolicy(sd, device=device)
+    ring = env.obs_ring()
+    n = env.n_envs
+    h_in = (torch.rand(n, N_AGENTS, HID, generator=g) - 0.5).to(device)
+    act, _, hid, mean = pol.act(ring, hid_in=h_in, explore=False, want_mean=True, hid_out=torch.empty(n, N_AGENTS, HID, device=device))
+    w = {k: v.to(device) for k, v in sd.items()}
+    for k in ("rnn.weight_ih", "rnn.weight_hh"):
+        w[k] = torch.from_numpy(round_tf32(sd[k].numpy())).to(device)
+    w1 = sd["fc1.weight"].numpy().copy(); w1[:, :OBS] = round_tf32(w1[:, :OBS]); w["fc1.weight"] = torch.from_numpy(w1).to(device)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        obs = ring.dense().view(n * N_AGENTS, OBS)
+        x = torch.cat([obs, torch.eye(N_AGENTS, device=device).repeat(n, 1)], dim=1) @ w["fc1.weight"].T + w["fc1.bias"]
+        x = torch.relu(torch.nn.functional.layer_norm(x, (HID,), w["layernorm.weight"], w["layernorm.bias"], 1e-5))
+        h0 = h_in.view(-1, HID)
+        gi = x @ w["rnn.weight_ih"].T + w["rnn.bias_ih"]; gh = h0 @ w["rnn.weight_hh"].T + w["rnn.bias_hh"]
+        r = torch.sigmoid(gi[:, :HID] + gh[:, :HID]); z = torch.sigmoid(gi[:, HID:2 * HID] + gh[:, HID:2 * HID])
+        nn_ = torch.tanh(gi[:, 2 * HID:] + r * gh[:, 2 * HID:])
+        h1 = (1 - z) * nn_ + z * h0
+        m = h1 @ w["fc2.weight"].T + w["fc2.bias"]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    err = max(float((mean.view(-1, ACT) - m).abs().max()), float((hid.view(-1, HID) - h1).abs().max()),
+              float((act.view(-1, ACT) - torch.tanh(m)).abs().max()))
+    assert err < 5e-5, f"policy mismatch {err}"
+    ro = DeviceRollout(env, pol)
+    ro.ring = ring
+    ro.step()
+    pol.close()
+    return err
