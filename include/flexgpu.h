@@ -243,6 +243,10 @@ int fp_get_state(FpHandle* h, void* d_out, int dtype, void* stream);
 int fp_state_ptrs(FpHandle* h, void** d_rec, void** d_voltage, void** d_setpoint,
                   void** d_pflow, void** d_qflow, void** d_isq);
 int fp_set_keep_flows(FpHandle* h, int keep);
+/* The fp64 observation-history ring, [N][history][32] doubles (5 x 6 values + 2 pad per entry): with fp_state_ptrs'
+ * rec / voltage / setpoint arrays it is the complete per-env device state (checkpointing).  write != 0: the
+ * caller is about to overwrite it; the derived fp32 observation rings are rebuilt from it on their next use. */
+int fp_history_ptr(FpHandle* h, void** d_hist, int64_t* doubles_per_env, int32_t write);
 
 /* -- power flow only (BASELINE config 2) -------------------------------------------------- */
 

@@ -870,6 +870,16 @@ int fp_state_ptrs(FpHandle* h, void** d_rec, void** d_voltage, void** d_setpoint
     return FP_OK;
 }
 
+// The fp64 observation-history ring (the source of truth of get_obs, quirk Q7): [N][history][FP_HIST_SLOT] doubles.
+// With write != 0 the caller is about to overwrite it (state restore): the derived fp32 rings are rebuilt on next use.
+int fp_history_ptr(FpHandle* h, void** d_hist, int64_t* doubles_per_env, int32_t write) {
+    if (!h || !d_hist) return FP_EINVAL;
+    *d_hist = h->d_hist;
+    if (doubles_per_env) *doubles_per_env = (int64_t)h->dc.history * FP_HIST_SLOT;
+    if (write) { h->obsm_valid = false; h->obsr_valid = false; }
+    return FP_OK;
+}
+
 int fp_set_keep_flows(FpHandle* h, int keep) {
     if (!h) return FP_EINVAL;
     if (keep && !h->d_pfl) {

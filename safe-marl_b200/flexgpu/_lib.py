@@ -75,6 +75,7 @@ _PROTOS = {
     "fp_get_state": (C.c_int, [_P, _P, C.c_int, _P]),
     "fp_state_ptrs": (C.c_int, [_P] + [C.POINTER(_P)] * 6),
     "fp_set_keep_flows": (C.c_int, [_P, C.c_int]),
+    "fp_history_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.c_int32]),
     "fp_power_flow": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fp_stats_read": (C.c_int, [_P, _P, _P]),
     "fp_stats_reset": (C.c_int, [_P, _P]),

@@ -430,6 +430,28 @@ class BatchedFlexProvisionEnv:
                                             _ptr(Isq), _ptr(iters), _ptr(failed), _stream()), "fp_power_flow")
         return dict(V=V, P=Pl, Q=Ql, Isq=Isq, iters=iters, failed=failed.bool())
 
+    # ------------------------------------------------------------------ checkpointing the device state
+    def _history(self, write):
+        p, per = C.c_void_p(), C.c_int64()
+        self._check(self._lib.fp_history_ptr(self._h, C.byref(p), C.byref(per), 1 if write else 0), "fp_history_ptr")
+        holder = _ExternalCudaBuffer(p.value, self.n_envs * per.value * 8, self.device.index or 0)
+        return torch.as_tensor(holder, device=self.device).view(torch.float64).view(self.n_envs, per.value)
+
+    def state_dict(self):
+        """The complete per-env device state as CPU tensors: records (energies, counters, masks), voltages, applied
+        setpoints, observation history.  The reference checkpoints no env state (train_agent.py:144-147 saves the model
+        only); this is for debugging and for resuming a rollout."""
+        torch.cuda.synchronize(self.device)
+        return {"rec": self.rec.cpu().clone(), "voltage": self.voltages.cpu().clone(), "setpoint": self.setpoints.cpu().clone(),
+                "history": self._history(False).cpu().clone(), "n_envs": self.n_envs, "seed": self.seed, "env_offset": self.env_offset}
+
+    def load_state_dict(self, sd):
+        if int(sd["n_envs"]) != self.n_envs:
+            raise ValueError("state_dict holds a different number of envs")
+        self.rec.copy_(sd["rec"].to(self.device)); self.voltages.copy_(sd["voltage"].to(self.device))
+        self.setpoints.copy_(sd["setpoint"].to(self.device)); self._history(True).copy_(sd["history"].to(self.device))
+        self.seed, self.env_offset = int(sd["seed"]), int(sd["env_offset"])
+
     # ------------------------------------------------------------------ safety layer (SAFEMADDPG)
     def load_safety_model(self, coef, intercept, slack_weight=1000.0):
         """The fitted voltage regressor as safemaddpg.py:182-184 reads it: coef [n_bus, 2 n_bus], intercept [n_bus]."""

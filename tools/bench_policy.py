@@ -19,10 +19,12 @@ ring = torch.rand(24, 5, 6, n_pad, device=dev)
 h = [torch.rand(E, 5, 64, device=dev) - 0.5, torch.empty(E, 5, 64, device=dev)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ts = []
+NOHID = bool(os.environ.get("NOHID")); NOFLUSH = bool(os.environ.get("NOFLUSH"))
 for k in range(iters + 3):
-    flush.zero_()
+    if not NOFLUSH:
+        flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); pol.act(ring, slot=k % 24, n_envs=E, hid_in=h[k % 2], hid_out=h[1 - k % 2], step=k); b.record()
+    a.record(); pol.act(ring, slot=k % 24, n_envs=E, hid_in=None if NOHID else h[k % 2], hid_out=h[1 - k % 2], step=k); b.record()
     torch.cuda.synchronize()
     if k >= 3:
         ts.append(a.elapsed_time(b) * 1e3)
