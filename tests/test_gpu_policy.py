@@ -198,3 +198,45 @@ def test_learner_batch_matches_reference_unpack_data(gold, cuda):
     raw = learner_batch(pol, buf, 32, start=int(gold["batch_start"]), reward_normalisation=False, critic_input=False)
     assert "critic_in" not in raw and float(raw["reward"].abs().max()) > 0
     pol.close(); buf.close()
+
+
+def test_rollout_matches_reference_train_process(cuda):
+    """End to end against the reference's own loop: tests/golden/ref_rollout.npz holds the 8 Transitions that
+    Model.train_process (madrl/models/model.py:198-267) wrote into a TransReplayBuffer -- reference env (on the Pyomo
+    stand-in), reference MADDPG / RNNAgent / select_action, the recorded exploration draws.  The device loop (tcgen05
+    policy -> fused translate_action + step + get_obs) from the same start row, E0, reset actions, weights and draws
+    must write the same Transition fields.  Tolerances: the policy differs from torch fp32 by ~1e-6 (fp32 arithmetic in a
+    different order), which the env turns into ~1e-7 relative on setpoints and rewards; observations are fp32 here
+    and fp64 -> fp32 in the reference (prep_obs)."""
+    from flexgpu import BatchedFlexProvisionEnv, Profiles
+    from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS
+    from flexgpu.predictor import DeviceReplayBuffer
+    g = np.load(os.path.join(os.path.dirname(GOLD), "ref_rollout.npz"))
+    T = g["tr_reward"].shape[0]
+    env = BatchedFlexProvisionEnv(None, n_envs=1, device=cuda, profiles=Profiles(g["P"], g["Q"], g["PV"], g["price"]))
+    pol = DevicePolicy({k: g["w_" + k] for k in KEYS}, device=cuda, std=1.0)
+    buf = DeviceReplayBuffer(64, TRANSITION_FIELDS, device=cuda)
+    ro = DeviceRollout(env, pol, replay=buf, max_steps=T)
+    env.reset([0], g["e0"][None], g["a0"][None], return_obs=False)          # trainer.env.reset() (model.py:208) with the reference's draws
+    assert np.max(np.abs(env.voltages[0].cpu().numpy() - g["V0"])) < 1e-8
+    env._check(env._lib.fp_obs_ring_reset_push(env._h, None, None), "fp_obs_ring_reset_push")    # the get_obs inside reset() (:155)
+    ro.ring = env.obs_ring(); ro.t = 0
+    ro._hid[ro._cur].zero_()
+    rewards = []
+    for t in range(T):
+        reward, done = ro.step(eps=torch.from_numpy(g["eps"][2 * t][None].astype(np.float32)))   # draw 2t + 1 feeds next_value only
+        rewards.append(float(reward[0]))
+    got = {k: v.cpu().numpy().astype(np.float64) for k, v in buf.get_batch(T, start=0).items()}
+    tol = dict(state=2e-6, next_state=2e-6, action=5e-6, log_prob_a=2e-4, reward=None, done=0, last_step=0, action_avail=0,
+               last_hid=5e-6, hid=5e-6)
+    for k, bound in tol.items():
+        want = g["tr_" + k]
+        assert got[k].shape == want.shape, k
+        if bound is None:
+            assert np.max(np.abs(got[k] - want) / np.abs(want)) < 1e-5, (k, got[k][:, 0], want[:, 0])     # fp32 field of an fp64 reward
+        else:
+            assert np.max(np.abs(got[k] - want)) <= bound, (k, float(np.max(np.abs(got[k] - want))))
+    assert np.max(np.abs(np.array(rewards) - g["tr_reward"][:, 0]) / np.abs(g["tr_reward"][:, 0])) < 1e-6        # the fp64 reward itself
+    assert got["last_step"][-1, 0] == 1.0 and got["done"][-1, 0] == 0.0           # done_ = t == max_steps - 1 (model.py:229)
+    assert abs(np.sum(rewards) / T - float(g["mean_train_reward"])) < 1e-6 * abs(float(g["mean_train_reward"]))   # model.py:252,261-264
+    pol.close(); buf.close(); env.close()
