@@ -238,5 +238,7 @@ def test_rollout_matches_reference_train_process(cuda):
             assert np.max(np.abs(got[k] - want)) <= bound, (k, float(np.max(np.abs(got[k] - want))))
     assert np.max(np.abs(np.array(rewards) - g["tr_reward"][:, 0]) / np.abs(g["tr_reward"][:, 0])) < 1e-6        # the fp64 reward itself
     assert got["last_step"][-1, 0] == 1.0 and got["done"][-1, 0] == 0.0           # done_ = t == max_steps - 1 (model.py:229)
-    assert abs(np.sum(rewards) / T - float(g["mean_train_reward"])) < 1e-6 * abs(float(g["mean_train_reward"]))   # model.py:252,261-264
+    # the reference's statistic counts the reward TWICE: info carries a 'reward' key (:697) that lands in the same
+    # 'mean_train_reward' slot as the step's reward (model.py:247-252), then the sum is divided by t + 1 (:261-264)
+    assert abs(2.0 * np.sum(rewards) / T - float(g["mean_train_reward"])) < 1e-6 * abs(float(g["mean_train_reward"]))
     pol.close(); buf.close(); env.close()
