@@ -40,5 +40,13 @@ def episode_means(stats):
     """Per-step means of every info key, as the reference reports them per episode (model.py:261-264),
     from the summed statistics of all envs and ranks."""
     n = float(stats["env_steps"])
-    return {("mean_train_" + k): (float(stats[k]) / n if n > 0 else 0.0)
-            for k in _lib.INFO_KEYS + ("violation_count", "line_violation_count")}
+    out = {("mean_train_" + k): (float(stats[k]) / n if n > 0 else 0.0)
+           for k in _lib.INFO_KEYS + ("violation_count", "line_violation_count")}
+    # The reference's own 'mean_train_reward' counts the reward twice: info carries a 'reward' key (the pre-penalty
+    # reward, flexibility_provision_env.py:697) that is accumulated into the same slot as the step's reward
+    # (model.py:247-252: sum(info['reward']) + sum(reward), the latter incl. -200 per failed step) before the
+    # division by the step count -- reported separately so that curves can be compared with the reference's logs.
+    fail_penalty = 200.0
+    out["mean_train_reward_as_reference_logs_it"] = ((2.0 * float(stats["reward"]) - fail_penalty * float(stats["solver_failed"])) / n
+                                                     if n > 0 else 0.0)
+    return out
