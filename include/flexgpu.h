@@ -331,14 +331,15 @@ int64_t fp_policy_launch_count(const FpPolicy* p);
 int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const float* ln_g, const float* ln_b,
                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                    const float* fc2_w, const float* fc2_b);
-/* One acting step.  d_ring / slot / n_pad: the observation ring.  d_hid_in (NULL = zeros) / d_hid_out: [n_envs][5][64]
- * hidden states (last_hid / hid of the Transition); d_reset (may be NULL): envs whose hidden state restarts at zero
+/* One acting step.  d_ring / slot / n_pad: the observation ring.  d_hid_in (NULL = zeros) / d_hid_out: hidden states
+ * (last_hid / hid of the Transition), [n_envs][5][64] or -- hid_env_minor != 0, the kernel's native layout: every access a
+ * coalesced 128-byte line -- [5][64][n_pad] (fp_policy_hidden_to_ring turns it into replay rows); d_reset (may be NULL): envs whose hidden state restarts at zero
  * (init_hidden, model.py:211).  Outputs [n_envs][5][4] fp32: d_mean (may be NULL), d_action = tanh(mean + std eps)
  * (what translate_action receives: feed it to fp_step* with FP_F32_POLICY), d_logp (may be NULL).  explore = 1: status
  * 'train' with exploration, eps from d_eps (caller-supplied standard-normal draws, [n_envs][5][4]) or, if NULL, from
  * Philox4x32-10 keyed by (seed; row, step); explore = 0: status 'test' (action = tanh(mean)).  std = fixed_policy_std. */
 int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_hid_in,
-                  const uint8_t* d_reset, float* d_hid_out, float* d_mean, float* d_action, float* d_logp,
+                  const uint8_t* d_reset, float* d_hid_out, int32_t hid_env_minor, float* d_mean, float* d_action, float* d_logp,
                   const float* d_eps, uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream);
 /* Transition fields (madrl/models/model.py:19, :230-242) straight into a replay ring: field rows (row0 + e) mod cap.
  *   fp_policy_gather_windows   state / next_state: the dense get_obs windows [5][144] of envs [0, n) from the ring
@@ -348,6 +349,8 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
  *                              last_step_all: t == max_steps - 1, model.py:229), all-ones action_avail; NULL fields skipped */
 int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n, float* d_out,
                              int64_t pitch, int64_t row0, int64_t cap, void* stream);
+int fp_policy_hidden_to_ring(FpPolicy* p, const float* d_hid_em, int64_t n_pad, int64_t n, float* d_field, int64_t row0,
+                             int64_t cap, void* stream);
 int fp_policy_rows_to_ring(FpPolicy* p, const float* d_src, int64_t n, int32_t width, float* d_field, int64_t row0,
                            int64_t cap, void* stream);
 int fp_policy_scalars_to_ring(FpPolicy* p, const double* d_reward, const uint8_t* d_done, int64_t n, int32_t last_step_all,

@@ -69,7 +69,8 @@ constexpr uint32_t C_A2HI = 0, C_A2LO = 64, C_A3HI = 128, C_A3LO = 192, C_RZ = 2
 struct PolParams {
     const float* ring; int64_t n_pad; int64_t n; int32_t slot;       // observation ring, newest slot
     const float* W1rot; const float* Wg; const float* vec;
-    const float* hid_in; const uint8_t* reset; float* hid_out;        // [n][5][64]; reset: h_in = 0 for these envs
+    const float* hid_in; const uint8_t* reset; float* hid_out;        // [n][5][64], or env-minor [5][64][n_pad] (hid_em); reset: h_in = 0 for these envs
+    int32_t hid_em;
     float* mean; float* action; float* logp;                          // [n][5][4]
     const float* eps;                                                 // optional caller-supplied N(0,1) draws [n][5][4]
     uint64_t seed; uint64_t step; float std_; float log_std; int32_t explore;
@@ -338,11 +339,17 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
             float h[CPT];
             {
                 const bool zero = !live || prm.hid_in == nullptr || (prm.reset != nullptr && prm.reset[e] != 0);
-                const float4* hp = reinterpret_cast<const float4*>(prm.hid_in + (zero ? 0 : r_glob) * POL_HID + c0);
+                if (prm.hid_em) {                                               // env-minor: one coalesced 128-byte line per unit and warp
+                    const float* hp = prm.hid_in + (zero ? 0 : ((int64_t)(a * POL_HID + c0) * prm.n_pad + e));
 #pragma unroll
-                for (int i = 0; i < CPT / 4; ++i) {
-                    const float4 t = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(hp + i);
-                    h[4 * i] = t.x; h[4 * i + 1] = t.y; h[4 * i + 2] = t.z; h[4 * i + 3] = t.w;
+                    for (int i = 0; i < CPT; ++i) h[i] = zero ? 0.0f : __ldg(hp + (int64_t)i * prm.n_pad);
+                } else {
+                    const float4* hp = reinterpret_cast<const float4*>(prm.hid_in + (zero ? 0 : r_glob) * POL_HID + c0);
+#pragma unroll
+                    for (int i = 0; i < CPT / 4; ++i) {
+                        const float4 t = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(hp + i);
+                        h[4 * i] = t.x; h[4 * i + 1] = t.y; h[4 * i + 2] = t.z; h[4 * i + 3] = t.w;
+                    }
                 }
             }
             if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small arrays have landed
@@ -406,7 +413,11 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                     }
                 }
                 fcp[qt * POL_M + row] = make_float4(p0, p1, p2, p3);
-                if (live) {
+                if (live && prm.hid_em) {
+                    float* ho = prm.hid_out + (int64_t)(a * POL_HID + c0) * prm.n_pad + e;
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) ho[(int64_t)i * prm.n_pad] = h[i];
+                } else if (live) {
                     float4* ho = reinterpret_cast<float4*>(prm.hid_out + r_glob * POL_HID + c0);
 #pragma unroll
                     for (int i = 0; i < CPT / 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
@@ -498,6 +509,28 @@ __global__ void __launch_bounds__(256) k_window_gather(const float* __restrict__
                 int64_t orow = row0 + e0 + j; orow = orow >= cap ? orow - cap : orow;
                 float* dst = out + orow * pitch + a * POL_OBS;
                 for (int k = lane; k < POL_OBS; k += 32) dst[k] = t[k][j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// env-minor [rows][n_pad] (rows = 5 agents x 64 units) -> ring rows (row0 + e) mod cap of `rows` contiguous floats:
+// the hidden states of the Transition (last_hid / hid, (1, 5, 64) per env) from the policy kernel's native layout
+__global__ void __launch_bounds__(256) k_em_gather(const float* __restrict__ src, int64_t n_pad, int rows, int64_t n,
+                                                   float* __restrict__ out, int64_t row0, int64_t cap) {
+    extern __shared__ float tbuf[];                               // [rows][33]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n_blk = (n + 31) >> 5;
+    for (int64_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const int64_t e0 = blk << 5;
+        for (int k = w; k < rows; k += 8) tbuf[k * 33 + lane] = (e0 + lane < n) ? src[(int64_t)k * n_pad + e0 + lane] : 0.0f;
+        __syncthreads();
+        for (int j = w; j < 32; j += 8) {
+            if (e0 + j < n) {
+                int64_t orow = row0 + e0 + j; orow = orow >= cap ? orow - cap : orow;
+                float* dst = out + orow * rows;
+                for (int k = lane; k < rows; k += 32) dst[k] = tbuf[k * 33 + j];
             }
         }
         __syncthreads();
@@ -699,8 +732,8 @@ int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const fl
 // (d_eps = caller-supplied standard-normal draws [n_envs][5][4], or null: Philox keyed by (seed, row, step));
 // explore = 0: status 'test'.  std = fixed_policy_std (default.yaml: 1.0).
 int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_hid_in,
-                  const uint8_t* d_reset, float* d_hid_out, float* d_mean, float* d_action, float* d_logp, const float* d_eps,
-                  uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream) {
+                  const uint8_t* d_reset, float* d_hid_out, int32_t hid_env_minor, float* d_mean, float* d_action, float* d_logp,
+                  const float* d_eps, uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream) {
     if (!p) return FP_EINVAL;
     if (!p->loaded) return pfail(p, FP_ESTATE, "fp_policy_act: call fp_policy_load first");
     if (!d_ring || !d_hid_out || !d_action || n_envs < 1 || slot < 0 || slot >= POL_H || n_pad < n_envs || (n_pad & 3))
@@ -711,7 +744,7 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
     std::memset(&prm, 0, sizeof(prm));
     prm.ring = d_ring; prm.n_pad = n_pad; prm.n = n_envs; prm.slot = slot;
     prm.W1rot = p->d_W1rot; prm.Wg = p->d_Wg; prm.vec = p->d_vec;
-    prm.hid_in = d_hid_in; prm.reset = d_reset; prm.hid_out = d_hid_out;
+    prm.hid_in = d_hid_in; prm.reset = d_reset; prm.hid_out = d_hid_out; prm.hid_em = hid_env_minor ? 1 : 0;
     prm.mean = d_mean; prm.action = d_action; prm.logp = d_logp; prm.eps = d_eps;
     prm.seed = seed; prm.step = step; prm.std_ = std_; prm.log_std = std::log(std_); prm.explore = explore;
     // the ring as a 3-D tensor [24 slots][30 = agent x feature][n_pad envs] (innermost first); a tile is the box
@@ -752,6 +785,20 @@ int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int
         return pfail(p, FP_EINVAL, "fp_policy_gather_windows: bad arguments");
     cudaSetDevice(p->device);
     k_window_gather<<<grid_for(((n + 31) / 32) * POL_NA * 256), 256, 0, (cudaStream_t)stream>>>(d_ring, n_pad, slot, n, d_out, pitch, row0, cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+// Hidden states in the policy kernel's env-minor layout [5][64][n_pad] -> replay rows (last_hid / hid, 320 floats per env)
+int fp_policy_hidden_to_ring(FpPolicy* p, const float* d_hid_em, int64_t n_pad, int64_t n, float* d_field, int64_t row0, int64_t cap,
+                             void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!d_hid_em || !d_field || n < 1 || n_pad < n || row0 < 0 || cap < n || row0 >= cap) return pfail(p, FP_EINVAL, "fp_policy_hidden_to_ring: bad arguments");
+    cudaSetDevice(p->device);
+    const int rows = POL_NA * POL_HID;
+    k_em_gather<<<grid_for(((n + 31) / 32) * 256), 256, rows * 33 * sizeof(float), (cudaStream_t)stream>>>(d_hid_em, n_pad, rows, n, d_field, row0, cap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;

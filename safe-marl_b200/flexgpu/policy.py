@@ -97,10 +97,11 @@ class DevicePolicy:
         return b
 
     def act(self, ring, slot=None, n_envs=None, hid_in=None, reset=None, explore=True, eps=None, step=0, hid_out=None,
-            want_mean=False, want_logp=True):
+            want_mean=False, want_logp=True, hid_layout="rows"):
         """ring: an ObsRing (env.obs_ring() / step(..., return_obs='ring')) or a raw [24, 5, 6, n_pad] fp32 tensor with
-        `slot` / `n_envs`.  Returns (action [N,5,4], log_prob [N,5,4] or None, hid [N,5,64], mean or None); the output
-        tensors are reused by the next call unless hid_out is given."""
+        `slot` / `n_envs`.  Returns (action [N,5,4], log_prob [N,5,4] or None, hid, mean or None); the output
+        tensors are reused by the next call unless hid_out is given.  hid_layout: "rows" = [N, 5, 64] (the reference's
+        (b, n, hid)), "env_minor" = [5, 64, n_pad] (the kernel's native layout: coalesced accesses; hid_out required)."""
         if hasattr(ring, "ring"):
             slot, n_envs, ring = ring.slot, ring.env.n_envs, ring.ring
         n_pad = ring.shape[-1]
@@ -108,6 +109,10 @@ class DevicePolicy:
         action = self._buf("action", (N, N_AGENTS, ACT))
         logp = self._buf("logp", (N, N_AGENTS, ACT)) if want_logp else None
         mean = self._buf("mean", (N, N_AGENTS, ACT)) if want_mean else None
+        em = hid_layout == "env_minor"
+        if em and (hid_out is None or tuple(hid_out.shape) != (N_AGENTS, HID, n_pad) or
+                   (hid_in is not None and tuple(hid_in.shape) != (N_AGENTS, HID, n_pad))):
+            raise ValueError("env-minor hidden states are [5, 64, n_pad] tensors (hid_out required)")
         if hid_out is None:
             hid_out = self._buf("hid", (N, N_AGENTS, HID))
         if hid_in is not None and hid_in.data_ptr() == hid_out.data_ptr():
@@ -115,8 +120,8 @@ class DevicePolicy:
         r = None if reset is None else reset.to(device=self.device, dtype=torch.uint8).contiguous()
         e = None if eps is None else eps.to(device=self.device, dtype=torch.float32).contiguous()
         self._check(self._lib.fp_policy_act(self._p, _ptr(ring), int(slot), int(n_pad), N, _ptr(hid_in), _ptr(r), _ptr(hid_out),
-                                            _ptr(mean), _ptr(action), _ptr(logp), _ptr(e), self.seed, int(step), self.std,
-                                            1 if explore else 0, _stream()), "fp_policy_act")
+                                            1 if em else 0, _ptr(mean), _ptr(action), _ptr(logp), _ptr(e), self.seed, int(step),
+                                            self.std, 1 if explore else 0, _stream()), "fp_policy_act")
         return action, logp, hid_out, mean
 
     def gather_windows(self, ring, n, out, pitch, row0=0, cap=None):
@@ -142,7 +147,9 @@ class DeviceRollout:
             raise ValueError("replay must be a DeviceReplayBuffer(TRANSITION_FIELDS) holding at least record_envs rows")
         self.max_steps = int(max_steps)
         dev = env.device
-        self._hid = [torch.zeros(self.N, N_AGENTS, HID, device=dev), torch.zeros(self.N, N_AGENTS, HID, device=dev)]
+        self._n_pad = (self.N + 31) // 32 * 32                      # the observation ring's padding (fp_obs_ring)
+        # hidden states in the policy kernel's env-minor layout [5, 64, n_pad]; hidden() gives the reference's [N, 5, 64]
+        self._hid = [torch.zeros(N_AGENTS, HID, self._n_pad, device=dev), torch.zeros(N_AGENTS, HID, self._n_pad, device=dev)]
         self._cur = 0
         self._reset_mask = None
         self.t = 0                                  # step within the episode
@@ -169,27 +176,37 @@ class DeviceRollout:
         pol._check(pol._lib.fp_policy_rows_to_ring(pol._p, _ptr(src), self.R, w, self._fptr[name], pos, self.replay.size,
                                                    _stream()), "fp_policy_rows_to_ring")
 
+    def _hidden_rows(self, name, hid_em, pos):
+        pol = self.policy
+        pol._check(pol._lib.fp_policy_hidden_to_ring(pol._p, _ptr(hid_em), self._n_pad, self.R, self._fptr[name], pos, self.replay.size,
+                                                     _stream()), "fp_policy_hidden_to_ring")
+
+    def hidden(self):
+        """The current hidden state in the reference's layout [N, 5, 64] (a copy)."""
+        return self._hid[self._cur][:, :, :self.N].permute(2, 0, 1).contiguous()
+
     def step(self, explore=True, eps=None):
         if self.ring is None:
             self.reset()
         env, pol = self.env, self.policy
         last_hid, hid = self._hid[self._cur], self._hid[1 - self._cur]
         action, logp, hid, _ = pol.act(self.ring, hid_in=last_hid, reset=self._reset_mask, explore=explore, eps=eps,
-                                       step=self.total_steps, hid_out=hid)                         # model.py:215-216
+                                       step=self.total_steps, hid_out=hid, hid_layout="env_minor")  # model.py:215-216
         pos = None
         if self.R:
             pos = self.replay.reserve(self.R)
             pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
             if self._reset_mask is not None:       # a restarted env's last_hid is the zero state it acted from
-                last_hid = torch.where(self._reset_mask[:, None, None].bool(), torch.zeros_like(last_hid), last_hid)
-            self._rows("last_hid", last_hid, pos)
+                keep = torch.ones(self._n_pad, device=last_hid.device); keep[:self.N] = 1.0 - self._reset_mask.float()
+                last_hid = last_hid * keep
+            self._hidden_rows("last_hid", last_hid, pos)
         # translate_action (:218) + env.step (:220) + get_obs (:223) in one launch
         reward, done, info, self.ring = env.step(action, translate=True, want_info=False, return_obs="ring")
         self.t += 1
         self.total_steps += 1
         if self.R:
             pol.gather_windows(self.ring, self.R, self._fptr["next_state"], TRANSITION_FIELDS["next_state"], pos, self.replay.size)
-            self._rows("action", action, pos); self._rows("log_prob_a", logp, pos); self._rows("hid", hid, pos)
+            self._rows("action", action, pos); self._rows("log_prob_a", logp, pos); self._hidden_rows("hid", hid, pos)
             self._rows("value", self._zeros, pos); self._rows("next_value", self._zeros, pos)
             pol._check(pol._lib.fp_policy_scalars_to_ring(
                 pol._p, _ptr(reward), _ptr(done), self.R, 1 if self.t == self.max_steps else 0, self._fptr["reward"],

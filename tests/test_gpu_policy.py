@@ -76,6 +76,15 @@ def test_policy_rows_are_independent_and_ragged_sizes(gold, cuda):
             full = got
         else:
             assert np.array_equal(got[0], full[0][:n]) and np.array_equal(got[1], full[1][:n])
+    # the env-minor hidden-state layout [5, 64, n_pad] (the kernel's native one) gives the same bits
+    n = 160
+    ring = make_ring(obs, 5, cuda)
+    h_rows = torch.from_numpy(gold["t_hid0"]).to(cuda).contiguous()
+    h_em = torch.zeros(5, 64, 160, device=cuda); h_em[:, :, :n] = h_rows.permute(1, 2, 0)
+    out_em = torch.empty(5, 64, 160, device=cuda)
+    _, _, hid_em, mean_em = pol.act(ring, slot=5, n_envs=n, hid_in=h_em.contiguous(), explore=False, want_mean=True, hid_out=out_em,
+                                    hid_layout="env_minor")
+    assert np.array_equal(mean_em.cpu().numpy(), full[0]) and np.array_equal(hid_em[:, :, :n].permute(2, 0, 1).cpu().numpy(), full[1])
     # reset mask: the masked envs act from a zero hidden state
     n = 160
     ring = make_ring(obs, 5, cuda)
@@ -133,10 +142,10 @@ def test_rollout_writes_the_transition_fields(gold, cuda, small_env):
     steps = []
     for t in range(4):                                          # the fourth step wraps the FIFO
         pre = ro.ring.dense().clone()
-        last_hid = ro._hid[ro._cur].clone()
+        last_hid = ro.hidden()
         reward, done = ro.step()
         steps.append(dict(state=pre[:R].reshape(R, -1), next_state=ro.ring.dense()[:R].reshape(R, -1).clone(),
-                          last_hid=last_hid[:R].reshape(R, -1), hid=ro._hid[ro._cur][:R].reshape(R, -1).clone(),
+                          last_hid=last_hid[:R].reshape(R, -1), hid=ro.hidden()[:R].reshape(R, -1),
                           action=pol._bufs["action"][:R].reshape(R, -1).clone(), log_prob_a=pol._bufs["logp"][:R].reshape(R, -1).clone(),
                           reward=reward[:R, None].float().repeat(1, 5).clone(), done=done[:R, None].float().clone()))
     assert len(buf) == 3 * R + 50
@@ -167,7 +176,7 @@ def test_rollout_episode_boundary_resets_hidden_state(gold, cuda, profiles):
     _, _, _, mean_z = pol.act(ring, hid_in=None, explore=False, want_mean=True, hid_out=torch.empty(64, 5, 64, device=cuda))
     mean_z = mean_z.cpu().numpy().copy()
     _, _, _, mean_r = pol.act(ring, hid_in=ro._hid[ro._cur], reset=ro._reset_mask, explore=False, want_mean=True,
-                              hid_out=torch.empty(64, 5, 64, device=cuda))
+                              hid_out=torch.empty_like(ro._hid[ro._cur]), hid_layout="env_minor")
     assert np.array_equal(mean_z, mean_r.cpu().numpy())
     stats = env.episode_stats()
     assert float(stats["env_steps"]) == 64 * 95 and float(stats["episodes"]) == 64

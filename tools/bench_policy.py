@@ -16,7 +16,8 @@ sd = {"fc1.weight": rng.normal(0, 0.1, (64, 149)), "fc1.bias": rng.uniform(-0.08
 pol = DevicePolicy(sd, device=dev)
 n_pad = (E + 31) // 32 * 32
 ring = torch.rand(24, 5, 6, n_pad, device=dev)
-h = [torch.rand(E, 5, 64, device=dev) - 0.5, torch.empty(E, 5, 64, device=dev)]
+EM = bool(os.environ.get("HID_EM", "1") != "0")
+h = [torch.rand(5, 64, n_pad, device=dev) - 0.5, torch.empty(5, 64, n_pad, device=dev)] if EM else [torch.rand(E, 5, 64, device=dev) - 0.5, torch.empty(E, 5, 64, device=dev)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ts = []
 NOHID = bool(os.environ.get("NOHID")); NOFLUSH = bool(os.environ.get("NOFLUSH"))
@@ -24,7 +25,7 @@ for k in range(iters + 3):
     if not NOFLUSH:
         flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); pol.act(ring, slot=k % 24, n_envs=E, hid_in=None if NOHID else h[k % 2], hid_out=h[1 - k % 2], step=k); b.record()
+    a.record(); pol.act(ring, slot=k % 24, n_envs=E, hid_in=None if NOHID else h[k % 2], hid_out=h[1 - k % 2], step=k, hid_layout="env_minor" if EM else "rows"); b.record()
     torch.cuda.synchronize()
     if k >= 3:
         ts.append(a.elapsed_time(b) * 1e3)
