@@ -518,13 +518,15 @@ __global__ void __launch_bounds__(256) k_window_gather(const float* __restrict__
 // env-minor [rows][n_pad] (rows = 5 agents x 64 units) -> ring rows (row0 + e) mod cap of `rows` contiguous floats:
 // the hidden states of the Transition (last_hid / hid, (1, 5, 64) per env) from the policy kernel's native layout
 __global__ void __launch_bounds__(256) k_em_gather(const float* __restrict__ src, int64_t n_pad, int rows, int64_t n,
-                                                   float* __restrict__ out, int64_t row0, int64_t cap) {
+                                                   float* __restrict__ out, int64_t row0, int64_t cap,
+                                                   const uint8_t* __restrict__ zero_mask) {
     extern __shared__ float tbuf[];                               // [rows][33]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t n_blk = (n + 31) >> 5;
     for (int64_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
         const int64_t e0 = blk << 5;
-        for (int k = w; k < rows; k += 8) tbuf[k * 33 + lane] = (e0 + lane < n) ? src[(int64_t)k * n_pad + e0 + lane] : 0.0f;
+        const bool take = (e0 + lane < n) && (zero_mask == nullptr || zero_mask[e0 + lane] == 0);
+        for (int k = w; k < rows; k += 8) tbuf[k * 33 + lane] = take ? src[(int64_t)k * n_pad + e0 + lane] : 0.0f;
         __syncthreads();
         for (int j = w; j < 32; j += 8) {
             if (e0 + j < n) {
@@ -791,14 +793,15 @@ int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int
     return FP_OK;
 }
 
-// Hidden states in the policy kernel's env-minor layout [5][64][n_pad] -> replay rows (last_hid / hid, 320 floats per env)
+// Hidden states in the policy kernel's env-minor layout [5][64][n_pad] -> replay rows (last_hid / hid, 320 floats per env);
+// d_zero_mask (may be null): envs whose row is written as zeros (a restarted env's last_hid is the zero state it acted from)
 int fp_policy_hidden_to_ring(FpPolicy* p, const float* d_hid_em, int64_t n_pad, int64_t n, float* d_field, int64_t row0, int64_t cap,
-                             void* stream) {
+                             const uint8_t* d_zero_mask, void* stream) {
     if (!p) return FP_EINVAL;
     if (!d_hid_em || !d_field || n < 1 || n_pad < n || row0 < 0 || cap < n || row0 >= cap) return pfail(p, FP_EINVAL, "fp_policy_hidden_to_ring: bad arguments");
     cudaSetDevice(p->device);
     const int rows = POL_NA * POL_HID;
-    k_em_gather<<<grid_for(((n + 31) / 32) * 256), 256, rows * 33 * sizeof(float), (cudaStream_t)stream>>>(d_hid_em, n_pad, rows, n, d_field, row0, cap);
+    k_em_gather<<<grid_for(((n + 31) / 32) * 256), 256, rows * 33 * sizeof(float), (cudaStream_t)stream>>>(d_hid_em, n_pad, rows, n, d_field, row0, cap, d_zero_mask);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;

@@ -232,22 +232,27 @@ class BatchedFlexProvisionEnv:
 
     RESET_RETRIES = 3        # redraws of an env whose initial power flow fails (the reference loops until solvable, :82-153)
 
-    def reset(self, start_index=None, e0=None, a0=None, mask=None, return_obs=True, check=False):
+    def reset(self, start_index=None, e0=None, a0=None, mask=None, return_obs=True, check=False, retries=None):
         """Replaces reset()/manual_reset() (:74-155, :157-239).
 
         With no draws given, each env draws (start row, E0, a0) from its own Philox stream
         keyed by (seed, env_offset + e, episode counter).  Envs whose initial power flow fails
         are re-drawn up to RESET_RETRIES times like the reference's `while not solvable` loop (:82-153) -- on the
         device, without a host round trip.  An env that still fails keeps FP_FLAG_RESET_FAILED in `flags`
-        (`reset_failed_count()` reads the count); check=True synchronises and raises FlexGpuError instead.
+        (`reset_failed_count()` reads the count); check=True synchronises and raises FlexGpuError instead;
+        `retries` overrides RESET_RETRIES (0: a single launch, for per-step auto-resets).
         A reset restarts the observation history of the envs it resets: a window returned earlier by
         get_obs() / step(return_obs=...) no longer holds their previous episode -- copy `next_obs` before resetting."""
         m = self._dev(mask, torch.uint8)
         if start_index is None:
             if self._reset_failed is None:
                 self._reset_failed = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._check(self._lib.fp_reset_random_retry(self._h, self.seed, self.env_offset, _ptr(m), self.RESET_RETRIES,
-                                                        _ptr(self._reset_failed), _stream()), "fp_reset_random_retry")
+            n_retry = self.RESET_RETRIES if retries is None else int(retries)
+            if n_retry == 0 and not check:         # per-step auto-reset: one launch, no failure count
+                self._check(self._lib.fp_reset_random(self._h, self.seed, self.env_offset, _ptr(m), _stream()), "fp_reset_random")
+            else:
+                self._check(self._lib.fp_reset_random_retry(self._h, self.seed, self.env_offset, _ptr(m), n_retry,
+                                                            _ptr(self._reset_failed), _stream()), "fp_reset_random_retry")
             if check and int(self._reset_failed.item()):
                 raise _lib.FlexGpuError(f"{int(self._reset_failed.item())} envs found no solvable initial state in "
                                         f"{self.RESET_RETRIES + 1} draws")

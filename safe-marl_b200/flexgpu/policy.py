@@ -137,21 +137,27 @@ class DeviceRollout:
     fields of the first `record_envs` envs into `replay` (a DeviceReplayBuffer with TRANSITION_FIELDS).  value /
     next_value are stored as zeros: MADDPG's losses recompute both from the critic (maddpg.py:104-107) and never read
     them.  Episodes end together (95 steps, quirk Q1): the finished envs are reset from their Philox streams and their
-    hidden state restarts at zero (init_hidden, model.py:211)."""
+    hidden state restarts at zero (init_hidden, model.py:211).  An env can also terminate EARLY (solver failure,
+    :314-337): with reset_done_each_step=True every step is followed by a masked reset of the envs it finished -- three
+    small launches (~55 us at 131 072 envs), no host round trip -- exactly as the reference ends that env's episode and
+    starts a new one; without it (the default: failures do not occur on feasible profiles) such an env pays its -200,
+    is flagged done / last_step in its Transition, and keeps stepping until the batch's common reset."""
 
-    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240):
+    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240, reset_done_each_step=False):
         self.env, self.policy, self.replay = env, policy, replay
         self.N = env.n_envs
         self.R = 0 if replay is None else int(self.N if record_envs is None else min(record_envs, self.N))
         if replay is not None and (dict(replay.fields) != TRANSITION_FIELDS or self.R > replay.size):
             raise ValueError("replay must be a DeviceReplayBuffer(TRANSITION_FIELDS) holding at least record_envs rows")
         self.max_steps = int(max_steps)
+        self.reset_done_each_step = bool(reset_done_each_step)
         dev = env.device
         self._n_pad = (self.N + 31) // 32 * 32                      # the observation ring's padding (fp_obs_ring)
         # hidden states in the policy kernel's env-minor layout [5, 64, n_pad]; hidden() gives the reference's [N, 5, 64]
         self._hid = [torch.zeros(N_AGENTS, HID, self._n_pad, device=dev), torch.zeros(N_AGENTS, HID, self._n_pad, device=dev)]
         self._cur = 0
         self._reset_mask = None
+        self._done_mask = None
         self.t = 0                                  # step within the episode
         self.total_steps = 0
         self.ring = None
@@ -176,10 +182,10 @@ class DeviceRollout:
         pol._check(pol._lib.fp_policy_rows_to_ring(pol._p, _ptr(src), self.R, w, self._fptr[name], pos, self.replay.size,
                                                    _stream()), "fp_policy_rows_to_ring")
 
-    def _hidden_rows(self, name, hid_em, pos):
+    def _hidden_rows(self, name, hid_em, pos, zero_mask=None):
         pol = self.policy
         pol._check(pol._lib.fp_policy_hidden_to_ring(pol._p, _ptr(hid_em), self._n_pad, self.R, self._fptr[name], pos, self.replay.size,
-                                                     _stream()), "fp_policy_hidden_to_ring")
+                                                     _ptr(zero_mask), _stream()), "fp_policy_hidden_to_ring")
 
     def hidden(self):
         """The current hidden state in the reference's layout [N, 5, 64] (a copy)."""
@@ -196,10 +202,7 @@ class DeviceRollout:
         if self.R:
             pos = self.replay.reserve(self.R)
             pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
-            if self._reset_mask is not None:       # a restarted env's last_hid is the zero state it acted from
-                keep = torch.ones(self._n_pad, device=last_hid.device); keep[:self.N] = 1.0 - self._reset_mask.float()
-                last_hid = last_hid * keep
-            self._hidden_rows("last_hid", last_hid, pos)
+            self._hidden_rows("last_hid", last_hid, pos, self._reset_mask)     # a restarted env's last_hid is the zero state it acted from
         # translate_action (:218) + env.step (:220) + get_obs (:223) in one launch
         reward, done, info, self.ring = env.step(action, translate=True, want_info=False, return_obs="ring")
         self.t += 1
@@ -219,6 +222,12 @@ class DeviceRollout:
             self.ring = env.reset(mask=mask, return_obs="ring")
             self._reset_mask = mask.clone()
             self.t = 0
+        elif self.reset_done_each_step:                                         # early terminations (solver failure): their own new episode
+            if self._done_mask is None:
+                self._done_mask = torch.empty(self.N, dtype=torch.uint8, device=done.device)
+            self._done_mask.copy_(done)
+            self.ring = env.reset(mask=self._done_mask, return_obs="ring", retries=0)
+            self._reset_mask = self._done_mask
         return reward, done
 
 

@@ -251,3 +251,37 @@ def test_rollout_matches_reference_train_process(cuda):
     # 'mean_train_reward' slot as the step's reward (model.py:247-252), then the sum is divided by t + 1 (:261-264)
     assert abs(2.0 * np.sum(rewards) / T - float(g["mean_train_reward"])) < 1e-6 * abs(float(g["mean_train_reward"]))
     pol.close(); buf.close(); env.close()
+
+
+def test_rollout_resets_early_terminations_each_step(gold, cuda, profiles):
+    """An env whose power flow fails terminates there (:314-337): the reference ends its episode and starts a new one with a
+    zero hidden state.  The device loop does the same with a masked reset after the step (no host round trip)."""
+    from flexgpu import BatchedFlexProvisionEnv
+    from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS
+    from flexgpu.predictor import DeviceReplayBuffer
+    n = 96
+    env = BatchedFlexProvisionEnv(None, n_envs=n, device=cuda, profiles=profiles, seed=6)
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda, seed=5)
+    buf = DeviceReplayBuffer(8 * n, TRANSITION_FIELDS, device=cuda)
+    ro = DeviceRollout(env, pol, replay=buf, reset_done_each_step=True)
+    ro.reset()
+    for _ in range(3):
+        ro.step()
+    fail = torch.zeros(n, dtype=torch.uint8, device=cuda); fail[5] = 1; fail[40] = 1
+    env.inject_failure(fail)
+    reward, done = ro.step()                                     # step 4: envs 5 and 40 fail -> -200, terminated, reset
+    env.inject_failure(None)
+    assert done[5] and done[40] and int(done.sum()) == 2 and float(reward[5]) < -199.0
+    steps = env.steps.cpu().numpy()
+    assert steps[5] == 1 and steps[40] == 1 and (np.delete(steps, [5, 40]) == 5).all()
+    hid_before = ro.hidden().clone()
+    ro.step()                                                    # step 5 of the others, step 1 of the two new episodes
+    got = buf.get_batch(n, start=len(buf) - n)                   # the transitions of that step
+    lh = got["last_hid"].view(n, 5, 64)
+    assert bool((lh[5] == 0).all()) and bool((lh[40] == 0).all())                     # they acted from init_hidden
+    keep = [i for i in range(n) if i not in (5, 40)]
+    assert torch.equal(lh[keep], hid_before[keep])
+    prev = buf.get_batch(n, start=len(buf) - 2 * n)              # the failing step's transitions: done and last_step set
+    assert float(prev["done"][5]) == 1.0 and float(prev["last_step"][40]) == 1.0 and float(prev["done"][6]) == 0.0
+    assert int(env.steps[5]) == 2 and int(env.steps[6]) == 6
+    pol.close(); buf.close(); env.close()
