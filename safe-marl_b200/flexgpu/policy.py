@@ -143,7 +143,7 @@ class DeviceRollout:
     starts a new one; without it (the default: failures do not occur on feasible profiles) such an env pays its -200,
     is flagged done / last_step in its Transition, and keeps stepping until the batch's common reset."""
 
-    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240, reset_done_each_step=False):
+    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240, reset_done_each_step=False, value_fn=None):
         self.env, self.policy, self.replay = env, policy, replay
         self.N = env.n_envs
         self.R = 0 if replay is None else int(self.N if record_envs is None else min(record_envs, self.N))
@@ -151,6 +151,11 @@ class DeviceRollout:
             raise ValueError("replay must be a DeviceReplayBuffer(TRANSITION_FIELDS) holding at least record_envs rows")
         self.max_steps = int(max_steps)
         self.reset_done_each_step = bool(reset_done_each_step)
+        # value_fn(obs [R, 5, 144], action [R, 5, 4]) -> [R, 5, 1]: the critic (e.g. behaviour_net.value, maddpg.py:29-76).  When
+        # given, the Transition's value / next_value are filled as train_process does (model.py:217, :225-226: the critic on
+        # (state, action) and on (next_state, a SECOND sampled action from the policy with the new hidden state)); the learner's
+        # module runs in torch -- it is not part of this library -- and the second policy evaluation doubles k_policy's cost.
+        self.value_fn = value_fn
         dev = env.device
         self._n_pad = (self.N + 31) // 32 * 32                      # the observation ring's padding (fp_obs_ring)
         # hidden states in the policy kernel's env-minor layout [5, 64, n_pad]; hidden() gives the reference's [N, 5, 64]
@@ -168,6 +173,9 @@ class DeviceRollout:
                 replay._check(replay._lib.fp_replay_field_ptr(replay._r, i, C.byref(p)), "fp_replay_field_ptr")
                 self._fptr[k] = p
             self._zeros = torch.zeros(self.R, N_AGENTS, device=dev)
+            if value_fn is not None:
+                self._dense = torch.empty(self.R, N_AGENTS * OBS, device=dev)
+                self._hid_scratch = torch.empty(N_AGENTS, HID, self._n_pad, device=dev)
 
     def reset(self):
         self.ring = self.env.reset(return_obs="ring")              # state, _ = env.reset() (model.py:208)
@@ -191,7 +199,11 @@ class DeviceRollout:
         """The current hidden state in the reference's layout [N, 5, 64] (a copy)."""
         return self._hid[self._cur][:, :, :self.N].permute(2, 0, 1).contiguous()
 
-    def step(self, explore=True, eps=None):
+    def _dense_obs(self):
+        self.policy.gather_windows(self.ring, self.R, self._dense, N_AGENTS * OBS, 0, self.R)
+        return self._dense.view(self.R, N_AGENTS, OBS)
+
+    def step(self, explore=True, eps=None, eps_next=None):
         if self.ring is None:
             self.reset()
         env, pol = self.env, self.policy
@@ -203,6 +215,10 @@ class DeviceRollout:
             pos = self.replay.reserve(self.R)
             pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
             self._hidden_rows("last_hid", last_hid, pos, self._reset_mask)     # a restarted env's last_hid is the zero state it acted from
+            if self.value_fn is not None:                                      # value = critic(state, action) (model.py:217)
+                with torch.no_grad():
+                    v = self.value_fn(self._dense_obs(), action[:self.R])
+                self._rows("value", v.reshape(self.R, N_AGENTS).float().contiguous(), pos)
         # translate_action (:218) + env.step (:220) + get_obs (:223) in one launch
         reward, done, info, self.ring = env.step(action, translate=True, want_info=False, return_obs="ring")
         self.t += 1
@@ -210,7 +226,14 @@ class DeviceRollout:
         if self.R:
             pol.gather_windows(self.ring, self.R, self._fptr["next_state"], TRANSITION_FIELDS["next_state"], pos, self.replay.size)
             self._rows("action", action, pos); self._rows("log_prob_a", logp, pos); self._hidden_rows("hid", hid, pos)
-            self._rows("value", self._zeros, pos); self._rows("next_value", self._zeros, pos)
+            if self.value_fn is None:
+                self._rows("value", self._zeros, pos); self._rows("next_value", self._zeros, pos)
+            else:       # next_value = critic(next_state, a second sampled action from the new hidden state) (model.py:225-226)
+                a2, _, _, _ = pol.act(self.ring, hid_in=hid, explore=explore, eps=eps_next, step=(1 << 40) + self.total_steps,
+                                      hid_out=self._hid_scratch, hid_layout="env_minor", want_logp=False)
+                with torch.no_grad():
+                    nv = self.value_fn(self._dense_obs(), a2[:self.R])
+                self._rows("next_value", nv.reshape(self.R, N_AGENTS).float().contiguous(), pos)
             pol._check(pol._lib.fp_policy_scalars_to_ring(
                 pol._p, _ptr(reward), _ptr(done), self.R, 1 if self.t == self.max_steps else 0, self._fptr["reward"],
                 self._fptr["done"], self._fptr["last_step"], self._fptr["action_avail"], pos, self.replay.size, _stream()),
@@ -293,3 +316,13 @@ def smoke(env, device):
     ro.step()
     pol.close()
     return err
+
+
+def critic_input(policy, state, action):
+    """The MADDPG critic's input rows (maddpg.py:29-66) for dense observations [B, 5, 144] and actions [B, 5, 4]:
+    [B * 5, 745] = all agents' observations | one-hot agent id | all agents' actions."""
+    B = state.shape[0]
+    st = state.reshape(B, N_AGENTS * OBS).contiguous(); ac = action.reshape(B, N_AGENTS * ACT).float().contiguous()
+    out = torch.empty(B * N_AGENTS, N_AGENTS * OBS + N_AGENTS + N_AGENTS * ACT, device=st.device)
+    policy._check(policy._lib.fp_learner_feed(policy._p, _ptr(st), _ptr(ac), None, B, _ptr(out), None, _stream()), "fp_learner_feed")
+    return out

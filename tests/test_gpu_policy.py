@@ -225,7 +225,20 @@ def test_rollout_matches_reference_train_process(cuda):
     env = BatchedFlexProvisionEnv(None, n_envs=1, device=cuda, profiles=Profiles(g["P"], g["Q"], g["PV"], g["price"]))
     pol = DevicePolicy({k: g["w_" + k] for k in KEYS}, device=cuda, std=1.0)
     buf = DeviceReplayBuffer(64, TRANSITION_FIELDS, device=cuda)
-    ro = DeviceRollout(env, pol, replay=buf, max_steps=T)
+    # the critic (madrl/critics/mlp_critic.py::MLPCritic, as MADDPG.value feeds it, maddpg.py:29-76) in plain torch on the
+    # library's critic-input rows: fills the Transition's value / next_value like model.py:217, :225-226
+    from flexgpu.policy import critic_input
+    wc = {k[3:]: torch.from_numpy(g[k]).to(cuda) for k in g.files if k.startswith("wc_")}
+    F = torch.nn.functional
+
+    def value_fn(obs, act):
+        x = F.linear(critic_input(pol, obs, act), wc["fc1.weight"], wc["fc1.bias"])
+        x = torch.relu(F.layer_norm(x, (64,), wc["layernorm.weight"], wc["layernorm.bias"], 1e-5))
+        h = torch.relu(F.linear(x, wc["fc2.weight"], wc["fc2.bias"]))
+        return F.linear(h, wc["fc3.weight"], wc["fc3.bias"]).view(obs.shape[0], 5, 1)
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ro = DeviceRollout(env, pol, replay=buf, max_steps=T, value_fn=value_fn)
     env.reset([0], g["e0"][None], g["a0"][None], return_obs=False)          # trainer.env.reset() (model.py:208) with the reference's draws
     assert np.max(np.abs(env.voltages[0].cpu().numpy() - g["V0"])) < 1e-8
     env._check(env._lib.fp_obs_ring_reset_push(env._h, None, None), "fp_obs_ring_reset_push")    # the get_obs inside reset() (:155)
@@ -233,11 +246,13 @@ def test_rollout_matches_reference_train_process(cuda):
     ro._hid[ro._cur].zero_()
     rewards = []
     for t in range(T):
-        reward, done = ro.step(eps=torch.from_numpy(g["eps"][2 * t][None].astype(np.float32)))   # draw 2t + 1 feeds next_value only
+        reward, done = ro.step(eps=torch.from_numpy(g["eps"][2 * t][None].astype(np.float32)),
+                               eps_next=torch.from_numpy(g["eps"][2 * t + 1][None].astype(np.float32)))   # draw 2t + 1: the next-value action
         rewards.append(float(reward[0]))
     got = {k: v.cpu().numpy().astype(np.float64) for k, v in buf.get_batch(T, start=0).items()}
+    torch.backends.cuda.matmul.allow_tf32 = prev_tf32
     tol = dict(state=2e-6, next_state=2e-6, action=5e-6, log_prob_a=2e-4, reward=None, done=0, last_step=0, action_avail=0,
-               last_hid=5e-6, hid=5e-6)
+               last_hid=5e-6, hid=5e-6, value=2e-5, next_value=2e-5)
     for k, bound in tol.items():
         want = g["tr_" + k]
         assert got[k].shape == want.shape, k
