@@ -346,7 +346,10 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
  *                              (pitch = floats per destination row, >= 720; row0 = 0, cap >= n: a dense tensor)
  *   fp_policy_rows_to_ring     any dense [n][width] fp32 array (action, log_prob_a, last_hid, hid, value ...)
  *   fp_policy_scalars_to_ring  reward repeated per agent (model.py:221), done, last_step (= done, or every env when
- *                              last_step_all: t == max_steps - 1, model.py:229), all-ones action_avail; NULL fields skipped */
+ *                              last_step_all: t == max_steps - 1, model.py:229), all-ones action_avail; NULL fields skipped
+ *   fp_policy_transition_tail  ONE launch for all the small fields of a step (model.py:230-242): action, log_prob_a (NULL:
+ *                              skipped), reward per agent, done, last_step, action_avail (NULL: skipped) and -- zero_values
+ *                              != 0 -- value / next_value as zeros (MADDPG's losses recompute both, maddpg.py:104-107) */
 int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n, float* d_out,
                              int64_t pitch, int64_t row0, int64_t cap, void* stream);
 int fp_policy_hidden_to_ring(FpPolicy* p, const float* d_hid_em, int64_t n_pad, int64_t n, float* d_field, int64_t row0,
@@ -356,6 +359,10 @@ int fp_policy_rows_to_ring(FpPolicy* p, const float* d_src, int64_t n, int32_t w
 int fp_policy_scalars_to_ring(FpPolicy* p, const double* d_reward, const uint8_t* d_done, int64_t n, int32_t last_step_all,
                               float* f_reward, float* f_done, float* f_last, float* f_avail, int64_t row0, int64_t cap,
                               void* stream);
+int fp_policy_transition_tail(FpPolicy* p, const float* d_action, const float* d_logp, const double* d_reward,
+                              const uint8_t* d_done, int64_t n, int32_t last_step_all, int32_t zero_values, float* f_action,
+                              float* f_logp, float* f_value, float* f_next_value, float* f_reward, float* f_done, float* f_last,
+                              float* f_avail, int64_t row0, int64_t cap, void* stream);
 /* Learner feed: the device part of unpack_data (model.py:308-323) on a batch sampled with fp_replay_sample.
  * d_critic_in [batch * 5][745] = the MADDPG critic's input rows (maddpg.py:29-66: all agents' observations, one-hot
  * agent id, all agents' actions); d_reward_norm [batch][5] = reward_normalisation (BatchNorm1d over the batch, training

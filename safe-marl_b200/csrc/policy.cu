@@ -484,57 +484,94 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
 }
 
 // ---------------------------------------------------------------------------- transitions -> replay ring, learner feed
-// Pure data movement.
+// Pure data movement.  The sources are env-minor ([row][n_pad]: the observation ring, the hidden states), the replay
+// fields env-major ([transition][width]): a transposition through shared memory in tiles of GT_ENVS = 128 envs, so that
+// both sides move >= 512 contiguous bytes per row (a 32-env tile reads 128-byte pieces 512 KB apart: 2.8 TB/s; this one
+// reads 512-byte pieces).  Tile [KR rows][129] floats (odd stride: both the row-wise fill and the column-wise drain are
+// conflict-free); the fill issues all of a thread's loads before the first store.
+constexpr int GT_ENVS = 128, GT_STRIDE = GT_ENVS + 1;
+
+template <int KR, class RowOf>
+__device__ __forceinline__ void gt_fill(float* t, const float* __restrict__ src, int64_t n_pad, int64_t e0, int64_t n, RowOf row_of,
+                                        const uint8_t* __restrict__ zero_mask) {
+    static_assert(KR % 16 == 0, "rows per tile: two batches of KR / 16 rows per warp");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    bool take[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t e = e0 + lane + 32 * i;
+        take[i] = (e < n) && (zero_mask == nullptr || zero_mask[e] == 0);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float v[KR / 16][4];
+#pragma unroll
+        for (int m = 0; m < KR / 16; ++m) {
+            const int k = w + 8 * (m + half * (KR / 16));
+            const float* sp = src + (int64_t)row_of(k) * n_pad + e0 + lane;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[m][i] = take[i] ? __ldg(sp + 32 * i) : 0.0f;
+        }
+#pragma unroll
+        for (int m = 0; m < KR / 16; ++m) {
+            const int k = w + 8 * (m + half * (KR / 16));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[k * GT_STRIDE + lane + 32 * i] = v[m][i];
+        }
+    }
+}
+// rows (row0 + e) mod cap of the field, columns [col0, col0 + KR) of a row of `pitch` floats
+template <int KR>
+__device__ __forceinline__ void gt_drain(const float* t, float* __restrict__ out, int64_t pitch, int col0, int64_t e0, int64_t n,
+                                         int64_t row0, int64_t cap) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int j = w; j < GT_ENVS; j += 8) {
+        if (e0 + j < n) {
+            int64_t orow = row0 + e0 + j; orow = orow >= cap ? orow - cap : orow;
+            float* dst = out + orow * pitch + col0;
+#pragma unroll
+            for (int k = lane; k < KR; k += 32) dst[k] = t[k * GT_STRIDE + j];
+        }
+    }
+}
+
 //   k_window_gather   dense observation windows [n][5][144] (oldest entry first: get_obs, :387-401) of envs [0, n) from
 //                     the env-minor ring into rows of pitch `pitch` floats (a replay field, or a dense tensor)
 __global__ void __launch_bounds__(256) k_window_gather(const float* __restrict__ ring, int64_t n_pad, int slot, int64_t n,
                                                        float* __restrict__ out, int64_t pitch, int64_t row0, int64_t cap) {
-    // block = (32 envs, one agent): the 144 x 32 block is read row by row (128-byte lines), transposed through shared
-    // memory and written as 32 rows of 144 contiguous floats (whole 32-byte sectors: a 24-byte scatter per history
-    // entry would cost a DRAM read-modify-write per store)
-    __shared__ float t[POL_OBS][33];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t n_blk = (n + 31) >> 5;
+    extern __shared__ float gt_tile[];                            // [144][129]
+    const int64_t n_blk = (n + GT_ENVS - 1) / GT_ENVS;
     for (int64_t blk = blockIdx.x; blk < n_blk * POL_NA; blk += gridDim.x) {
         const int a = (int)(blk % POL_NA);
-        const int64_t e0 = (blk / POL_NA) << 5;
-        for (int k = w; k < POL_OBS; k += 8) {                    // k = r * 6 + f: r-th oldest entry lives in ring slot (slot + 1 + r) mod 24
+        const int64_t e0 = (blk / POL_NA) * GT_ENVS;
+        // k = r * 6 + f: the r-th oldest entry lives in ring slot (slot + 1 + r) mod 24
+        gt_fill<POL_OBS>(gt_tile, ring, n_pad, e0, n, [&](int k) {
             const int r = k / POL_F, f = k - r * POL_F;
-            const int s = (slot + 1 + r) % POL_H;
-            t[k][lane] = (e0 + lane < n) ? ring[((int64_t)(s * POL_NA + a) * POL_F + f) * n_pad + e0 + lane] : 0.0f;
-        }
+            int s = slot + 1 + r; s = s >= POL_H ? s - POL_H : s;
+            return (s * POL_NA + a) * POL_F + f;
+        }, nullptr);
         __syncthreads();
-        for (int j = w; j < 32; j += 8) {
-            if (e0 + j < n) {
-                int64_t orow = row0 + e0 + j; orow = orow >= cap ? orow - cap : orow;
-                float* dst = out + orow * pitch + a * POL_OBS;
-                for (int k = lane; k < POL_OBS; k += 32) dst[k] = t[k][j];
-            }
-        }
+        gt_drain<POL_OBS>(gt_tile, out, pitch, a * POL_OBS, e0, n, row0, cap);
         __syncthreads();
     }
 }
 
-// env-minor [rows][n_pad] (rows = 5 agents x 64 units) -> ring rows (row0 + e) mod cap of `rows` contiguous floats:
-// the hidden states of the Transition (last_hid / hid, (1, 5, 64) per env) from the policy kernel's native layout
-__global__ void __launch_bounds__(256) k_em_gather(const float* __restrict__ src, int64_t n_pad, int rows, int64_t n,
+// env-minor [320 = 5 agents x 64 units][n_pad] -> ring rows (row0 + e) mod cap of 320 contiguous floats: the hidden
+// states of the Transition (last_hid / hid, (1, 5, 64) per env) from the policy kernel's native layout; a tile is
+// (128 envs, one half of the 320 rows)
+constexpr int EM_ROWS = POL_NA * POL_HID, EM_KR = EM_ROWS / 2;
+__global__ void __launch_bounds__(256) k_em_gather(const float* __restrict__ src, int64_t n_pad, int64_t n,
                                                    float* __restrict__ out, int64_t row0, int64_t cap,
                                                    const uint8_t* __restrict__ zero_mask) {
-    extern __shared__ float tbuf[];                               // [rows][33]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t n_blk = (n + 31) >> 5;
-    for (int64_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
-        const int64_t e0 = blk << 5;
-        const bool take = (e0 + lane < n) && (zero_mask == nullptr || zero_mask[e0 + lane] == 0);
-        for (int k = w; k < rows; k += 8) tbuf[k * 33 + lane] = take ? src[(int64_t)k * n_pad + e0 + lane] : 0.0f;
+    extern __shared__ float gt_tile[];                            // [160][129]
+    const int64_t n_blk = (n + GT_ENVS - 1) / GT_ENVS;
+    for (int64_t blk = blockIdx.x; blk < n_blk * 2; blk += gridDim.x) {
+        const int h = (int)(blk & 1);
+        const int64_t e0 = (blk >> 1) * GT_ENVS;
+        gt_fill<EM_KR>(gt_tile, src, n_pad, e0, n, [&](int k) { return h * EM_KR + k; }, zero_mask);
         __syncthreads();
-        for (int j = w; j < 32; j += 8) {
-            if (e0 + j < n) {
-                int64_t orow = row0 + e0 + j; orow = orow >= cap ? orow - cap : orow;
-                float* dst = out + orow * rows;
-                for (int k = lane; k < rows; k += 32) dst[k] = tbuf[k * 33 + j];
-            }
-        }
+        gt_drain<EM_KR>(gt_tile, out, EM_ROWS, h * EM_KR, e0, n, row0, cap);
         __syncthreads();
     }
 }
@@ -566,6 +603,31 @@ __global__ void k_scalars_to_ring(const double* __restrict__ reward, const uint8
 #pragma unroll
             for (int j = 0; j < POL_NA * POL_ACT; ++j) f_avail[o * (POL_NA * POL_ACT) + j] = 1.0f;
         }
+    }
+}
+
+// The small Transition fields of n envs in ONE launch (model.py:221, :229-242): action / log_prob_a rows, reward repeated per
+// agent, done, last_step (= done, or every env when last_step_all), all-ones action_avail, and -- zero_values -- value /
+// next_value as zeros (MADDPG's losses recompute both).  Thread = (env, column of the 20-wide rows): coalesced throughout.
+__global__ void k_transition_tail(const float* __restrict__ action, const float* __restrict__ logp, const double* __restrict__ reward,
+                                  const uint8_t* __restrict__ done, int64_t n, int last_step_all, int zero_values,
+                                  float* __restrict__ f_action, float* __restrict__ f_logp, float* __restrict__ f_value,
+                                  float* __restrict__ f_next_value, float* __restrict__ f_reward, float* __restrict__ f_done,
+                                  float* __restrict__ f_last, float* __restrict__ f_avail, int64_t row0, int64_t cap) {
+    constexpr int W = POL_NA * POL_ACT;
+    const int64_t total = n * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / W;
+        const int c = (int)(i - e * W);
+        int64_t o = row0 + e; o = o >= cap ? o - cap : o;
+        f_action[o * W + c] = action[i];
+        if (f_logp) f_logp[o * W + c] = logp[i];
+        if (f_avail) f_avail[o * W + c] = 1.0f;
+        if (c < POL_NA) {
+            f_reward[o * POL_NA + c] = (float)reward[e];
+            if (zero_values) { f_value[o * POL_NA + c] = 0.0f; f_next_value[o * POL_NA + c] = 0.0f; }
+        }
+        if (c == POL_NA) { const bool d = done[e] != 0; f_done[o] = d ? 1.0f : 0.0f; f_last[o] = (d || last_step_all) ? 1.0f : 0.0f; }
     }
 }
 
@@ -611,6 +673,14 @@ int grid_for(int64_t total) {
     return (int)(g > 148 * 16 ? 148 * 16 : g);
 }
 
+int gt_grid(int64_t tiles, int per_sm) {       // persistent grid of the transposing gathers: per_sm CTAs per SM
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t g = (int64_t)sms * per_sm;
+    return (int)(tiles < g ? (tiles < 1 ? 1 : tiles) : g);
+}
+
 float round_tf32(float x) {                    // round to nearest even on the 13 dropped mantissa bits
     uint32_t u; std::memcpy(&u, &x, 4);
     if ((u & 0x7F800000u) == 0x7F800000u) return x;
@@ -625,6 +695,7 @@ float round_tf32(float x) {                    // round to nearest even on the 1
 struct FpPolicy {
     int device = 0;
     int loaded = 0;
+    int attr_window = 0, attr_hidden = 0;          // opt-in shared-memory sizes of the gather kernels set on this handle's device
     float* d_W1rot = nullptr; float* d_Wg = nullptr; float* d_vec = nullptr;
     int64_t launches = 0;
     std::string err;
@@ -786,7 +857,9 @@ int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int
     if (!d_ring || !d_out || n < 1 || pitch < POL_NA * POL_OBS || row0 < 0 || cap < n || row0 >= cap || slot < 0 || slot >= POL_H)
         return pfail(p, FP_EINVAL, "fp_policy_gather_windows: bad arguments");
     cudaSetDevice(p->device);
-    k_window_gather<<<grid_for(((n + 31) / 32) * POL_NA * 256), 256, 0, (cudaStream_t)stream>>>(d_ring, n_pad, slot, n, d_out, pitch, row0, cap);
+    constexpr int smem_w = POL_OBS * GT_STRIDE * (int)sizeof(float);
+    if (!p->attr_window) { cudaFuncSetAttribute(k_window_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w); p->attr_window = 1; }
+    k_window_gather<<<gt_grid(((n + GT_ENVS - 1) / GT_ENVS) * POL_NA, 3), 256, smem_w, (cudaStream_t)stream>>>(d_ring, n_pad, slot, n, d_out, pitch, row0, cap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;
@@ -800,8 +873,9 @@ int fp_policy_hidden_to_ring(FpPolicy* p, const float* d_hid_em, int64_t n_pad, 
     if (!p) return FP_EINVAL;
     if (!d_hid_em || !d_field || n < 1 || n_pad < n || row0 < 0 || cap < n || row0 >= cap) return pfail(p, FP_EINVAL, "fp_policy_hidden_to_ring: bad arguments");
     cudaSetDevice(p->device);
-    const int rows = POL_NA * POL_HID;
-    k_em_gather<<<grid_for(((n + 31) / 32) * 256), 256, rows * 33 * sizeof(float), (cudaStream_t)stream>>>(d_hid_em, n_pad, rows, n, d_field, row0, cap, d_zero_mask);
+    constexpr int smem_h = EM_KR * GT_STRIDE * (int)sizeof(float);
+    if (!p->attr_hidden) { cudaFuncSetAttribute(k_em_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_h); p->attr_hidden = 1; }
+    k_em_gather<<<gt_grid(((n + GT_ENVS - 1) / GT_ENVS) * 2, 2), 256, smem_h, (cudaStream_t)stream>>>(d_hid_em, n_pad, n, d_field, row0, cap, d_zero_mask);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;
@@ -825,6 +899,24 @@ int fp_policy_scalars_to_ring(FpPolicy* p, const double* d_reward, const uint8_t
     if (!d_reward || !d_done || n < 1 || row0 < 0 || cap < n || row0 >= cap) return pfail(p, FP_EINVAL, "fp_policy_scalars_to_ring: bad arguments");
     cudaSetDevice(p->device);
     k_scalars_to_ring<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(d_reward, d_done, n, last_step_all, f_reward, f_done, f_last, f_avail, row0, cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+int fp_policy_transition_tail(FpPolicy* p, const float* d_action, const float* d_logp, const double* d_reward, const uint8_t* d_done,
+                              int64_t n, int32_t last_step_all, int32_t zero_values, float* f_action, float* f_logp, float* f_value,
+                              float* f_next_value, float* f_reward, float* f_done, float* f_last, float* f_avail, int64_t row0,
+                              int64_t cap, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!d_action || !d_reward || !d_done || !f_action || !f_reward || !f_done || !f_last || (f_logp && !d_logp) ||
+        (zero_values && (!f_value || !f_next_value)) || n < 1 || row0 < 0 || cap < n || row0 >= cap)
+        return pfail(p, FP_EINVAL, "fp_policy_transition_tail: bad arguments");
+    cudaSetDevice(p->device);
+    k_transition_tail<<<grid_for(n * POL_NA * POL_ACT), 256, 0, (cudaStream_t)stream>>>(d_action, d_logp, d_reward, d_done, n, last_step_all,
+                                                                                       zero_values, f_action, f_logp, f_value, f_next_value,
+                                                                                       f_reward, f_done, f_last, f_avail, row0, cap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;

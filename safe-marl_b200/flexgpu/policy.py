@@ -97,16 +97,16 @@ class DevicePolicy:
         return b
 
     def act(self, ring, slot=None, n_envs=None, hid_in=None, reset=None, explore=True, eps=None, step=0, hid_out=None,
-            want_mean=False, want_logp=True, hid_layout="rows"):
+            want_mean=False, want_logp=True, hid_layout="rows", out="action"):
         """ring: an ObsRing (env.obs_ring() / step(..., return_obs='ring')) or a raw [24, 5, 6, n_pad] fp32 tensor with
         `slot` / `n_envs`.  Returns (action [N,5,4], log_prob [N,5,4] or None, hid, mean or None); the output
-        tensors are reused by the next call unless hid_out is given.  hid_layout: "rows" = [N, 5, 64] (the reference's
+        tensors are reused by the next call unless hid_out is given (out: name of the reused action buffer).  hid_layout: "rows" = [N, 5, 64] (the reference's
         (b, n, hid)), "env_minor" = [5, 64, n_pad] (the kernel's native layout: coalesced accesses; hid_out required)."""
         if hasattr(ring, "ring"):
             slot, n_envs, ring = ring.slot, ring.env.n_envs, ring.ring
         n_pad = ring.shape[-1]
         N = int(n_envs)
-        action = self._buf("action", (N, N_AGENTS, ACT))
+        action = self._buf(out, (N, N_AGENTS, ACT))
         logp = self._buf("logp", (N, N_AGENTS, ACT)) if want_logp else None
         mean = self._buf("mean", (N, N_AGENTS, ACT)) if want_mean else None
         em = hid_layout == "env_minor"
@@ -225,19 +225,19 @@ class DeviceRollout:
         self.total_steps += 1
         if self.R:
             pol.gather_windows(self.ring, self.R, self._fptr["next_state"], TRANSITION_FIELDS["next_state"], pos, self.replay.size)
-            self._rows("action", action, pos); self._rows("log_prob_a", logp, pos); self._hidden_rows("hid", hid, pos)
-            if self.value_fn is None:
-                self._rows("value", self._zeros, pos); self._rows("next_value", self._zeros, pos)
-            else:       # next_value = critic(next_state, a second sampled action from the new hidden state) (model.py:225-226)
+            self._hidden_rows("hid", hid, pos)
+            if self.value_fn is not None:   # next_value = critic(next_state, a second sampled action from the new hidden state) (model.py:225-226)
                 a2, _, _, _ = pol.act(self.ring, hid_in=hid, explore=explore, eps=eps_next, step=(1 << 40) + self.total_steps,
-                                      hid_out=self._hid_scratch, hid_layout="env_minor", want_logp=False)
+                                      hid_out=self._hid_scratch, hid_layout="env_minor", want_logp=False, out="action2")
                 with torch.no_grad():
                     nv = self.value_fn(self._dense_obs(), a2[:self.R])
                 self._rows("next_value", nv.reshape(self.R, N_AGENTS).float().contiguous(), pos)
-            pol._check(pol._lib.fp_policy_scalars_to_ring(
-                pol._p, _ptr(reward), _ptr(done), self.R, 1 if self.t == self.max_steps else 0, self._fptr["reward"],
-                self._fptr["done"], self._fptr["last_step"], self._fptr["action_avail"], pos, self.replay.size, _stream()),
-                "fp_policy_scalars_to_ring")
+            # action, log_prob_a, reward per agent, done, last_step, action_avail (and value / next_value = 0 without a critic): one launch
+            f = self._fptr
+            pol._check(pol._lib.fp_policy_transition_tail(
+                pol._p, _ptr(action), _ptr(logp), _ptr(reward), _ptr(done), self.R, 1 if self.t == self.max_steps else 0,
+                1 if self.value_fn is None else 0, f["action"], f["log_prob_a"], f["value"], f["next_value"], f["reward"], f["done"],
+                f["last_step"], f["action_avail"], pos, self.replay.size, _stream()), "fp_policy_transition_tail")
         self._cur = 1 - self._cur
         self._reset_mask = None
         if self.t >= env.episode_limit - 1 or self.t >= self.max_steps:        # every env of the batch has terminated (Q1)
