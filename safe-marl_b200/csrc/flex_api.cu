@@ -55,6 +55,8 @@ struct FpHandle {
     cudaStream_t host_streams[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
     cudaEvent_t host_ev_in = nullptr, host_ev_out[FP_HOST_STREAMS] = {nullptr, nullptr, nullptr};
     int fuse_obs = 0;            // set around the fp_step of fp_step_obs: the step kernel pushes the observation
+    int keep_hist = 1;           // fp_set_obs_history: 0 = the fused ring step does not maintain the fp64 history ring
+    bool hist_valid = true;      // false after a ring-only step: restored from the env-minor ring on demand (hist_ensure)
     int host_chunks = 0;         // 0 = not decided yet (FLEXGPU_HOST_CHUNKS or the default)
     // the chunk pipeline of fp_step_host as instantiated CUDA graphs, one per set of (pinned) host
     // buffers: one launch per step instead of five API calls per chunk
@@ -482,7 +484,7 @@ int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
     }
     p.reward = d_reward; p.done = d_done; p.info = d_info; p.mask = d_mask;
     p.stats_partial = h->d_stats_partial;
-    if (h->fuse_obs) { p.obs_push = 1; p.obs_q = h->ring_q; p.hist = h->d_hist; p.obsr = h->d_obsr; p.n_pad = h->n_pad; }
+    if (h->fuse_obs) { p.obs_push = 1; p.obs_q = h->ring_q; p.hist = h->keep_hist ? h->d_hist : nullptr; p.obsr = h->d_obsr; p.n_pad = h->n_pad; }
     CUDA_TRY(h, launch_env_any(h, MODE_STEP, p, (cudaStream_t)stream));
     h->launches++;
     return FP_OK;
@@ -658,11 +660,30 @@ static void fill_obs_params(FpHandle* h, ObsParams& p, void* out, int push) {
     p.out = out; p.push = push;
 }
 
+// The fp64 history ring after ring-only steps (fp_set_obs_history(h, 0)): restored from the env-minor ring, which is
+// valid whenever the history is not.
+static int hist_ensure(FpHandle* h, cudaStream_t st) {
+    if (h->hist_valid) return FP_OK;
+    if (!h->d_obsr || !h->obsr_valid) return fail(h, FP_ESTATE, "observation history lost: neither the fp64 ring nor the env-minor ring is valid");
+    ObsParams p; fill_obs_params(h, p, nullptr, 0);
+    CUDA_TRY(h, launch_hist_from_ring(p, h->d_obsr, h->n_pad, h->ring_q, st));
+    h->launches++;
+    h->hist_valid = true;
+    return FP_OK;
+}
+
+int fp_set_obs_history(FpHandle* h, int keep) {
+    if (!h) return FP_EINVAL;
+    h->keep_hist = keep ? 1 : 0;
+    return FP_OK;
+}
+
 int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
     if (!h) return FP_EINVAL;
     USE_DEVICE(h);
     if (!h->d_P) return fail(h, FP_ESTATE, "fp_get_obs: call fp_load_profiles first");
     if (!d_out || (dtype != FP_F32 && dtype != FP_F64)) return fail(h, FP_EINVAL, "fp_get_obs: bad arguments");
+    { const int rc = hist_ensure(h, (cudaStream_t)stream); if (rc != FP_OK) return rc; }
     ObsParams p; fill_obs_params(h, p, d_out, push ? 1 : 0);
     CUDA_TRY(h, launch_obs(p, dtype == FP_F64, h->grid_obs, (cudaStream_t)stream));
     h->launches++;
@@ -675,6 +696,7 @@ int fp_get_obs(FpHandle* h, void* d_out, int dtype, int push, void* stream) {
 static int obs_ring_prepare(FpHandle* h, bool push, cudaStream_t st) {
     const int H = h->dc.history, na = h->dc.na;
     const int64_t per_env = (int64_t)na * 3 * H * 6;
+    { const int rc = hist_ensure(h, st); if (rc != FP_OK) return rc; }   // the rebuild and the push below use the fp64 ring
     ObsParams p; fill_obs_params(h, p, nullptr, 1);
     if (!h->d_obsm) {
         CUDA_TRY(h, cudaSetDevice(h->device));
@@ -737,6 +759,7 @@ static int obs_envminor_prepare(FpHandle* h, bool push, cudaStream_t st) {
         h->obsr_valid = false;
     }
     if (!h->obsr_valid) {
+        if (!h->hist_valid) return fail(h, FP_ESTATE, "observation history lost: neither the fp64 ring nor the env-minor ring is valid");
         ObsParams p; fill_obs_params(h, p, nullptr, 1);
         CUDA_TRY(h, launch_obsr_rebuild(p, h->d_obsr, h->n_pad, st));
         h->launches++;
@@ -780,6 +803,7 @@ int fp_step_ring(FpHandle* h, const void* d_actions, int act_dtype, double* d_re
     rc = fp_step(h, d_actions, act_dtype, d_reward, d_done, d_info, nullptr, stream);
     h->fuse_obs = 0;
     if (rc != FP_OK) return rc;
+    if (!h->keep_hist) h->hist_valid = false;      // ring-only stepping: the fp64 history ring missed this push (hist_ensure)
     h->obsm_valid = false;                         // the env-major window ring missed this push
     *d_ring = h->d_obsr;
     if (slot) *slot = h->ring_q;
@@ -874,6 +898,8 @@ int fp_state_ptrs(FpHandle* h, void** d_rec, void** d_voltage, void** d_setpoint
 // With write != 0 the caller is about to overwrite it (state restore): the derived fp32 rings are rebuilt on next use.
 int fp_history_ptr(FpHandle* h, void** d_hist, int64_t* doubles_per_env, int32_t write) {
     if (!h || !d_hist) return FP_EINVAL;
+    if (write) h->hist_valid = true;               // about to be overwritten as a whole
+    else { const int rc = hist_ensure(h, nullptr); if (rc != FP_OK) return rc; cudaStreamSynchronize(nullptr); }
     *d_hist = h->d_hist;
     if (doubles_per_env) *doubles_per_env = (int64_t)h->dc.history * FP_HIST_SLOT;
     if (write) { h->obsm_valid = false; h->obsr_valid = false; }

@@ -476,6 +476,26 @@ __global__ void k_obsr_rebuild(const ObsParams prm, float* __restrict__ obsr, in
     }
 }
 
+// The reverse: restore the fp64 history ring from the env-minor ring after ring-only stepping (fp_set_obs_history(h, 0):
+// the fused step then pushes the fp32 ring alone).  Window position s (oldest first) = push number cnt - H + s lives in
+// ring slot (q - H + 1 + s) mod H; the restored entries are the fp32 values widened, i.e. every fp32 read of the
+// history is unchanged and an fp64 read sees the observation at fp32 precision.
+__global__ void k_hist_from_ring(const ObsParams prm, const float* __restrict__ obsr, int64_t n_pad, int q) {
+    const DevCfg& c = prm.c;
+    const int na = c.na, H = c.history;
+    const int64_t total = (int64_t)H * FP_HIST_SLOT * prm.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / (H * FP_HIST_SLOT);
+        const int r = (int)(i - e * (H * FP_HIST_SLOT)), s = r / FP_HIST_SLOT, af = r - s * FP_HIST_SLOT;
+        const int32_t cnt = (int32_t)(uint32_t)prm.rec[e * FP_REC_STRIDE + FP_REC_HIST];
+        const int k = cnt - H + s;
+        if (k < 0) continue;
+        const int slot = ((q - H + 1 + s) % H + H) % H;
+        prm.hist[e * (int64_t)(H * FP_HIST_SLOT) + (k % H) * FP_HIST_SLOT + af] =
+            (af < na * 6) ? (double)obsr[((int64_t)slot * na * 6 + af) * n_pad + e] : 0.0;
+    }
+}
+
 // Zero the columns of the envs a reset touches (mask == nullptr: all).  A thread owns an env: the 32 envs of a warp
 // write whole lines when they are reset together (the usual case: episodes of a batch end together).
 __global__ void k_obsr_clear(float* __restrict__ obsr, const uint8_t* __restrict__ mask, int64_t n, int64_t n_pad, int rows) {
@@ -665,6 +685,10 @@ cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t 
     return cudaGetLastError();
 }
 
+cudaError_t launch_hist_from_ring(const ObsParams& prm, const float* obsr, int64_t n_pad, int q, cudaStream_t st) {
+    k_hist_from_ring<<<148 * 16, 256, 0, st>>>(prm, obsr, n_pad, q);
+    return cudaGetLastError();
+}
 cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad, cudaStream_t st) {
     k_obsr_rebuild<<<148 * 16, 256, 0, st>>>(prm, obsr, n_pad);
     return cudaGetLastError();

@@ -88,6 +88,7 @@ cudaError_t launch_obsm_clear(float* obsm, const uint8_t* mask, int64_t n, int f
 cudaError_t launch_obsm_rebuild(const ObsParams& prm, float* obsm, cudaStream_t st);
 cudaError_t launch_obsm_compact(float* obsm, int64_t rows, int H, cudaStream_t st);
 cudaError_t launch_obsr_rebuild(const ObsParams& prm, float* obsr, int64_t n_pad, cudaStream_t st);
+cudaError_t launch_hist_from_ring(const ObsParams& prm, const float* obsr, int64_t n_pad, int q, cudaStream_t st);
 cudaError_t launch_obsr_clear(float* obsr, const uint8_t* mask, int64_t n, int64_t n_pad, int rows, cudaStream_t st);
 cudaError_t launch_obsr_reset_push(const ObsParams& prm, float* obsr, int64_t n_pad, int q, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_obsr_gather(const float* obsr, float* out, int64_t n, int64_t n_pad, int na, int H, int q, cudaStream_t st);

@@ -72,6 +72,7 @@ _PROTOS = {
     "fp_obs_ring": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(C.c_int64), _P]),
     "fp_obs_ring_reset_push": (C.c_int, [_P, _P, _P]),
     "fp_obs_ring_gather": (C.c_int, [_P, _P, _P]),
+    "fp_set_obs_history": (C.c_int, [_P, C.c_int]),
     "fp_get_state": (C.c_int, [_P, _P, C.c_int, _P]),
     "fp_state_ptrs": (C.c_int, [_P] + [C.POINTER(_P)] * 6),
     "fp_set_keep_flows": (C.c_int, [_P, C.c_int]),

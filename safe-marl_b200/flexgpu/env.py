@@ -435,6 +435,12 @@ class BatchedFlexProvisionEnv:
                                             _ptr(Isq), _ptr(iters), _ptr(failed), _stream()), "fp_power_flow")
         return dict(V=V, P=Pl, Q=Ql, Isq=Isq, iters=iters, failed=failed.bool())
 
+    def set_obs_history(self, keep=True):
+        """keep=False: ring-only stepping for device rollouts -- step(..., return_obs='ring') pushes the env-minor fp32
+        ring alone (91 -> 79 us per 131 072 envs); the fp64 history behind get_obs() is restored from the ring when a
+        call needs it, with its entries at fp32 precision (fp32 reads are unchanged)."""
+        self._check(self._lib.fp_set_obs_history(self._h, 1 if keep else 0), "fp_set_obs_history")
+
     # ------------------------------------------------------------------ checkpointing the device state (SURVEY 5)
     def _history(self, write):
         p, per = C.c_void_p(), C.c_int64()

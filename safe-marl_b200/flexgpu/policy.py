@@ -143,8 +143,12 @@ class DeviceRollout:
     starts a new one; without it (the default: failures do not occur on feasible profiles) such an env pays its -200,
     is flagged done / last_step in its Transition, and keeps stepping until the batch's common reset."""
 
-    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240, reset_done_each_step=False, value_fn=None):
+    def __init__(self, env, policy, replay=None, record_envs=None, max_steps=240, reset_done_each_step=False, value_fn=None,
+                 fp64_history=False):
         self.env, self.policy, self.replay = env, policy, replay
+        # the loop consumes the fp32 ring only: by default the step stops pushing the fp64 history ring as well
+        # (env.set_obs_history); a later env.get_obs() restores it from the ring at fp32 precision
+        env.set_obs_history(bool(fp64_history))
         self.N = env.n_envs
         self.R = 0 if replay is None else int(self.N if record_envs is None else min(record_envs, self.N))
         if replay is not None and (dict(replay.fields) != TRANSITION_FIELDS or self.R > replay.size):
