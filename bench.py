@@ -372,7 +372,20 @@ def main():
             evo[k][0].record(stream); env.step(acts[k % n_act], want_info=False, return_obs="ring"); evo[k][1].record(stream)
         barrier()
         obs_ms = sum(a.elapsed_time(b) for a, b in evo)
-        obs_extra = (E * Ko, obs_ms)
+        # the same with ring-only stepping (set_obs_history(False): the fp64 history ring behind get_obs() is not pushed;
+        # what the device rollout uses)
+        env.set_obs_history(False)
+        for k in range(3):
+            env.step(acts[k % n_act], want_info=False, return_obs="ring")
+        barrier()
+        for k in range(Ko):
+            if not args.no_flush:
+                flush.zero_()
+            evo[k][0].record(stream); env.step(acts[k % n_act], want_info=False, return_obs="ring"); evo[k][1].record(stream)
+        barrier()
+        obs_ring_ms = sum(a.elapsed_time(b) for a, b in evo)
+        env.set_obs_history(True)
+        obs_extra = (E * Ko, obs_ms, obs_ring_ms)
 
     # ---- the rollout loop on the device (model.py:213-254): tcgen05 policy -> fused translate_action + step + get_obs
     #      [-> Transition fields into the device replay ring]; nothing crosses PCIe (only the statistics, afterwards)
@@ -507,11 +520,12 @@ def main():
         ring.close()
 
     t = torch.tensor([dev_ms, e2e_s, kern_ms, obs_extra[1] if obs_extra else 0.0, strong[2] if strong else 0.0,
-                      rollout["acting"][1] if rollout else 0.0, rollout["recording"][1] if rollout else 0.0],
+                      rollout["acting"][1] if rollout else 0.0, rollout["recording"][1] if rollout else 0.0,
+                      obs_extra[2] if obs_extra else 0.0],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, kern_ms, obs_ms, strong_ms, roll_ms, rollrec_ms = (float(x) for x in t)
+    dev_ms, e2e_s, kern_ms, obs_ms, strong_ms, roll_ms, rollrec_ms, obs_ring_ms = (float(x) for x in t)
     stats = env.episode_stats(reduce=True)                     # the one NCCL collective (16 doubles)
     total_envs = E * world
     value = total_envs * K / (dev_ms * 1e-3)
@@ -555,7 +569,10 @@ def main():
         if obs_extra is not None:
             line["step_plus_get_obs_env_steps_per_s"] = obs_extra[0] * world / (obs_ms * 1e-3)
             line["step_plus_get_obs"] = {"api": "step(..., return_obs='ring') -> fp_step_ring (one launch)", "steps": 40,
-                                         "ms_per_step": obs_ms / 40, "l2": "flushed before every step"}
+                                         "ms_per_step": obs_ms / 40, "l2": "flushed before every step",
+                                         "ring_only": {"api": "set_obs_history(False): the fp64 history ring is not pushed (device rollouts)",
+                                                       "env_steps_per_s": obs_extra[0] * world / (obs_ring_ms * 1e-3),
+                                                       "ms_per_step": obs_ring_ms / 40}}
         if rollout is not None:
             line["rollout_env_steps_per_s"] = rollout["acting"][0] * world / (roll_ms * 1e-3)
             line["rollout"] = {"loop": "k_policy (RNNAgent fc1-LayerNorm-ReLU-GRUCell-fc2 + tanh-Normal sampling, tcgen05) -> fp_step_ring "

@@ -539,21 +539,44 @@ __global__ void k_obsr_reset_push(const ObsParams prm, float* __restrict__ obsr,
 }
 
 // Dense view of the ring: out[e][a][s * 6 + f] = obsr[(q - H + 1 + s) mod H][a][f][e]  (the reference's get_obs layout,
-// :387-401).  A CTA transposes a block of 32 envs through shared memory: coalesced on both sides.
+// :387-401).  A CTA transposes a tile of (128 envs, one agent) through shared memory -- rows of 129 floats: the row-wise
+// fill and the column-wise drain are both conflict-free -- so that both sides move >= 512 contiguous bytes per row (a
+// 32-env tile reads 128-byte pieces 512 KB apart, which DRAM serves at less than half its rate).
 __global__ void __launch_bounds__(256) k_obsr_gather(const float* __restrict__ obsr, float* __restrict__ out, int64_t n, int64_t n_pad,
                                                      int na, int H, int q) {
-    extern __shared__ float tile[];                // [rows = H * na * 6][33]
-    const int rows = H * na * 6, W = H * 6;
+    extern __shared__ float tile[];                // [W = 6 H][129]
+    const int W = H * 6;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t e0 = (int64_t)blockIdx.x * 32; e0 < n; e0 += (int64_t)gridDim.x * 32) {
-        for (int r = warp; r < rows; r += 8) tile[r * 33 + lane] = (e0 + lane < n_pad) ? obsr[(int64_t)r * n_pad + e0 + lane] : 0.f;
+    const int64_t n_blk = (n + 127) >> 7;
+    for (int64_t blk = blockIdx.x; blk < n_blk * na; blk += gridDim.x) {
+        const int a = (int)(blk % na);
+        const int64_t e0 = (blk / na) << 7;
+        for (int k0 = warp; k0 < W; k0 += 32) {    // four rows per warp and trip: sixteen loads in flight per thread
+            float v[4][4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int k = k0 + 8 * m;
+                const int sl = k / 6, f = k - 6 * sl;
+                int slot = q + 1 + sl; slot = slot >= H ? slot - H : slot;      // q - H + 1 + sl (mod H)
+                const float* sp = obsr + ((int64_t)(slot * na + a) * 6 + f) * n_pad + e0 + lane;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[m][i] = (k < W && e0 + lane + 32 * i < n) ? __ldg(sp + 32 * i) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int k = k0 + 8 * m;
+                if (k < W) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tile[k * 129 + lane + 32 * i] = v[m][i];
+                }
+            }
+        }
         __syncthreads();
-        const int64_t ne = (n - e0 < 32) ? (n - e0) : 32;
-        for (int64_t o = threadIdx.x; o < ne * na * W; o += 256) {
-            const int j = (int)(o / (na * W)), r = (int)(o - (int64_t)j * (na * W));
-            const int a = r / W, k = r - a * W, sl = k / 6, f = k - 6 * sl;
-            const int slot = (q + 1 + sl) % H;     // q - H + 1 + sl (mod H)
-            out[(e0 + j) * (int64_t)(na * W) + r] = tile[((slot * na + a) * 6 + f) * 33 + j];
+        for (int j = warp; j < 128; j += 8) {
+            if (e0 + j < n) {
+                float* dst = out + ((e0 + j) * na + a) * (int64_t)W;
+                for (int k = lane; k < W; k += 32) dst[k] = tile[k * 129 + j];
+            }
         }
         __syncthreads();
     }
@@ -815,16 +838,12 @@ cudaError_t launch_obsr_reset_push(const ObsParams& prm, float* obsr, int64_t n_
 }
 
 cudaError_t launch_obsr_gather(const float* obsr, float* out, int64_t n, int64_t n_pad, int na, int H, int q, cudaStream_t st) {
-    const size_t bytes = (size_t)H * na * 6 * 33 * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_obsr_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    const size_t bytes = (size_t)H * 6 * 129 * sizeof(float);
     if (bytes > 200 * 1024) return cudaErrorInvalidValue;
-    const int64_t ctas = (n + 31) / 32;
-    k_obsr_gather<<<(unsigned)(ctas < 148 * 2 ? ctas : 148 * 2), 256, bytes, st>>>(obsr, out, n, n_pad, na, H, q);
+    cudaError_t e = cudaFuncSetAttribute(k_obsr_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   // per device: set on every call
+    if (e != cudaSuccess) return e;
+    const int64_t ctas = ((n + 127) / 128) * na;
+    k_obsr_gather<<<(unsigned)(ctas < 148 * 3 ? ctas : 148 * 3), 256, bytes, st>>>(obsr, out, n, n_pad, na, H, q);
     return cudaGetLastError();
 }
 
