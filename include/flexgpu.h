@@ -369,6 +369,17 @@ int fp_policy_transition_tail(FpPolicy* p, const float* d_action, const float* d
                               const uint8_t* d_done, int64_t n, int32_t last_step_all, int32_t zero_values, float* f_action,
                               float* f_logp, float* f_value, float* f_next_value, float* f_reward, float* f_done, float* f_last,
                               float* f_avail, int64_t row0, int64_t cap, void* stream);
+/* The critic of the rollout loop: MADDPG.value (madrl/models/maddpg.py:29-76) with the shared-parameter MLPCritic
+ * (madrl/critics/mlp_critic.py:5-36: fc1 -> LayerNorm -> ReLU -> fc2 -> ReLU -> fc3) as train_process evaluates it for the
+ * Transition's value / next_value (madrl/models/model.py:217, :225-226), on tcgen05 (k_critic), reading the observation
+ * ring directly.  fp_critic_load: HOST fp32 arrays in torch's state_dict layouts -- fc1.weight [64][745] (720 observation
+ * columns | 5 agent-id columns | 20 action columns), fc1.bias [64], layernorm.weight / .bias [64], fc2.weight [64][64],
+ * fc2.bias [64], fc3.weight [1][64], fc3.bias [1].  fp_critic_value: d_actions [n_envs][5][4] fp32 (what fp_policy_act
+ * returned), d_value [n_envs][5] fp32. */
+int fp_critic_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const float* ln_g, const float* ln_b,
+                   const float* fc2_w, const float* fc2_b, const float* fc3_w, const float* fc3_b);
+int fp_critic_value(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_actions,
+                    float* d_value, void* stream);
 /* Learner feed: the device part of unpack_data (model.py:308-323) on a batch sampled with fp_replay_sample.
  * d_critic_in [batch * 5][745] = the MADDPG critic's input rows (maddpg.py:29-66: all agents' observations, one-hot
  * agent id, all agents' actions); d_reward_norm [batch][5] = reward_normalisation (BatchNorm1d over the batch, training

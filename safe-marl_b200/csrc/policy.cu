@@ -483,6 +483,260 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
+// ---------------------------------------------------------------------------- critic: MADDPG.value on tcgen05
+// k_critic replaces, for N envs x 5 agents at once, MADDPG.value (madrl/models/maddpg.py:29-76) with the shared-parameter
+// MLPCritic (madrl/critics/mlp_critic.py:5-36: fc1 -> LayerNorm -> ReLU -> fc2 -> ReLU -> fc3) as train_process calls it for
+// the Transition's value / next_value (madrl/models/model.py:217, :225-226).  The critic's 745-wide input row of (env, agent
+// i) is [all five agents' observations (720) | one-hot(i) (5) | all five agents' actions (20)]: only the one-hot differs
+// between the five rows of an env, so fc1 is evaluated ONCE per env on its 740 shared columns and the one-hot column is
+// folded into a per-agent bias.  A tile is 128 envs, input = the env-minor observation ring, untouched:
+//     for agent block a = 0..4:  TMA box [24][6][128] of agent a -> staging;  P0 split -> TMEM;  M1: acc1 += X_a Wc_a^T
+//         (36 k-steps x (hi, lo); the fc1 block of agent a -- ring rotation folded into the weights like k_policy's W1 --
+//         streams through a three-deep shared-memory buffer); block 0 also adds the actions' 20 columns (K padded to 24)
+//     for agent i = 0..4:  E1: acc1 + bias(i) -> LayerNorm -> ReLU -> split -> A2;  M2: acc2 = A2 W2^T;  E2: ReLU,
+//         dot with fc3 (fp32, CUDA cores), four-thread reduction, + bias -> value[env][i]
+// Phases are serial (workers <-> MMA warp through the same two mbarriers as k_policy); precision as k_policy: activations
+// two-term TF32 split, fc1 / fc2 matrices held as TF32, fc3 in fp32.
+constexpr uint32_t CR_WB_BYTES = W1_BYTES;                                   // one agent block of fc1: [36 kc][64 n][4]
+constexpr int CR_NWB = 3;                                                    // weight-block buffers in flight
+constexpr uint32_t CR_W2_BYTES = POL_HID * POL_HID * 4;                      // fc2: [16 kc][64 n][4]
+constexpr int CR_KACT = 24;                                                  // 20 action columns + 4 zero columns
+constexpr uint32_t CR_WA_BYTES = CR_KACT * POL_HID * 4;                      // [6 kc][64 n][4]
+// small arrays (floats): b1a[5][64] (fc1.bias + the one-hot column of agent i), ln_g[64], ln_b[64], b2[64], w3[64], b3 (+ pad)
+constexpr int CV_B1A = 0, CV_LNG = 320, CV_LNB = 384, CV_B2 = 448, CV_W3 = 512, CV_B3 = 576, CV_FLOATS = 592;
+constexpr uint32_t CO_WB = 0, CO_W2 = CO_WB + CR_NWB * CR_WB_BYTES, CO_WA = CO_W2 + CR_W2_BYTES, CO_VEC = CO_WA + CR_WA_BYTES;
+constexpr uint32_t CO_STAGE = (CO_VEC + CV_FLOATS * 4 + 127) / 128 * 128;    // [144][128] fp32
+constexpr uint32_t CO_LN = CO_STAGE + POL_OBS * POL_M * 4;                   // [TPR][128 rows] float2
+constexpr uint32_t CO_FC = CO_LN + TPR * POL_M * 8;                          // [TPR][128 rows] float: fc3 partial sums
+constexpr uint32_t CO_BAR = CO_FC + TPR * POL_M * 4;                         // a_ready, mma_done, small arrays, x_full, wb[3]
+constexpr uint32_t CO_TMEM = CO_BAR + 64;
+constexpr uint32_t CR_SMEM = CO_TMEM + 16;
+static_assert(CR_SMEM <= 227 * 1024, "critic kernel exceeds the shared memory of one SM");
+static_assert(CO_W2 % 128 == 0 && CO_WA % 128 == 0 && CO_VEC % 16 == 0 && CO_STAGE % 128 == 0, "operand alignment");
+// TMEM columns: X hi | lo (fc1 operand; A2 hi | lo of fc2 aliases its first 128 columns), acc1, acc2, actions hi | lo
+constexpr uint32_t CC_ACC1 = 288, CC_ACC2 = 352, CC_ACTHI = 416, CC_ACTLO = 440;
+
+struct CritParams {
+    const float* ring; int64_t n_pad; int64_t n; int32_t slot;
+    const float* Wc1rot; const float* W2; const float* Wa; const float* vec;
+    const float* actions;                                             // [n][5][4]
+    float* value;                                                     // [n][5]
+    int32_t use_tma;
+};
+
+__global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const float* vec = reinterpret_cast<const float*>(smem + CO_VEC);
+    float* stage = reinterpret_cast<float*>(smem + CO_STAGE);
+    float2* lnp = reinterpret_cast<float2*>(smem + CO_LN);
+    float* fcp = reinterpret_cast<float*>(smem + CO_FC);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + CO_TMEM);
+    const uint32_t bar_a = smem_u32(smem + CO_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24, bar_wb0 = bar_a + 32;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
+    const int row = tid & (POL_M - 1), qt = (tid >> 7) & (TPR - 1);
+    const int64_t n_tiles = (prm.n + POL_M - 1) / POL_M;
+    const int64_t n_my = (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_blocks = n_my * POL_NA;                                  // (tile, agent block) pairs of this CTA, in order
+
+    auto tile_of = [&](int64_t j) -> int64_t { return (int64_t)blockIdx.x + (j / POL_NA) * gridDim.x; };
+    auto tma_request = [&](int64_t j) {                                      // one thread: observation block j -> staging
+        mbar_expect_tx(bar_x, POL_OBS * POL_M * 4);
+        tma_load_box(smem_u32(stage), &tmap, (int32_t)(tile_of(j) * POL_M), (int32_t)(j % POL_NA) * POL_F, bar_x);
+    };
+    auto load_wb = [&](int64_t j) {                                          // one thread: fc1 block of agent j % 5 -> buffer j % 3
+        const uint32_t bar = bar_wb0 + 8 * (uint32_t)(j % CR_NWB);
+        mbar_expect_tx(bar, CR_WB_BYTES);
+        tma_load_1d(smem_u32(smem + CO_WB + (j % CR_NWB) * CR_WB_BYTES),
+                    prm.Wc1rot + ((size_t)prm.slot * POL_NA + (size_t)(j % POL_NA)) * (CR_WB_BYTES / 4), CR_WB_BYTES, bar);
+    };
+    auto request = [&](int64_t j) {                                          // workers, rings narrower than a tile: LDGSTS
+        const int a = (int)(j % POL_NA);
+        const int64_t e0 = tile_of(j) * POL_M;
+        const int c4 = (tid & 31) * 4;
+        const bool inside = e0 + c4 + 4 <= prm.n_pad;
+#pragma unroll
+        for (int i = 0; i < POL_OBS * 32 / N_WORKERS; ++i) {
+            const int k = (tid >> 5) + (N_WORKERS / 32) * i;
+            const int sl = k / POL_F, f = k - sl * POL_F;
+            float* dst = stage + k * POL_M + c4;
+            if (inside) cp_async16(dst, prm.ring + ((int64_t)(sl * POL_NA + a) * POL_F + f) * prm.n_pad + e0 + c4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+
+    if (tid == 0) {
+        mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1); mbar_init(bar_x, 1);
+        for (int i = 0; i < CR_NWB; ++i) mbar_init(bar_wb0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (n_blocks > 0) {
+            if (prm.use_tma) tma_request(0);
+            load_wb(0);
+            if (n_blocks > 1) load_wb(1);
+        }
+        mbar_expect_tx(bar_w, CR_W2_BYTES + CR_WA_BYTES + CV_FLOATS * 4);    // fc2, action columns, small arrays: one barrier
+        tma_load_1d(smem_u32(smem + CO_W2), prm.W2, CR_W2_BYTES, bar_w);
+        tma_load_1d(smem_u32(smem + CO_WA), prm.Wa, CR_WA_BYTES, bar_w);
+        tma_load_1d(smem_u32(smem + CO_VEC), prm.vec, CV_FLOATS * 4, bar_w);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (!prm.use_tma && tid < N_WORKERS && n_blocks > 0) request(0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == N_WORKERS / 32) {
+        // =============================================================== MMA warp
+        const uint32_t w2 = smem_u32(smem + CO_W2), wa = smem_u32(smem + CO_WA);
+        uint32_t pa = 0;
+        bool first = true;
+        for (int64_t j = 0; j < n_blocks; ++j) {
+            const int a = (int)(j % POL_NA);
+            // ---- M1: fc1, agent block a (accumulating over the five blocks)
+            mbar_wait(bar_a, pa); pa ^= 1u;
+            mbar_wait(bar_wb0 + 8 * (uint32_t)(j % CR_NWB), (uint32_t)((j / CR_NWB) & 1));
+            if (first) { mbar_wait(bar_w, 0u); first = false; }
+            tc_fence_after();
+            __syncwarp();
+            if (elect_one()) {
+                // every worker has read the staging block, and fc1 of block j - 1 has completed (the workers waited for it
+                // before this P0): the next observation block and the weights of block j + 2 (buffer of block j - 1) may travel
+                if (prm.use_tma && j + 1 < n_blocks) tma_request(j + 1);
+                if (j + 2 < n_blocks) load_wb(j + 2);
+                const uint32_t wb = smem_u32(smem + CO_WB + (j % CR_NWB) * CR_WB_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < POL_OBS / 8; ++ks) {
+                    const uint64_t db = umma_desc(wb + ks * 2 * (64 * 16), 64 * 16, 128);
+                    umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + C_XHI + 8 * ks, db, idesc_n(64), (a > 0 || ks > 0) ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + C_XLO + 8 * ks, db, idesc_n(64), 1u);
+                }
+                if (a == 0) {
+#pragma unroll
+                    for (int ks = 0; ks < CR_KACT / 8; ++ks) {
+                        const uint64_t db = umma_desc(wa + ks * 2 * (64 * 16), 64 * 16, 128);
+                        umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + CC_ACTHI + 8 * ks, db, idesc_n(64), 1u);
+                        umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + CC_ACTLO + 8 * ks, db, idesc_n(64), 1u);
+                    }
+                }
+                umma_commit(bar_m);
+            }
+            __syncwarp();
+            if (a != POL_NA - 1) continue;
+            // ---- M2: fc2, once per agent row
+            for (int i = 0; i < POL_NA; ++i) {
+                mbar_wait(bar_a, pa); pa ^= 1u;
+                tc_fence_after();
+                __syncwarp();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < POL_HID / 8; ++ks) {
+                        const uint64_t db = umma_desc(w2 + ks * 2 * (64 * 16), 64 * 16, 128);
+                        umma_tf32_ts(tmem_base + CC_ACC2, tmem_base + C_A2HI + 8 * ks, db, idesc_n(64), ks > 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_base + CC_ACC2, tmem_base + C_A2LO + 8 * ks, db, idesc_n(64), 1u);
+                    }
+                    umma_commit(bar_m);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =============================================================== workers: four threads per env row (column quarters)
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int c0 = CPT * qt;
+        constexpr int KQ = POL_OBS / TPR;                                       // observation inputs per thread and block: 36
+        uint32_t pm = 0, px = 0;
+        bool first = true;
+        for (int64_t j = 0; j < n_blocks; ++j) {
+            const int a = (int)(j % POL_NA);
+            const int64_t e = tile_of(j) * POL_M + row;
+            const bool live = e < prm.n;
+            // ---- P0: observation block of agent a -> TMEM (fc1 of the previous block has completed: every worker waited)
+            if (prm.use_tma) { mbar_wait(bar_x, px); px ^= 1u; }
+            else cp_async_wait_all();
+            group_sync<1, N_WORKERS>();
+#pragma unroll
+            for (int c = 0; c < KQ / 4; ++c) {
+                const int k0 = KQ * qt + 4 * c;
+                split_st4(lane_base, C_XHI + k0, C_XLO + k0, stage[(k0 + 0) * POL_M + row], stage[(k0 + 1) * POL_M + row],
+                          stage[(k0 + 2) * POL_M + row], stage[(k0 + 3) * POL_M + row]);
+            }
+            if (a == 0 && qt < 3) {                                             // the env's 20 action values (+ 4 zero columns): 8 per thread
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 8 * qt + i;
+                    v[i] = (live && k < POL_NA * POL_ACT) ? __ldg(prm.actions + e * (POL_NA * POL_ACT) + k) : 0.0f;
+                }
+                split_st4(lane_base, CC_ACTHI + 8 * qt, CC_ACTLO + 8 * qt, v[0], v[1], v[2], v[3]);
+                split_st4(lane_base, CC_ACTHI + 8 * qt + 4, CC_ACTLO + 8 * qt + 4, v[4], v[5], v[6], v[7]);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+            if (!prm.use_tma) {
+                group_sync<1, N_WORKERS>();                                     // every thread has read the staging block
+                if (j + 1 < n_blocks) request(j + 1);
+            }
+            if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small arrays have landed
+            mbar_wait(bar_m, pm); pm ^= 1u;                                     // fc1 of this block has completed
+            tc_fence_after();
+            if (a != POL_NA - 1) continue;
+
+            // ---- per agent row: E1 (bias, LayerNorm, ReLU) -> M2 (fc2) -> E2 (ReLU, fc3)
+            float y1[CPT];
+            tmem_ld16(lane_base + CC_ACC1 + c0, y1);
+            tmem_wait_ld();
+            for (int i = 0; i < POL_NA; ++i) {
+                float v[CPT];
+                float s = 0.0f, ss = 0.0f;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) { v[c] = __fadd_rn(y1[c], vec[CV_B1A + i * POL_HID + c0 + c]); s = __fadd_rn(s, v[c]); ss = fmaf(v[c], v[c], ss); }
+                lnp[qt * POL_M + row] = make_float2(s, ss);
+                group_sync<1, N_WORKERS>();
+                float S = 0.0f, SS = 0.0f;
+#pragma unroll
+                for (int q4 = 0; q4 < TPR; ++q4) { const float2 t = lnp[q4 * POL_M + row]; S = __fadd_rn(S, t.x); SS = __fadd_rn(SS, t.y); }
+                const float mean = __fmul_rn(S, 1.0f / POL_HID);
+                const float var = fmaxf(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
+                const float rstd = rsqrtf(__fadd_rn(var, 1e-5f));
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const float t = fmaf(__fmul_rn(__fsub_rn(v[c], mean), rstd), vec[CV_LNG + c0 + c], vec[CV_LNB + c0 + c]);
+                    v[c] = fmaxf(t, 0.0f);                                       // hid_activation = relu
+                }
+#pragma unroll
+                for (int c = 0; c < CPT / 4; ++c)
+                    split_st4(lane_base, C_A2HI + c0 + 4 * c, C_A2LO + c0 + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_a);
+                mbar_wait(bar_m, pm); pm ^= 1u;
+                tc_fence_after();
+                float u[CPT];
+                tmem_ld16(lane_base + CC_ACC2 + c0, u);
+                tmem_wait_ld();
+                float part = 0.0f;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) part = fmaf(fmaxf(__fadd_rn(u[c], vec[CV_B2 + c0 + c]), 0.0f), vec[CV_W3 + c0 + c], part);
+                fcp[qt * POL_M + row] = part;
+                tc_fence_before();
+                group_sync<1, N_WORKERS>();
+                if (qt == 0 && live)
+                    prm.value[e * POL_NA + i] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fcp[row], fcp[POL_M + row]), fcp[2 * POL_M + row]), fcp[3 * POL_M + row]), vec[CV_B3]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
 // ---------------------------------------------------------------------------- transitions -> replay ring, learner feed
 // Pure data movement.  The sources are env-minor ([row][n_pad]: the observation ring, the hidden states), the replay
 // fields env-major ([transition][width]): a transposition through shared memory in tiles of GT_ENVS = 128 envs, so that
@@ -697,6 +951,8 @@ struct FpPolicy {
     int loaded = 0;
     int attr_window = 0, attr_hidden = 0;          // opt-in shared-memory sizes of the gather kernels set on this handle's device
     float* d_W1rot = nullptr; float* d_Wg = nullptr; float* d_vec = nullptr;
+    int critic_loaded = 0;
+    float* d_Wc1rot = nullptr; float* d_Wc2 = nullptr; float* d_Wca = nullptr; float* d_cvec = nullptr;   // critic (fp_critic_load)
     int64_t launches = 0;
     std::string err;
 };
@@ -722,6 +978,26 @@ int pfail(FpPolicy* p, int code, const std::string& msg) {
 }
 }  // namespace
 
+// The ring as a 3-D tensor [24 slots][30 = agent x feature][n_pad envs] (innermost first); a tile is the box [24][6][128] at
+// (env block, agent * 6, 0); envs past n_pad read as zeros.  Rings narrower than a tile: *use_tma = 0 (LDGSTS path).
+static int ring_tensor_map(FpPolicy* p, const float* d_ring, int64_t n_pad, CUtensorMap* tmap, int32_t* use_tma, const char* who) {
+    std::memset(tmap, 0, sizeof(*tmap));
+    *use_tma = 0;
+    if (n_pad >= POL_M && ((uintptr_t)d_ring & 15) == 0) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return pfail(p, FP_ECUDA, std::string(who) + ": cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t gdim[3] = {(cuuint64_t)n_pad, (cuuint64_t)(POL_NA * POL_F), (cuuint64_t)POL_H};
+        const cuuint64_t gstride[2] = {(cuuint64_t)n_pad * 4, (cuuint64_t)n_pad * 4 * (POL_NA * POL_F)};
+        const cuuint32_t box[3] = {POL_M, POL_F, POL_H}, estr[3] = {1, 1, 1};
+        const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_ring), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return pfail(p, FP_ECUDA, std::string(who) + ": cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        *use_tma = 1;
+    }
+    return FP_OK;
+}
+
 extern "C" {
 
 int fp_policy_create(int device, FpPolicy** out) {
@@ -739,6 +1015,7 @@ int fp_policy_destroy(FpPolicy* p) {
     if (!p) return FP_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_vec);
+    cudaFree(p->d_Wc1rot); cudaFree(p->d_Wc2); cudaFree(p->d_Wca); cudaFree(p->d_cvec);
     delete p;
     return FP_OK;
 }
@@ -820,23 +1097,8 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
     prm.hid_in = d_hid_in; prm.reset = d_reset; prm.hid_out = d_hid_out; prm.hid_em = hid_env_minor ? 1 : 0;
     prm.mean = d_mean; prm.action = d_action; prm.logp = d_logp; prm.eps = d_eps;
     prm.seed = seed; prm.step = step; prm.std_ = std_; prm.log_std = std::log(std_); prm.explore = explore;
-    // the ring as a 3-D tensor [24 slots][30 = agent x feature][n_pad envs] (innermost first); a tile is the box
-    // [24][6][128] at (env block, agent * 6, 0); envs past n_pad read as zeros
     alignas(64) CUtensorMap tmap;
-    std::memset(&tmap, 0, sizeof(tmap));
-    prm.use_tma = 0;
-    if (n_pad >= POL_M && ((uintptr_t)d_ring & 15) == 0) {
-        EncodeTiledFn enc = encode_tiled_fn();
-        if (!enc) return pfail(p, FP_ECUDA, "fp_policy_act: cuTensorMapEncodeTiled is not available from this driver");
-        const cuuint64_t gdim[3] = {(cuuint64_t)n_pad, (cuuint64_t)(POL_NA * POL_F), (cuuint64_t)POL_H};
-        const cuuint64_t gstride[2] = {(cuuint64_t)n_pad * 4, (cuuint64_t)n_pad * 4 * (POL_NA * POL_F)};
-        const cuuint32_t box[3] = {POL_M, POL_F, POL_H}, estr[3] = {1, 1, 1};
-        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_ring), gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return pfail(p, FP_ECUDA, "fp_policy_act: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-        prm.use_tma = 1;
-    }
+    { const int rc = ring_tensor_map(p, d_ring, n_pad, &tmap, &prm.use_tma, "fp_policy_act"); if (rc != FP_OK) return rc; }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const int64_t tiles = (n_envs + POL_M - 1) / POL_M * POL_NA;
@@ -917,6 +1179,81 @@ int fp_policy_transition_tail(FpPolicy* p, const float* d_action, const float* d
     k_transition_tail<<<grid_for(n * POL_NA * POL_ACT), 256, 0, (cudaStream_t)stream>>>(d_action, d_logp, d_reward, d_done, n, last_step_all,
                                                                                        zero_values, f_action, f_logp, f_value, f_next_value,
                                                                                        f_reward, f_done, f_last, f_avail, row0, cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+// Critic weights, HOST fp32 arrays in torch's state_dict layouts (MLPCritic, madrl/critics/mlp_critic.py:5-20, as
+// MADDPG.construct_value_net builds it, maddpg.py:18-27): fc1.weight [64][745] (720 observation columns | 5 agent-id columns |
+// 20 action columns), fc1.bias [64], layernorm.weight / .bias [64], fc2.weight [64][64], fc2.bias [64], fc3.weight [1][64],
+// fc3.bias [1].
+int fp_critic_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const float* ln_g, const float* ln_b, const float* fc2_w,
+                   const float* fc2_b, const float* fc3_w, const float* fc3_b) {
+    if (!p) return FP_EINVAL;
+    if (!fc1_w || !fc1_b || !ln_g || !ln_b || !fc2_w || !fc2_b || !fc3_w || !fc3_b) return pfail(p, FP_EINVAL, "fp_critic_load: null weight array");
+    cudaSetDevice(p->device);
+    const int KIN = POL_NA * POL_OBS + POL_NA + POL_NA * POL_ACT;          // 745
+    const size_t blk = CR_WB_BYTES / 4;
+    // fc1, observation columns: per ring rotation q and agent block a, UMMA K-major layout [kc][n][4] (see fp_policy_load)
+    std::vector<float> W1((size_t)POL_H * POL_NA * blk, 0.0f);
+    for (int q = 0; q < POL_H; ++q)
+        for (int a = 0; a < POL_NA; ++a)
+            for (int sl = 0; sl < POL_H; ++sl) {
+                const int r = ((sl - q - 1) % POL_H + POL_H) % POL_H;
+                for (int f = 0; f < POL_F; ++f) {
+                    const int k = sl * POL_F + f, src = a * POL_OBS + r * POL_F + f;
+                    for (int n = 0; n < POL_HID; ++n)
+                        W1[((size_t)q * POL_NA + a) * blk + ((size_t)(k >> 2) * POL_HID + n) * 4 + (k & 3)] = round_tf32(fc1_w[(size_t)n * KIN + src]);
+                }
+            }
+    std::vector<float> W2(CR_W2_BYTES / 4, 0.0f), Wa(CR_WA_BYTES / 4, 0.0f), vec(CV_FLOATS, 0.0f);
+    for (int n = 0; n < POL_HID; ++n) {
+        for (int k = 0; k < POL_HID; ++k) W2[((size_t)(k >> 2) * POL_HID + n) * 4 + (k & 3)] = round_tf32(fc2_w[(size_t)n * POL_HID + k]);
+        for (int k = 0; k < POL_NA * POL_ACT; ++k)
+            Wa[((size_t)(k >> 2) * POL_HID + n) * 4 + (k & 3)] = round_tf32(fc1_w[(size_t)n * KIN + POL_NA * POL_OBS + POL_NA + k]);
+        for (int a = 0; a < POL_NA; ++a) vec[CV_B1A + a * POL_HID + n] = fc1_b[n] + fc1_w[(size_t)n * KIN + POL_NA * POL_OBS + a];   // one-hot column folded in
+        vec[CV_LNG + n] = ln_g[n]; vec[CV_LNB + n] = ln_b[n]; vec[CV_B2 + n] = fc2_b[n]; vec[CV_W3 + n] = fc3_w[n];           // fc3 runs in fp32: unrounded
+    }
+    vec[CV_B3] = fc3_b[0];
+    cudaFree(p->d_Wc1rot); cudaFree(p->d_Wc2); cudaFree(p->d_Wca); cudaFree(p->d_cvec);
+    p->d_Wc1rot = p->d_Wc2 = p->d_Wca = p->d_cvec = nullptr; p->critic_loaded = 0;
+    if (cudaMalloc(&p->d_Wc1rot, W1.size() * 4) != cudaSuccess || cudaMalloc(&p->d_Wc2, W2.size() * 4) != cudaSuccess ||
+        cudaMalloc(&p->d_Wca, Wa.size() * 4) != cudaSuccess || cudaMalloc(&p->d_cvec, vec.size() * 4) != cudaSuccess)
+        return pfail(p, FP_ENOMEM, "fp_critic_load: cudaMalloc failed");
+    cudaMemcpy(p->d_Wc1rot, W1.data(), W1.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_Wc2, W2.data(), W2.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_Wca, Wa.data(), Wa.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_cvec, vec.data(), vec.size() * 4, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaFuncSetAttribute(k_critic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CR_SMEM);
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->critic_loaded = 1;
+    return FP_OK;
+}
+
+// MADDPG.value (maddpg.py:29-76) for n_envs envs: d_value[n_envs][5] = the critic on (the observation ring's windows of all
+// agents, agent id, d_actions[n_envs][5][4]) -- the Transition's value (model.py:217) or, on the ring after the step and a
+// second sampled action, next_value (:225-226).
+int fp_critic_value(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_actions,
+                    float* d_value, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!p->critic_loaded) return pfail(p, FP_ESTATE, "fp_critic_value: call fp_critic_load first");
+    if (!d_ring || !d_actions || !d_value || n_envs < 1 || slot < 0 || slot >= POL_H || n_pad < n_envs || (n_pad & 3))
+        return pfail(p, FP_EINVAL, "fp_critic_value: bad arguments");
+    cudaSetDevice(p->device);
+    CritParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.ring = d_ring; prm.n_pad = n_pad; prm.n = n_envs; prm.slot = slot;
+    prm.Wc1rot = p->d_Wc1rot; prm.W2 = p->d_Wc2; prm.Wa = p->d_Wca; prm.vec = p->d_cvec;
+    prm.actions = d_actions; prm.value = d_value;
+    alignas(64) CUtensorMap tmap;
+    { const int rc = ring_tensor_map(p, d_ring, n_pad, &tmap, &prm.use_tma, "fp_critic_value"); if (rc != FP_OK) return rc; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const int64_t tiles = (n_envs + POL_M - 1) / POL_M;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    k_critic<<<grid, POL_THREADS, CR_SMEM, (cudaStream_t)stream>>>(prm, tmap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;

@@ -24,6 +24,8 @@ _WEIGHT_KEYS = ("fc1.weight", "fc1.bias", "layernorm.weight", "layernorm.bias", 
                 "rnn.bias_ih", "rnn.bias_hh", "fc2.weight", "fc2.bias")
 _WEIGHT_SHAPES = ((HID, OBS + N_AGENTS), (HID,), (HID,), (HID,), (3 * HID, HID), (3 * HID, HID), (3 * HID,), (3 * HID,),
                   (ACT, HID), (ACT,))
+_CRITIC_KEYS = ("fc1.weight", "fc1.bias", "layernorm.weight", "layernorm.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias")
+_CRITIC_SHAPES = ((HID, N_AGENTS * (OBS + ACT) + N_AGENTS), (HID,), (HID,), (HID,), (HID, HID), (HID,), (1, HID), (1,))
 
 
 def _ptr(t):
@@ -57,6 +59,7 @@ class DevicePolicy:
         self.std = float(std)                       # fixed_policy_std (default.yaml: 1.0; gaussian_policy False)
         self.seed = int(seed)
         self._bufs = {}
+        self.has_critic = False
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -88,6 +91,31 @@ class DevicePolicy:
 
     def launch_count(self):
         return int(self._lib.fp_policy_launch_count(self._p))
+
+    def load_critic(self, sd):
+        """sd: MLPCritic.state_dict() (madrl/critics/mlp_critic.py, as MADDPG.construct_value_net builds it: input 745)."""
+        arrs = []
+        for k, shape in zip(_CRITIC_KEYS, _CRITIC_SHAPES):
+            v = sd[k]
+            a = np.ascontiguousarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+            if a.shape != shape:
+                raise ValueError(f"critic {k}: expected {shape}, got {a.shape} (hid_size 64, 5 x (144 + 4) + 5 inputs)")
+            arrs.append(a)
+        self._check(self._lib.fp_critic_load(self._p, *[a.ctypes.data_as(C.c_void_p) for a in arrs]), "fp_critic_load")
+        self.has_critic = True
+
+    def value(self, ring, action, slot=None, n_envs=None, out=None):
+        """MADDPG.value (maddpg.py:29-76) on the observation ring and `action` [N, 5, 4]: [N, 5, 1] (k_critic, tcgen05)."""
+        if hasattr(ring, "ring"):
+            slot, n_envs, ring = ring.slot, ring.env.n_envs, ring.ring
+        N = int(n_envs)
+        act = action.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(act.shape) != (N, N_AGENTS, ACT):
+            raise ValueError("action must be [n_envs, 5, 4]")
+        out = self._buf("value", (N, N_AGENTS, 1)) if out is None else out
+        self._check(self._lib.fp_critic_value(self._p, _ptr(ring), int(slot), int(ring.shape[-1]), N, _ptr(act), _ptr(out), _stream()),
+                    "fp_critic_value")
+        return out
 
     def _buf(self, name, shape):
         b = self._bufs.get(name)
@@ -155,11 +183,14 @@ class DeviceRollout:
             raise ValueError("replay must be a DeviceReplayBuffer(TRANSITION_FIELDS) holding at least record_envs rows")
         self.max_steps = int(max_steps)
         self.reset_done_each_step = bool(reset_done_each_step)
-        # value_fn(obs [R, 5, 144], action [R, 5, 4]) -> [R, 5, 1]: the critic (e.g. behaviour_net.value, maddpg.py:29-76).  When
-        # given, the Transition's value / next_value are filled as train_process does (model.py:217, :225-226: the critic on
-        # (state, action) and on (next_state, a SECOND sampled action from the policy with the new hidden state)); the learner's
-        # module runs in torch -- it is not part of this library -- and the second policy evaluation doubles k_policy's cost.
+        # value_fn: the critic behind the Transition's value / next_value, filled as train_process does (model.py:217, :225-226:
+        # the critic on (state, action) and on (next_state, a SECOND sampled action from the policy with the new hidden state;
+        # the second policy evaluation doubles k_policy's cost).  "native" = k_critic (tcgen05; policy.load_critic(...) holds the
+        # reference's MLPCritic), straight from the observation ring; or a callable (obs [R, 5, 144], action [R, 5, 4]) ->
+        # [R, 5, 1], e.g. behaviour_net.value (maddpg.py:29-76) as a torch module.
         self.value_fn = value_fn
+        if value_fn == "native" and not policy.has_critic:
+            raise ValueError('value_fn="native" needs the critic weights: policy.load_critic(MLPCritic.state_dict())')
         dev = env.device
         self._n_pad = (self.N + 31) // 32 * 32                      # the observation ring's padding (fp_obs_ring)
         # hidden states in the policy kernel's env-minor layout [5, 64, n_pad]; hidden() gives the reference's [N, 5, 64]
@@ -178,7 +209,8 @@ class DeviceRollout:
                 self._fptr[k] = p
             self._zeros = torch.zeros(self.R, N_AGENTS, device=dev)
             if value_fn is not None:
-                self._dense = torch.empty(self.R, N_AGENTS * OBS, device=dev)
+                if value_fn != "native":
+                    self._dense = torch.empty(self.R, N_AGENTS * OBS, device=dev)
                 self._hid_scratch = torch.empty(N_AGENTS, HID, self._n_pad, device=dev)
 
     def reset(self):
@@ -207,6 +239,13 @@ class DeviceRollout:
         self.policy.gather_windows(self.ring, self.R, self._dense, N_AGENTS * OBS, 0, self.R)
         return self._dense.view(self.R, N_AGENTS, OBS)
 
+    def _value(self, action, name):
+        """The critic on (the ring as it stands, action) for the recorded envs: [R, 5] fp32, contiguous."""
+        if self.value_fn == "native":
+            return self.policy.value(self.ring, action, out=self.policy._buf(name, (self.N, N_AGENTS, 1))).view(self.N, N_AGENTS)[:self.R]
+        with torch.no_grad():
+            return self.value_fn(self._dense_obs(), action[:self.R]).reshape(self.R, N_AGENTS).float().contiguous()
+
     def step(self, explore=True, eps=None, eps_next=None):
         if self.ring is None:
             self.reset()
@@ -220,9 +259,7 @@ class DeviceRollout:
             pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
             self._hidden_rows("last_hid", last_hid, pos, self._reset_mask)     # a restarted env's last_hid is the zero state it acted from
             if self.value_fn is not None:                                      # value = critic(state, action) (model.py:217)
-                with torch.no_grad():
-                    v = self.value_fn(self._dense_obs(), action[:self.R])
-                self._rows("value", v.reshape(self.R, N_AGENTS).float().contiguous(), pos)
+                self._rows("value", self._value(action, "value"), pos)
         # translate_action (:218) + env.step (:220) + get_obs (:223) in one launch
         reward, done, info, self.ring = env.step(action, translate=True, want_info=False, return_obs="ring")
         self.t += 1
@@ -233,9 +270,7 @@ class DeviceRollout:
             if self.value_fn is not None:   # next_value = critic(next_state, a second sampled action from the new hidden state) (model.py:225-226)
                 a2, _, _, _ = pol.act(self.ring, hid_in=hid, explore=explore, eps=eps_next, step=(1 << 40) + self.total_steps,
                                       hid_out=self._hid_scratch, hid_layout="env_minor", want_logp=False, out="action2")
-                with torch.no_grad():
-                    nv = self.value_fn(self._dense_obs(), a2[:self.R])
-                self._rows("next_value", nv.reshape(self.R, N_AGENTS).float().contiguous(), pos)
+                self._rows("next_value", self._value(a2, "next_value"), pos)
             # action, log_prob_a, reward per agent, done, last_step, action_avail (and value / next_value = 0 without a critic): one launch
             f = self._fptr
             pol._check(pol._lib.fp_policy_transition_tail(

@@ -209,14 +209,17 @@ def test_learner_batch_matches_reference_unpack_data(gold, cuda):
     pol.close(); buf.close()
 
 
-def test_rollout_matches_reference_train_process(cuda):
+@pytest.mark.parametrize("critic", ["torch", "native"])
+def test_rollout_matches_reference_train_process(cuda, critic):
     """End to end against the reference's own loop: tests/golden/ref_rollout.npz holds the 8 Transitions that
     Model.train_process (madrl/models/model.py:198-267) wrote into a TransReplayBuffer -- reference env (on the Pyomo
     stand-in), reference MADDPG / RNNAgent / select_action, the recorded exploration draws.  The device loop (tcgen05
     policy -> fused translate_action + step + get_obs) from the same start row, E0, reset actions, weights and draws
     must write the same Transition fields.  Tolerances: the policy differs from torch fp32 by ~1e-6 (fp32 arithmetic in a
     different order), which the env turns into ~1e-7 relative on setpoints and rewards; observations are fp32 here
-    and fp64 -> fp32 in the reference (prep_obs)."""
+    and fp64 -> fp32 in the reference (prep_obs).  value / next_value: the reference's own MLPCritic weights, either as a
+    torch module on the library's critic-input rows (2e-5) or through k_critic (critic="native": fc1 / fc2 held as TF32,
+    a weight perturbation of 2^-12 on 745-term rows: bound 1e-3, observed ~1e-4)."""
     from flexgpu import BatchedFlexProvisionEnv, Profiles
     from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS
     from flexgpu.predictor import DeviceReplayBuffer
@@ -238,7 +241,9 @@ def test_rollout_matches_reference_train_process(cuda):
         return F.linear(h, wc["fc3.weight"], wc["fc3.bias"]).view(obs.shape[0], 5, 1)
     prev_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
-    ro = DeviceRollout(env, pol, replay=buf, max_steps=T, value_fn=value_fn)
+    if critic == "native":
+        pol.load_critic({k[3:]: g[k] for k in g.files if k.startswith("wc_")})
+    ro = DeviceRollout(env, pol, replay=buf, max_steps=T, value_fn="native" if critic == "native" else value_fn)
     env.reset([0], g["e0"][None], g["a0"][None], return_obs=False)          # trainer.env.reset() (model.py:208) with the reference's draws
     assert np.max(np.abs(env.voltages[0].cpu().numpy() - g["V0"])) < 1e-8
     env._check(env._lib.fp_obs_ring_reset_push(env._h, None, None), "fp_obs_ring_reset_push")    # the get_obs inside reset() (:155)
@@ -252,7 +257,7 @@ def test_rollout_matches_reference_train_process(cuda):
     got = {k: v.cpu().numpy().astype(np.float64) for k, v in buf.get_batch(T, start=0).items()}
     torch.backends.cuda.matmul.allow_tf32 = prev_tf32
     tol = dict(state=2e-6, next_state=2e-6, action=5e-6, log_prob_a=2e-4, reward=None, done=0, last_step=0, action_avail=0,
-               last_hid=5e-6, hid=5e-6, value=2e-5, next_value=2e-5)
+               last_hid=5e-6, hid=5e-6, value=2e-5 if critic == "torch" else 1e-3, next_value=2e-5 if critic == "torch" else 1e-3)
     for k, bound in tol.items():
         want = g["tr_" + k]
         assert got[k].shape == want.shape, k
@@ -300,3 +305,54 @@ def test_rollout_resets_early_terminations_each_step(gold, cuda, profiles):
     assert float(prev["done"][5]) == 1.0 and float(prev["last_step"][40]) == 1.0 and float(prev["done"][6]) == 0.0
     assert int(env.steps[5]) == 2 and int(env.steps[6]) == 6
     pol.close(); buf.close(); env.close()
+
+
+def _critic_torch(w, obs_all, act_all, cuda):
+    """MADDPG.value (maddpg.py:29-76) + MLPCritic.forward (mlp_critic.py:27-36) in plain torch fp32 on [n, 720] observations
+    and [n, 20] actions: rows (env, agent i) = [obs of all agents | one-hot(i) | actions of all agents]."""
+    F = torch.nn.functional
+    n = obs_all.shape[0]
+    eye = torch.eye(5, device=cuda)
+    x = torch.cat([obs_all[:, None, :].expand(n, 5, 720), eye[None].expand(n, 5, 5), act_all[:, None, :].expand(n, 5, 20)], dim=-1).reshape(n * 5, 745)
+    y = F.linear(x, w["fc1.weight"], w["fc1.bias"])
+    y = torch.relu(F.layer_norm(y, (64,), w["layernorm.weight"], w["layernorm.bias"], 1e-5))
+    h = torch.relu(F.linear(y, w["fc2.weight"], w["fc2.bias"]))
+    return F.linear(h, w["fc3.weight"], w["fc3.bias"]).view(n, 5, 1)
+
+
+@pytest.mark.parametrize("n", [300, 40, 1, 2 * 148 * 128 + 77])
+def test_native_critic_matches_torch(cuda, n):
+    """fp_critic_value (k_critic, tcgen05) against plain torch fp32 with the same TF32-rounded fc1 / fc2 matrices (the
+    device holds them as TF32, activations keep fp32 accuracy; bound 2e-5, observed ~1e-6): the TMA path with a ragged last
+    tile, the LDGSTS path of rings narrower than a tile, a single env, and several tiles per CTA (weight blocks cycling
+    through their three buffers); three ring rotations."""
+    from flexgpu.policy import DevicePolicy, round_tf32
+    rng = np.random.default_rng(11)
+    sd = {"fc1.weight": rng.normal(0, 0.05, (64, 745)), "fc1.bias": rng.uniform(-0.04, 0.04, 64), "layernorm.weight": 1 + rng.normal(0, 0.1, 64),
+          "layernorm.bias": rng.normal(0, 0.1, 64), "fc2.weight": rng.uniform(-0.125, 0.125, (64, 64)), "fc2.bias": rng.uniform(-0.125, 0.125, 64),
+          "fc3.weight": rng.uniform(-0.125, 0.125, (1, 64)), "fc3.bias": rng.uniform(-0.125, 0.125, 1)}
+    sd = {k: v.astype(np.float32) for k, v in sd.items()}
+    pol = DevicePolicy(None, device=cuda)
+    pol.load_critic(sd)
+    w = {k: torch.from_numpy(v).to(cuda) for k, v in sd.items()}
+    w1 = sd["fc1.weight"].copy(); w1[:, :720] = round_tf32(w1[:, :720]); w1[:, 725:] = round_tf32(w1[:, 725:])
+    w["fc1.weight"] = torch.from_numpy(w1).to(cuda); w["fc2.weight"] = torch.from_numpy(round_tf32(sd["fc2.weight"])).to(cuda)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for slot in (0, 9, 23):
+            obs = torch.rand(n, 5, 144, device=cuda, generator=g) * 2 - 0.5
+            act = torch.tanh(torch.randn(n, 5, 4, device=cuda, generator=g))
+            n_pad = (n + 31) // 32 * 32
+            ring = torch.zeros(24, 5, 6, n_pad, device=cuda)
+            wv = obs.view(n, 5, 24, 6)
+            for r in range(24):
+                ring[(slot + 1 + r) % 24, :, :, :n] = wv[:, :, r, :].permute(1, 2, 0)
+            got = pol.value(ring.contiguous(), act, slot=slot, n_envs=n).clone()
+            want = _critic_torch(w, obs.reshape(n, 720), act.reshape(n, 20), cuda)
+            err = float((got - want).abs().max())
+            assert got.shape == (n, 5, 1) and err < 2e-5, (slot, err)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    pol.close()
