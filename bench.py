@@ -399,10 +399,14 @@ def main():
               "rnn.weight_hh": rngp.uniform(-0.125, 0.125, (192, 64)), "rnn.bias_ih": rngp.uniform(-0.125, 0.125, 192),
               "rnn.bias_hh": rngp.uniform(-0.125, 0.125, 192), "fc2.weight": rngp.normal(0, 0.1, (4, 64)), "fc2.bias": rngp.uniform(-0.125, 0.125, 4)}
         pol = DevicePolicy(sd, device=dev, std=1.0, seed=11 + rank)
+        # the critic of train_process's value / next_value (model.py:217, :225-226): the reference's MLPCritic, random init
+        pol.load_critic({"fc1.weight": rngp.normal(0, 0.05, (64, 745)), "fc1.bias": rngp.uniform(-0.04, 0.04, 64), "layernorm.weight": np.ones(64),
+                         "layernorm.bias": np.zeros(64), "fc2.weight": rngp.uniform(-0.125, 0.125, (64, 64)), "fc2.bias": rngp.uniform(-0.125, 0.125, 64),
+                         "fc3.weight": rngp.uniform(-0.125, 0.125, (1, 64)), "fc3.bias": rngp.uniform(-0.125, 0.125, 1)})
         rollout = {}
-        for label, rec in (("acting", 0), ("recording", E)):
+        for label, rec, vf in (("acting", 0, None), ("recording", E, None), ("critic", E, "native")):
             buf = DeviceReplayBuffer(2 * E, TRANSITION_FIELDS, device=dev) if rec else None
-            ro = DeviceRollout(env, pol, replay=buf, record_envs=rec)
+            ro = DeviceRollout(env, pol, replay=buf, record_envs=rec, value_fn=vf)
             ro.reset()
             for k in range(3):
                 ro.step()
@@ -521,11 +525,11 @@ def main():
 
     t = torch.tensor([dev_ms, e2e_s, kern_ms, obs_extra[1] if obs_extra else 0.0, strong[2] if strong else 0.0,
                       rollout["acting"][1] if rollout else 0.0, rollout["recording"][1] if rollout else 0.0,
-                      obs_extra[2] if obs_extra else 0.0],
+                      obs_extra[2] if obs_extra else 0.0, rollout["critic"][1] if rollout else 0.0],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, kern_ms, obs_ms, strong_ms, roll_ms, rollrec_ms, obs_ring_ms = (float(x) for x in t)
+    dev_ms, e2e_s, kern_ms, obs_ms, strong_ms, roll_ms, rollrec_ms, obs_ring_ms, rollcrit_ms = (float(x) for x in t)
     stats = env.episode_stats(reduce=True)                     # the one NCCL collective (16 doubles)
     total_envs = E * world
     value = total_envs * K / (dev_ms * 1e-3)
@@ -582,6 +586,10 @@ def main():
                                                           "ms_per_step": rollrec_ms / 30, "launches_per_step": rollout["recording"][2],
                                                           "bytes_per_transition": 4 * sum(TRANSITION_FIELDS.values()),
                                                           "recorded_envs_per_step": E},
+                               "with_critic": {"loop": "the whole train_process body (model.py:213-254): + value = critic(state, action) and next_value = "
+                                                       "critic(next_state, a second sampled action) through k_critic (MLPCritic on tcgen05), every transition written",
+                                               "env_steps_per_s": rollout["critic"][0] * world / (rollcrit_ms * 1e-3), "ms_per_step": rollcrit_ms / 30,
+                                               "launches_per_step": rollout["critic"][2]},
                                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "l2": "flushed before every step"}
         if strong is not None:
             line["config5_strong"] = {"workload": "fused_env_step_2^20_envs_total (BASELINE config 5, strong scaling: split over the run's GPUs)",
