@@ -347,6 +347,12 @@ int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const fl
 int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n_envs, const float* d_hid_in,
                   const uint8_t* d_reset, float* d_hid_out, int32_t hid_env_minor, float* d_mean, float* d_action, float* d_logp,
                   const float* d_eps, uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream);
+/* select_action alone, on the fc2 outputs a previous fp_policy_act stored in d_mean: another exploration draw of the SAME
+ * policy evaluation.  train_process evaluates the policy on (next_state, hid) for the next-value action (model.py:225) and
+ * again, on the same inputs, at the top of the next step (:215-216); with this the second evaluation is a re-draw
+ * (bit-identical to running fp_policy_act again with these draws). */
+int fp_policy_sample(FpPolicy* p, const float* d_mean, int64_t n_envs, float* d_action, float* d_logp, const float* d_eps,
+                     uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream);
 /* Transition fields (madrl/models/model.py:19, :230-242) straight into a replay ring: field rows (row0 + e) mod cap.
  *   fp_policy_gather_windows   state / next_state: the dense get_obs windows [5][144] of envs [0, n) from the ring
  *                              (pitch = floats per destination row, >= 720; row0 = 0, cap >= n: a dense tensor)

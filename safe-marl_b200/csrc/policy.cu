@@ -205,6 +205,61 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return copysignf(t, x);
 }
 
+// select_action (utils/util.py:50-64, continuous / action_enforcebound) of one (env, agent) row from its fc2 output m:
+// explore: x = m + std eps, action = tanh(x), log_prob = Normal(m, std).log_prob(x) - log(1 - action^2 + 1e-6), with eps from the
+// caller's array or Philox4x32-10 keyed by (seed; row, step) + Box-Muller; otherwise status 'test': action = tanh(m).
+__device__ __forceinline__ void select_action_row(const float (&m)[4], int64_t r_glob, int explore, const float* __restrict__ eps,
+                                                  uint64_t seed, uint64_t step, float std_, float log_std, float (&act)[4], float (&lp)[4]) {
+    if (explore) {
+        float z[4];
+        if (eps != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(eps) + r_glob);
+            z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
+        } else {                                                 // Philox4x32-10 keyed by the seed, counter = (row, step)
+            U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
+            ctr.z = (uint32_t)step; ctr.w = (uint32_t)(step >> 32);
+            const U4 rr = philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+            // Box-Muller on (0, 1] x [0, 1) uniforms
+            const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
+            const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
+            const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+            float s0, cs0, s1, cs1;
+            __sincosf(6.283185307179586f * u1, &s0, &cs0);
+            __sincosf(6.283185307179586f * u3, &s1, &cs1);
+            z[0] = ra * cs0; z[1] = ra * s0; z[2] = rb * cs1; z[3] = rb * s1;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x = fmaf(std_, z[i], m[i]);              // Normal(mean, std).rsample()
+            const float y = tanh_fast(x);
+            // Normal.log_prob(x) = -(x - mean)^2 / (2 var) - log(std) - log(sqrt(2 pi)), then the tanh correction
+            const float d = __fsub_rn(x, m[i]);
+            float l = -__fdividef(__fmul_rn(d, d), __fmul_rn(2.0f, __fmul_rn(std_, std_)));
+            l = __fsub_rn(__fsub_rn(l, log_std), 0.9189385332046727f);
+            lp[i] = __fsub_rn(l, __logf(__fadd_rn(__fsub_rn(1.0f, __fmul_rn(y, y)), 1e-6f)));
+            act[i] = y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { act[i] = tanh_fast(m[i]); lp[i] = 0.0f; }   // status == 'test' (util.py:82-85)
+    }
+}
+
+// select_action alone, from stored fc2 outputs (fp_policy_act's d_mean): a second draw for the same policy evaluation --
+// train_process evaluates the policy on (next_state, hid) for the next-value action (model.py:225) and AGAIN, on the same
+// inputs, at the top of the next step (:215-216); only the exploration draw differs.
+__global__ void k_sample(const float* __restrict__ mean, int64_t rows, int explore, const float* __restrict__ eps, uint64_t seed, uint64_t step,
+                         float std_, float log_std, float* __restrict__ action, float* __restrict__ logp) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(mean) + r);
+        const float m[4] = {t.x, t.y, t.z, t.w};
+        float act[4], lp[4];
+        select_action_row(m, r, explore, eps, seed, step, std_, log_std, act, lp);
+        reinterpret_cast<float4*>(action)[r] = make_float4(act[0], act[1], act[2], act[3]);
+        if (logp != nullptr) reinterpret_cast<float4*>(logp)[r] = make_float4(lp[0], lp[1], lp[2], lp[3]);
+    }
+}
+
 __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
@@ -438,39 +493,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                 }
                 if (prm.mean != nullptr) reinterpret_cast<float4*>(prm.mean)[r_glob] = make_float4(m[0], m[1], m[2], m[3]);
                 float act[4], lp[4];
-                if (prm.explore) {
-                    float z[4];
-                    if (prm.eps != nullptr) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(prm.eps) + r_glob);
-                        z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-                    } else {                                                 // Philox4x32-10 keyed by the seed, counter = (row, step)
-                        U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
-                        ctr.z = (uint32_t)prm.step; ctr.w = (uint32_t)(prm.step >> 32);
-                        const U4 rr = philox4x32_10(ctr, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
-                        // Box-Muller on (0, 1] x [0, 1) uniforms
-                        const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
-                        const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
-                        const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
-                        float s0, cs0, s1, cs1;
-                        __sincosf(6.283185307179586f * u1, &s0, &cs0);
-                        __sincosf(6.283185307179586f * u3, &s1, &cs1);
-                        z[0] = ra * cs0; z[1] = ra * s0; z[2] = rb * cs1; z[3] = rb * s1;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float x = fmaf(prm.std_, z[i], m[i]);          // Normal(mean, std).rsample()
-                        const float y = tanh_fast(x);
-                        // Normal.log_prob(x) = -(x - mean)^2 / (2 var) - log(std) - log(sqrt(2 pi)), then the tanh correction
-                        const float d = __fsub_rn(x, m[i]);
-                        float l = -__fdividef(__fmul_rn(d, d), __fmul_rn(2.0f, __fmul_rn(prm.std_, prm.std_)));
-                        l = __fsub_rn(__fsub_rn(l, prm.log_std), 0.9189385332046727f);
-                        lp[i] = __fsub_rn(l, __logf(__fadd_rn(__fsub_rn(1.0f, __fmul_rn(y, y)), 1e-6f)));
-                        act[i] = y;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { act[i] = tanh_fast(m[i]); lp[i] = 0.0f; }   // status == 'test' (util.py:82-85)
-                }
+                select_action_row(m, r_glob, prm.explore, prm.eps, prm.seed, prm.step, prm.std_, prm.log_std, act, lp);
                 reinterpret_cast<float4*>(prm.action)[r_glob] = make_float4(act[0], act[1], act[2], act[3]);
                 if (prm.logp != nullptr) reinterpret_cast<float4*>(prm.logp)[r_glob] = make_float4(lp[0], lp[1], lp[2], lp[3]);
             }
@@ -1104,6 +1127,22 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
     const int64_t tiles = (n_envs + POL_M - 1) / POL_M * POL_NA;
     const int grid = (int)(tiles < sms ? tiles : sms);
     k_policy<<<grid, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(prm, tmap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
+    p->launches++;
+    return FP_OK;
+}
+
+// select_action alone on stored fc2 outputs d_mean [n_envs][5][4] (fp_policy_act's d_mean): another exploration draw of the
+// same policy evaluation (same arguments as fp_policy_act's sampling part; bit-identical to re-running it with these draws).
+int fp_policy_sample(FpPolicy* p, const float* d_mean, int64_t n_envs, float* d_action, float* d_logp, const float* d_eps,
+                     uint64_t seed, uint64_t step, float std_, int32_t explore, void* stream) {
+    if (!p) return FP_EINVAL;
+    if (!d_mean || !d_action || n_envs < 1) return pfail(p, FP_EINVAL, "fp_policy_sample: bad arguments");
+    if (!(std_ > 0.0f)) return pfail(p, FP_EINVAL, "fp_policy_sample: std must be positive");
+    cudaSetDevice(p->device);
+    k_sample<<<grid_for(n_envs * POL_NA), 256, 0, (cudaStream_t)stream>>>(d_mean, n_envs * POL_NA, explore, d_eps, seed, step, std_, std::log(std_),
+                                                                          d_action, d_logp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;

@@ -125,7 +125,7 @@ class DevicePolicy:
         return b
 
     def act(self, ring, slot=None, n_envs=None, hid_in=None, reset=None, explore=True, eps=None, step=0, hid_out=None,
-            want_mean=False, want_logp=True, hid_layout="rows", out="action"):
+            want_mean=False, want_logp=True, hid_layout="rows", out="action", mean_out=None):
         """ring: an ObsRing (env.obs_ring() / step(..., return_obs='ring')) or a raw [24, 5, 6, n_pad] fp32 tensor with
         `slot` / `n_envs`.  Returns (action [N,5,4], log_prob [N,5,4] or None, hid, mean or None); the output
         tensors are reused by the next call unless hid_out is given (out: name of the reused action buffer).  hid_layout: "rows" = [N, 5, 64] (the reference's
@@ -136,7 +136,7 @@ class DevicePolicy:
         N = int(n_envs)
         action = self._buf(out, (N, N_AGENTS, ACT))
         logp = self._buf("logp", (N, N_AGENTS, ACT)) if want_logp else None
-        mean = self._buf("mean", (N, N_AGENTS, ACT)) if want_mean else None
+        mean = mean_out if mean_out is not None else (self._buf("mean", (N, N_AGENTS, ACT)) if want_mean else None)
         em = hid_layout == "env_minor"
         if em and (hid_out is None or tuple(hid_out.shape) != (N_AGENTS, HID, n_pad) or
                    (hid_in is not None and tuple(hid_in.shape) != (N_AGENTS, HID, n_pad))):
@@ -151,6 +151,17 @@ class DevicePolicy:
                                             1 if em else 0, _ptr(mean), _ptr(action), _ptr(logp), _ptr(e), self.seed, int(step),
                                             self.std, 1 if explore else 0, _stream()), "fp_policy_act")
         return action, logp, hid_out, mean
+
+    def sample(self, mean, explore=True, eps=None, step=0, want_logp=True, out="action"):
+        """select_action alone on stored fc2 outputs `mean` [N, 5, 4] (act(..., want_mean=True)): another exploration draw of
+        the same policy evaluation -- bit-identical to calling act() again on the same inputs with these draws."""
+        N = int(mean.shape[0])
+        action = self._buf(out, (N, N_AGENTS, ACT))
+        logp = self._buf("logp", (N, N_AGENTS, ACT)) if want_logp else None
+        e = None if eps is None else eps.to(device=self.device, dtype=torch.float32).contiguous()
+        self._check(self._lib.fp_policy_sample(self._p, _ptr(mean), N, _ptr(action), _ptr(logp), _ptr(e), self.seed, int(step),
+                                               self.std, 1 if explore else 0, _stream()), "fp_policy_sample")
+        return action, logp
 
     def gather_windows(self, ring, n, out, pitch, row0=0, cap=None):
         slot, ringt = ring.slot, ring.ring
@@ -198,6 +209,12 @@ class DeviceRollout:
         self._cur = 0
         self._reset_mask = None
         self._done_mask = None
+        # with a critic, the policy evaluation behind the next-value action (model.py:225: policy(next_state, hid)) IS the
+        # evaluation the next step starts with (:215-216: same observations, same hidden state) -- only the exploration draw
+        # differs.  Its fc2 outputs and new hidden state are kept, and the next step re-draws (fp_policy_sample) instead of
+        # running k_policy again, unless a reset intervened.  Same bits as evaluating twice.
+        self._mean2 = torch.empty(self.N, N_AGENTS, ACT, device=dev) if value_fn is not None else None
+        self._cache_valid = False
         self.t = 0                                  # step within the episode
         self.total_steps = 0
         self.ring = None
@@ -217,6 +234,7 @@ class DeviceRollout:
         self.ring = self.env.reset(return_obs="ring")              # state, _ = env.reset() (model.py:208)
         self._hid[self._cur].zero_()                                # init_hidden (model.py:211)
         self._reset_mask = None
+        self._cache_valid = False
         self.t = 0
         return self.ring
 
@@ -251,8 +269,14 @@ class DeviceRollout:
             self.reset()
         env, pol = self.env, self.policy
         last_hid, hid = self._hid[self._cur], self._hid[1 - self._cur]
-        action, logp, hid, _ = pol.act(self.ring, hid_in=last_hid, reset=self._reset_mask, explore=explore, eps=eps,
-                                       step=self.total_steps, hid_out=hid, hid_layout="env_minor")  # model.py:215-216
+        if self._cache_valid and self._reset_mask is None:          # evaluated already for the previous step's next-value action: re-draw
+            action, logp = pol.sample(self._mean2, explore=explore, eps=eps, step=self.total_steps)
+            self._hid[1 - self._cur], self._hid_scratch = self._hid_scratch, self._hid[1 - self._cur]
+            hid = self._hid[1 - self._cur]
+        else:
+            action, logp, hid, _ = pol.act(self.ring, hid_in=last_hid, reset=self._reset_mask, explore=explore, eps=eps,
+                                           step=self.total_steps, hid_out=hid, hid_layout="env_minor")  # model.py:215-216
+        self._cache_valid = False
         pos = None
         if self.R:
             pos = self.replay.reserve(self.R)
@@ -269,7 +293,9 @@ class DeviceRollout:
             self._hidden_rows("hid", hid, pos)
             if self.value_fn is not None:   # next_value = critic(next_state, a second sampled action from the new hidden state) (model.py:225-226)
                 a2, _, _, _ = pol.act(self.ring, hid_in=hid, explore=explore, eps=eps_next, step=(1 << 40) + self.total_steps,
-                                      hid_out=self._hid_scratch, hid_layout="env_minor", want_logp=False, out="action2")
+                                      hid_out=self._hid_scratch, hid_layout="env_minor", want_logp=False, out="action2",
+                                      mean_out=self._mean2)
+                self._cache_valid = True
                 self._rows("next_value", self._value(a2, "next_value"), pos)
             # action, log_prob_a, reward per agent, done, last_step, action_avail (and value / next_value = 0 without a critic): one launch
             f = self._fptr
