@@ -21,7 +21,8 @@
 //     P0  workers: 2xTF32 split of the observation block (x = hi + lo, hi TF32-exact)          -> TMEM cols [0, 288)
 //     M1  fc1:  acc1[128][64]  = (Xhi + Xlo) W1^T                  36 MMAs, K = 144                  cols [288, 352)
 //     E1  workers: + bias(agent), LayerNorm (four-thread reduction), ReLU, split -> A2; h_in split -> A3  [0, 256)
-//     M2  GRU:  rz[128][128] = A2 Wih_rz^T + A3 Whh_rz^T;  gi_n = A2 Wih_n^T;  gh_n = A3 Whh_n^T   64 MMAs  [256, 512)
+//     M2  GRU:  rz[128][128] = A2 Wih_rz^T + A3 Whh_rz^T;  gi_n = A2 Wih_n^T;  gh_n = A3 Whh_n^T  128 MMAs  [256, 512)
+//         issued in two column halves with a commit each (gate rows permuted by the loader): E2 starts on half 0
 //     E2  workers: r, z = sigmoid, n = tanh(gi_n + r gh_n), h' = (1 - z) n + z h -> global; fc2 (64 -> 4: 256 FMAs per
 //         row, on the CUDA cores in fp32 with the unrounded weights -- cheaper than a third tensor-core round trip),
 //         four-thread reduction, + bias, tanh-Normal sampling (Philox4x32-10 + Box-Muller, or caller-supplied eps)
@@ -58,7 +59,7 @@ constexpr uint32_t OFF_STAGE = OFF_VEC + V_FLOATS * 4;                     // [1
 constexpr uint32_t OFF_LN = OFF_STAGE + POL_OBS * POL_M * 4;               // [TPR][128 rows] float2 (sum, sum of squares)
 constexpr uint32_t OFF_FC = OFF_LN + TPR * POL_M * 8;                      // [TPR][128 rows] float4: fc2 partial sums
 constexpr uint32_t OFF_BAR = OFF_FC + TPR * POL_M * 16;                    // a_ready, mma_done, weights, x_full
-constexpr uint32_t OFF_TMEM = OFF_BAR + 32;
+constexpr uint32_t OFF_TMEM = OFF_BAR + 48;                                // (+ mma_done of the two column halves of the GRU GEMMs)
 constexpr uint32_t POL_SMEM = OFF_TMEM + 16;
 static_assert(POL_SMEM <= 227 * 1024, "policy kernel exceeds the shared memory of one SM");
 static_assert(OFF_STAGE % 128 == 0 && OFF_WG % 128 == 0 && OFF_VEC % 16 == 0 && (V_FLOATS * 4) % 16 == 0, "operand alignment");
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
     float2* lnp = reinterpret_cast<float2*>(smem + OFF_LN);
     float4* fcp = reinterpret_cast<float4*>(smem + OFF_FC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24;
+    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24, bar_q0 = bar_a + 32;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
     const int row = tid & (POL_M - 1), qt = (tid >> 7) & (TPR - 1);        // row of the tile, column quarter
     const int64_t n_blocks = (prm.n + POL_M - 1) / POL_M, n_tiles = n_blocks * POL_NA;
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
 
     if (tid == 0) {
         mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1); mbar_init(bar_x, 1);
+        mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (prm.use_tma && (int64_t)blockIdx.x < n_tiles) tma_request(blockIdx.x);
         mbar_expect_tx(bar_w, W1_BYTES + WG_BYTES + V_FLOATS * 4);          // weights: three bulk copies, one barrier
@@ -342,22 +344,30 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
             tc_fence_after();
             __syncwarp();
             if (elect_one()) {
+                // The GEMMs are issued in two COLUMN HALVES, each with its own commit: half h holds, for every worker
+                // thread of a row, the 8 hidden units of its chunk h (r | z columns adjacent, n-gate blocks alike: the
+                // loader permutes the gate rows), i.e. exactly what one trip of the GRU-cell loop below consumes.  The
+                // workers start chunk 0 -- bound by the SFUs -- while the tensor pipe still works on half 1, instead of
+                // waiting for all the MMAs.  Same MMA cycles (N = 64 / 32 instead of 128 / 64), twice the instructions.
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-                for (int ks = 0; ks < POL_HID / 8; ++ks) {
-                    const uint64_t d_rz_i = umma_desc(b_rz_ih + ks * 2 * (128 * 16), 128 * 16, 128);
-                    const uint64_t d_rz_h = umma_desc(b_rz_hh + ks * 2 * (128 * 16), 128 * 16, 128);
-                    const uint64_t d_n_i = umma_desc(b_n_ih + ks * 2 * (64 * 16), 64 * 16, 128);
-                    const uint64_t d_n_h = umma_desc(b_n_hh + ks * 2 * (64 * 16), 64 * 16, 128);
-                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A2HI + 8 * ks, d_rz_i, idesc_n(128), ks > 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A2LO + 8 * ks, d_rz_i, idesc_n(128), 1u);
-                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A3HI + 8 * ks, d_rz_h, idesc_n(128), 1u);
-                    umma_tf32_ts(tmem_base + C_RZ, tmem_base + C_A3LO + 8 * ks, d_rz_h, idesc_n(128), 1u);
-                    umma_tf32_ts(tmem_base + C_GIN, tmem_base + C_A2HI + 8 * ks, d_n_i, idesc_n(64), ks > 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_base + C_GIN, tmem_base + C_A2LO + 8 * ks, d_n_i, idesc_n(64), 1u);
-                    umma_tf32_ts(tmem_base + C_GHN, tmem_base + C_A3HI + 8 * ks, d_n_h, idesc_n(64), ks > 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_base + C_GHN, tmem_base + C_A3LO + 8 * ks, d_n_h, idesc_n(64), 1u);
+                    for (int ks = 0; ks < POL_HID / 8; ++ks) {
+                        const uint64_t d_rz_i = umma_desc(b_rz_ih + ks * 2 * (128 * 16) + hf * 64 * 16, 128 * 16, 128);
+                        const uint64_t d_rz_h = umma_desc(b_rz_hh + ks * 2 * (128 * 16) + hf * 64 * 16, 128 * 16, 128);
+                        const uint64_t d_n_i = umma_desc(b_n_ih + ks * 2 * (64 * 16) + hf * 32 * 16, 64 * 16, 128);
+                        const uint64_t d_n_h = umma_desc(b_n_hh + ks * 2 * (64 * 16) + hf * 32 * 16, 64 * 16, 128);
+                        umma_tf32_ts(tmem_base + C_RZ + 64 * hf, tmem_base + C_A2HI + 8 * ks, d_rz_i, idesc_n(64), ks > 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_base + C_RZ + 64 * hf, tmem_base + C_A2LO + 8 * ks, d_rz_i, idesc_n(64), 1u);
+                        umma_tf32_ts(tmem_base + C_RZ + 64 * hf, tmem_base + C_A3HI + 8 * ks, d_rz_h, idesc_n(64), 1u);
+                        umma_tf32_ts(tmem_base + C_RZ + 64 * hf, tmem_base + C_A3LO + 8 * ks, d_rz_h, idesc_n(64), 1u);
+                        umma_tf32_ts(tmem_base + C_GIN + 32 * hf, tmem_base + C_A2HI + 8 * ks, d_n_i, idesc_n(32), ks > 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_base + C_GIN + 32 * hf, tmem_base + C_A2LO + 8 * ks, d_n_i, idesc_n(32), 1u);
+                        umma_tf32_ts(tmem_base + C_GHN + 32 * hf, tmem_base + C_A3HI + 8 * ks, d_n_h, idesc_n(32), ks > 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_base + C_GHN + 32 * hf, tmem_base + C_A3LO + 8 * ks, d_n_h, idesc_n(32), 1u);
+                    }
+                    umma_commit(bar_q0 + 8 * hf);
                 }
-                umma_commit(bar_m);
             }
             __syncwarp();
         }
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
         // =============================================================== workers: four threads per row (column quarters)
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int c0 = CPT * qt;                                               // this thread's 16 hidden columns
-        uint32_t pm = 0, px = 0;
+        uint32_t pm = 0, px = 0, pq = 0;
         bool first = true;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int a = (int)(tile % POL_NA);
@@ -443,18 +453,18 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
             mbar_arrive(bar_a);
 
             // ---- E2: GRU cell (torch.nn.GRUCell: r, z, n gate order) -> h'; fc2 partial sums
-            mbar_wait(bar_m, pm); pm ^= 1u;
-            tc_fence_after();
             {
                 float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
 #pragma unroll
                 for (int hc = 0; hc < CPT / 8; ++hc) {                          // two chunks of 8 columns: half the live registers
                     const int cc = c0 + 8 * hc;
                     float rp[8], zp[8], gi[8], gh[8];
-                    tmem_ld8(lane_base + C_RZ + cc, rp);
-                    tmem_ld8(lane_base + C_RZ + 64 + cc, zp);
-                    tmem_ld8(lane_base + C_GIN + cc, gi);
-                    tmem_ld8(lane_base + C_GHN + cc, gh);
+                    mbar_wait(bar_q0 + 8 * hc, pq);                             // column half hc of the GRU GEMMs: [quarter][r8 | z8], [quarter][n8]
+                    tc_fence_after();
+                    tmem_ld8(lane_base + C_RZ + 64 * hc + 16 * qt, rp);
+                    tmem_ld8(lane_base + C_RZ + 64 * hc + 16 * qt + 8, zp);
+                    tmem_ld8(lane_base + C_GIN + 32 * hc + 8 * qt, gi);
+                    tmem_ld8(lane_base + C_GHN + 32 * hc + 8 * qt, gh);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -467,6 +477,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                         p2 = fmaf(hn, vec[V_W2 + 128 + cc + i], p2); p3 = fmaf(hn, vec[V_W2 + 192 + cc + i], p3);
                     }
                 }
+                pq ^= 1u;
                 fcp[qt * POL_M + row] = make_float4(p0, p1, p2, p3);
                 if (live && prm.hid_em) {
                     float* ho = prm.hid_out + (int64_t)(a * POL_HID + c0) * prm.n_pad + e;
@@ -1068,16 +1079,30 @@ int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const fl
                     W1[(size_t)q * POL_OBS * POL_HID + ((size_t)(k >> 2) * POL_HID + n) * 4 + (k & 3)] = round_tf32(fc1_w[(size_t)n * KIN + src]);
             }
         }
-    auto pack = [](std::vector<float>& dst, size_t off, const float* w, int row0, int rows, int npad) {   // w [.][64] rows row0 .. row0 + rows
-        for (int n = 0; n < rows; ++n)
-            for (int k = 0; k < POL_HID; ++k)
-                dst[off + ((size_t)(k >> 2) * npad + n) * 4 + (k & 3)] = round_tf32(w[(size_t)(row0 + n) * POL_HID + k]);
-    };
     std::vector<float> Wg(WG_BYTES / 4, 0.0f), vec(V_FLOATS, 0.0f);
-    pack(Wg, 0, w_ih, 0, 128, 128);
-    pack(Wg, WG_RZ_BYTES / 4, w_hh, 0, 128, 128);
-    pack(Wg, 2 * WG_RZ_BYTES / 4, w_ih, 128, 64, 64);
-    pack(Wg, 2 * WG_RZ_BYTES / 4 + WG_N_BYTES / 4, w_hh, 128, 64, 64);
+    {
+        // gate rows permuted so that a column half holds, per quarter q (= worker thread of the row), the 8 units of chunk h with
+        // their r and z outputs adjacent: rz packed row 64 h + 16 q + 8 g + j = gate row 64 g + 16 q + 8 h + j; n packed row
+        // 32 h + 8 q + j = n-gate row 16 q + 8 h + j
+        auto pack_rz = [](std::vector<float>& dst, size_t off, const float* w) {
+            for (int np = 0; np < 128; ++np) {
+                const int h = np >> 6, q = (np >> 4) & 3, g = (np >> 3) & 1, j = np & 7, n = 64 * g + 16 * q + 8 * h + j;
+                for (int k = 0; k < POL_HID; ++k)
+                    dst[off + ((size_t)(k >> 2) * 128 + np) * 4 + (k & 3)] = round_tf32(w[(size_t)n * POL_HID + k]);
+            }
+        };
+        auto pack_n = [](std::vector<float>& dst, size_t off, const float* w) {
+            for (int np = 0; np < 64; ++np) {
+                const int h = np >> 5, q = (np >> 3) & 3, j = np & 7, n = 128 + 16 * q + 8 * h + j;
+                for (int k = 0; k < POL_HID; ++k)
+                    dst[off + ((size_t)(k >> 2) * 64 + np) * 4 + (k & 3)] = round_tf32(w[(size_t)n * POL_HID + k]);
+            }
+        };
+        pack_rz(Wg, 0, w_ih);
+        pack_rz(Wg, WG_RZ_BYTES / 4, w_hh);
+        pack_n(Wg, 2 * WG_RZ_BYTES / 4, w_ih);
+        pack_n(Wg, 2 * WG_RZ_BYTES / 4 + WG_N_BYTES / 4, w_hh);
+    }
     for (int o = 0; o < POL_ACT; ++o)
         for (int k = 0; k < POL_HID; ++k) vec[V_W2 + o * POL_HID + k] = fc2_w[(size_t)o * POL_HID + k];      // fc2 runs in fp32: unrounded
     for (int a = 0; a < POL_NA; ++a)
