@@ -524,31 +524,42 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
 // i) is [all five agents' observations (720) | one-hot(i) (5) | all five agents' actions (20)]: only the one-hot differs
 // between the five rows of an env, so fc1 is evaluated ONCE per env on its 740 shared columns and the one-hot column is
 // folded into a per-agent bias.  A tile is 128 envs, input = the env-minor observation ring, untouched:
-//     for agent block a = 0..4:  TMA box [24][6][128] of agent a -> staging;  P0 split -> TMEM;  M1: acc1 += X_a Wc_a^T
-//         (36 k-steps x (hi, lo); the fc1 block of agent a -- ring rotation folded into the weights like k_policy's W1 --
-//         streams through a three-deep shared-memory buffer); block 0 also adds the actions' 20 columns (K padded to 24)
-//     for agent i = 0..4:  E1: acc1 + bias(i) -> LayerNorm -> ReLU -> split -> A2;  M2: acc2 = A2 W2^T;  E2: ReLU,
-//         dot with fc3 (fp32, CUDA cores), four-thread reduction, + bias -> value[env][i]
-// Phases are serial (workers <-> MMA warp through the same two mbarriers as k_policy); precision as k_policy: activations
-// two-term TF32 split, fc1 / fc2 matrices held as TF32, fc3 in fp32.
+//   fc1: ten HALF-BLOCKS per tile (agent a, ring slots 12 hf .. 12 hf + 11: K = 72).  A half-block is one TMA box [12][6][128]
+//        into one of three staging buffers (requested three half-blocks ahead: the HBM stream never waits for the workers)
+//        plus the matching half of agent a's fc1 block -- ring rotation folded into the weights like k_policy's W1 -- into
+//        one of four weight buffers (two ahead); the workers split it into one of two TMEM operand buffers while the MMAs
+//        of the previous half-block run (acc1 += X Wc^T: 9 k-steps x (hi, lo)); the first half-block also adds the actions'
+//        20 columns (K padded to 24)
+//   per agent i = 0..4: E1: acc1 + bias(i) -> LayerNorm -> ReLU -> split -> A2[i & 1];  M2: acc2[i & 1] = A2 W2^T;  E2: ReLU,
+//        dot with fc3 (fp32, CUDA cores), four-thread reduction, + bias -> value[env][i];  operand and accumulator are
+//        double-buffered: E1 of agent i + 1 runs under fc2 of agent i
+// Workers and the MMA warp meet through two mbarrier pairs (a_ready[b], mma_done[b], b = TMEM buffer); every commit is
+// awaited exactly once per worker, in order.  Precision as k_policy: activations two-term TF32 split, fc1 / fc2 matrices
+// held as TF32, fc3 in fp32.
+constexpr int CR_KH = POL_OBS / 2;                                           // K of a half-block: 72
+constexpr int CR_NST = 3, CR_NWB = 4;                                        // staging buffers, weight buffers in flight
+constexpr uint32_t CR_ST_BYTES = CR_KH * POL_M * 4;                          // [72][128] fp32 = 36 864
 constexpr uint32_t CR_WB_BYTES = W1_BYTES;                                   // one agent block of fc1: [36 kc][64 n][4]
-constexpr int CR_NWB = 3;                                                    // weight-block buffers in flight
+constexpr uint32_t CR_WH_BYTES = CR_WB_BYTES / 2;                            // ... and its half: [18 kc][64 n][4] = 18 432
 constexpr uint32_t CR_W2_BYTES = POL_HID * POL_HID * 4;                      // fc2: [16 kc][64 n][4]
 constexpr int CR_KACT = 24;                                                  // 20 action columns + 4 zero columns
 constexpr uint32_t CR_WA_BYTES = CR_KACT * POL_HID * 4;                      // [6 kc][64 n][4]
+constexpr int CR_HB = 2 * POL_NA;                                            // half-blocks per tile
 // small arrays (floats): b1a[5][64] (fc1.bias + the one-hot column of agent i), ln_g[64], ln_b[64], b2[64], w3[64], b3 (+ pad)
 constexpr int CV_B1A = 0, CV_LNG = 320, CV_LNB = 384, CV_B2 = 448, CV_W3 = 512, CV_B3 = 576, CV_FLOATS = 592;
-constexpr uint32_t CO_WB = 0, CO_W2 = CO_WB + CR_NWB * CR_WB_BYTES, CO_WA = CO_W2 + CR_W2_BYTES, CO_VEC = CO_WA + CR_WA_BYTES;
-constexpr uint32_t CO_STAGE = (CO_VEC + CV_FLOATS * 4 + 127) / 128 * 128;    // [144][128] fp32
-constexpr uint32_t CO_LN = CO_STAGE + POL_OBS * POL_M * 4;                   // [TPR][128 rows] float2
-constexpr uint32_t CO_FC = CO_LN + TPR * POL_M * 8;                          // [TPR][128 rows] float: fc3 partial sums
-constexpr uint32_t CO_BAR = CO_FC + TPR * POL_M * 4;                         // a_ready, mma_done, small arrays, x_full, wb[3]
-constexpr uint32_t CO_TMEM = CO_BAR + 64;
+constexpr uint32_t CO_ST = 0, CO_WB = CO_ST + CR_NST * CR_ST_BYTES, CO_W2 = CO_WB + CR_NWB * CR_WH_BYTES, CO_WA = CO_W2 + CR_W2_BYTES,
+                   CO_VEC = CO_WA + CR_WA_BYTES;
+constexpr uint32_t CO_LN = (CO_VEC + CV_FLOATS * 4 + 127) / 128 * 128;       // [2][TPR][128 rows] float2
+constexpr uint32_t CO_FC = CO_LN + 2 * TPR * POL_M * 8;                      // [2][TPR][128 rows] float: fc3 partial sums
+constexpr uint32_t CO_BAR = CO_FC + 2 * TPR * POL_M * 4;                     // a_ready[2], mma_done[2], small arrays, x_full[3], wb[4]
+constexpr uint32_t CO_TMEM = CO_BAR + 96;
 constexpr uint32_t CR_SMEM = CO_TMEM + 16;
 static_assert(CR_SMEM <= 227 * 1024, "critic kernel exceeds the shared memory of one SM");
-static_assert(CO_W2 % 128 == 0 && CO_WA % 128 == 0 && CO_VEC % 16 == 0 && CO_STAGE % 128 == 0, "operand alignment");
-// TMEM columns: X hi | lo (fc1 operand; A2 hi | lo of fc2 aliases its first 128 columns), acc1, acc2, actions hi | lo
-constexpr uint32_t CC_ACC1 = 288, CC_ACC2 = 352, CC_ACTHI = 416, CC_ACTLO = 440;
+static_assert(CO_WB % 128 == 0 && CO_W2 % 128 == 0 && CO_WA % 128 == 0 && CO_VEC % 16 == 0 && CO_BAR % 8 == 0, "operand alignment");
+// TMEM columns: operand buffer b at 144 b: hi [0, 72) | lo [72, 144) (fc2's operands A2[0] / A2[1] alias the buffers: hi at
+// +0, lo at +64), acc1, acc2[0], acc2[1] (the actions' operand of the first half-block aliases acc2[1])
+constexpr uint32_t CC_XB = 2 * CR_KH, CC_ACC1 = 288, CC_ACC2_0 = 352, CC_ACC2_1 = 416, CC_ACTHI = 416, CC_ACTLO = 440;
+static_assert(2 * CC_XB == CC_ACC1 && CC_XB + 128 <= CC_ACC1 && CC_ACC2_1 + 64 <= 512, "TMEM map");
 
 struct CritParams {
     const float* ring; int64_t n_pad; int64_t n; int32_t slot;
@@ -561,37 +572,40 @@ struct CritParams {
 __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const float* vec = reinterpret_cast<const float*>(smem + CO_VEC);
-    float* stage = reinterpret_cast<float*>(smem + CO_STAGE);
     float2* lnp = reinterpret_cast<float2*>(smem + CO_LN);
     float* fcp = reinterpret_cast<float*>(smem + CO_FC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + CO_TMEM);
-    const uint32_t bar_a = smem_u32(smem + CO_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24, bar_wb0 = bar_a + 32;
+    const uint32_t bar_a0 = smem_u32(smem + CO_BAR), bar_m0 = bar_a0 + 16, bar_w = bar_a0 + 32, bar_x0 = bar_a0 + 40, bar_wb0 = bar_a0 + 64;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
     const int row = tid & (POL_M - 1), qt = (tid >> 7) & (TPR - 1);
     const int64_t n_tiles = (prm.n + POL_M - 1) / POL_M;
     const int64_t n_my = (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t n_blocks = n_my * POL_NA;                                  // (tile, agent block) pairs of this CTA, in order
+    const int64_t n_hb = n_my * CR_HB;                                       // half-blocks of this CTA, in order: g = 10 tile + 2 a + hf
 
-    auto tile_of = [&](int64_t j) -> int64_t { return (int64_t)blockIdx.x + (j / POL_NA) * gridDim.x; };
-    auto tma_request = [&](int64_t j) {                                      // one thread: observation block j -> staging
-        mbar_expect_tx(bar_x, POL_OBS * POL_M * 4);
-        tma_load_box(smem_u32(stage), &tmap, (int32_t)(tile_of(j) * POL_M), (int32_t)(j % POL_NA) * POL_F, bar_x);
+    auto tile_of = [&](int64_t g) -> int64_t { return (int64_t)blockIdx.x + (g / CR_HB) * gridDim.x; };
+    auto tma_request = [&](int64_t g) {                                      // one thread: half-block g -> staging buffer g % 3
+        const uint32_t bar = bar_x0 + 8 * (uint32_t)(g % CR_NST);
+        const int a = (int)((g % CR_HB) >> 1), hf = (int)(g & 1);
+        mbar_expect_tx(bar, CR_ST_BYTES);
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(smem + CO_ST + (g % CR_NST) * CR_ST_BYTES)), "l"(&tmap), "r"((int32_t)(tile_of(g) * POL_M)), "r"(a * POL_F),
+                       "r"(hf * (POL_H / 2)), "r"(bar) : "memory");
     };
-    auto load_wb = [&](int64_t j) {                                          // one thread: fc1 block of agent j % 5 -> buffer j % 3
-        const uint32_t bar = bar_wb0 + 8 * (uint32_t)(j % CR_NWB);
-        mbar_expect_tx(bar, CR_WB_BYTES);
-        tma_load_1d(smem_u32(smem + CO_WB + (j % CR_NWB) * CR_WB_BYTES),
-                    prm.Wc1rot + ((size_t)prm.slot * POL_NA + (size_t)(j % POL_NA)) * (CR_WB_BYTES / 4), CR_WB_BYTES, bar);
+    auto load_wb = [&](int64_t g) {                                          // one thread: fc1 half-block weights -> buffer g % 4
+        const uint32_t bar = bar_wb0 + 8 * (uint32_t)(g % CR_NWB);
+        const size_t a = (size_t)((g % CR_HB) >> 1), hf = (size_t)(g & 1);
+        mbar_expect_tx(bar, CR_WH_BYTES);
+        tma_load_1d(smem_u32(smem + CO_WB + (g % CR_NWB) * CR_WH_BYTES),
+                    prm.Wc1rot + (((size_t)prm.slot * POL_NA + a) * 2 + hf) * (CR_WH_BYTES / 4), CR_WH_BYTES, bar);
     };
-    auto request = [&](int64_t j) {                                          // workers, rings narrower than a tile: LDGSTS
-        const int a = (int)(j % POL_NA);
-        const int64_t e0 = tile_of(j) * POL_M;
+    auto request = [&](int64_t g) {                                          // workers, rings narrower than a tile: LDGSTS, not pipelined
+        const int a = (int)((g % CR_HB) >> 1), hf = (int)(g & 1);
+        const int64_t e0 = tile_of(g) * POL_M;
+        float* stage = reinterpret_cast<float*>(smem + CO_ST + (g % CR_NST) * CR_ST_BYTES);
         const int c4 = (tid & 31) * 4;
         const bool inside = e0 + c4 + 4 <= prm.n_pad;
-#pragma unroll
-        for (int i = 0; i < POL_OBS * 32 / N_WORKERS; ++i) {
-            const int k = (tid >> 5) + (N_WORKERS / 32) * i;
-            const int sl = k / POL_F, f = k - sl * POL_F;
+        for (int k = tid >> 5; k < CR_KH; k += N_WORKERS / 32) {              // 16-byte chunks: 32 per row, one row per warp and trip
+            const int sl = hf * (POL_H / 2) + k / POL_F, f = k % POL_F;
             float* dst = stage + k * POL_M + c4;
             if (inside) cp_async16(dst, prm.ring + ((int64_t)(sl * POL_NA + a) * POL_F + f) * prm.n_pad + e0 + c4);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -600,14 +614,13 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
     };
 
     if (tid == 0) {
-        mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1); mbar_init(bar_x, 1);
+        mbar_init(bar_a0, N_WORKERS); mbar_init(bar_a0 + 8, N_WORKERS); mbar_init(bar_m0, 1); mbar_init(bar_m0 + 8, 1);
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < CR_NST; ++i) mbar_init(bar_x0 + 8 * i, 1);
         for (int i = 0; i < CR_NWB; ++i) mbar_init(bar_wb0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (n_blocks > 0) {
-            if (prm.use_tma) tma_request(0);
-            load_wb(0);
-            if (n_blocks > 1) load_wb(1);
-        }
+        for (int64_t g = 0; g < CR_NST && g < n_hb; ++g) if (prm.use_tma) tma_request(g);
+        for (int64_t g = 0; g < 2 && g < n_hb; ++g) load_wb(g);
         mbar_expect_tx(bar_w, CR_W2_BYTES + CR_WA_BYTES + CV_FLOATS * 4);    // fc2, action columns, small arrays: one barrier
         tma_load_1d(smem_u32(smem + CO_W2), prm.W2, CR_W2_BYTES, bar_w);
         tma_load_1d(smem_u32(smem + CO_WA), prm.Wa, CR_WA_BYTES, bar_w);
@@ -617,7 +630,6 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (!prm.use_tma && tid < N_WORKERS && n_blocks > 0) request(0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -626,29 +638,32 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
     if (warp == N_WORKERS / 32) {
         // =============================================================== MMA warp
         const uint32_t w2 = smem_u32(smem + CO_W2), wa = smem_u32(smem + CO_WA);
-        uint32_t pa = 0;
+        uint32_t pa0 = 0u, pa1 = 0u;                                        // phase parities of a_ready[0] / [1]
         bool first = true;
-        for (int64_t j = 0; j < n_blocks; ++j) {
-            const int a = (int)(j % POL_NA);
-            // ---- M1: fc1, agent block a (accumulating over the five blocks)
-            mbar_wait(bar_a, pa); pa ^= 1u;
-            mbar_wait(bar_wb0 + 8 * (uint32_t)(j % CR_NWB), (uint32_t)((j / CR_NWB) & 1));
+        for (int64_t g = 0; g < n_hb; ++g) {
+            const int hb = (int)(g % CR_HB), b = (int)(g & 1);
+            // ---- fc1, half-block g (K = 72; the tile's first one: + the actions)
+            if (b) { mbar_wait(bar_a0 + 8, pa1); pa1 ^= 1u; } else { mbar_wait(bar_a0, pa0); pa0 ^= 1u; }
+            mbar_wait(bar_wb0 + 8 * (uint32_t)(g % CR_NWB), (uint32_t)((g / CR_NWB) & 1));
             if (first) { mbar_wait(bar_w, 0u); first = false; }
             tc_fence_after();
             __syncwarp();
             if (elect_one()) {
-                // every worker has read the staging block, and fc1 of block j - 1 has completed (the workers waited for it
-                // before this P0): the next observation block and the weights of block j + 2 (buffer of block j - 1) may travel
-                if (prm.use_tma && j + 1 < n_blocks) tma_request(j + 1);
-                if (j + 2 < n_blocks) load_wb(j + 2);
-                const uint32_t wb = smem_u32(smem + CO_WB + (j % CR_NWB) * CR_WB_BYTES);
+                // every worker has read staging buffer g % 3, and the MMAs of half-block g - 2 have completed (the workers waited
+                // for them before writing this operand buffer): half-block g + 3 and the weights of g + 2 may travel
+                if (prm.use_tma && g + CR_NST < n_hb) tma_request(g + CR_NST);
+                if (g + 2 < n_hb) load_wb(g + 2);
+                const uint32_t wb = smem_u32(smem + CO_WB + (g % CR_NWB) * CR_WH_BYTES), xb = tmem_base + CC_XB * b;
+                // one descriptor per half-block: a k-step advances its 16-byte-granular start address by a constant (the address
+                // field cannot carry: shared memory ends far below 2^18)
+                const uint64_t d0 = umma_desc(wb, 64 * 16, 128);
 #pragma unroll
-                for (int ks = 0; ks < POL_OBS / 8; ++ks) {
-                    const uint64_t db = umma_desc(wb + ks * 2 * (64 * 16), 64 * 16, 128);
-                    umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + C_XHI + 8 * ks, db, idesc_n(64), (a > 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + C_XLO + 8 * ks, db, idesc_n(64), 1u);
+                for (int ks = 0; ks < CR_KH / 8; ++ks) {
+                    const uint64_t db = d0 + (uint64_t)((ks * 2 * (64 * 16)) >> 4);
+                    umma_tf32_ts(tmem_base + CC_ACC1, xb + 8 * ks, db, idesc_n(64), (hb > 0 || ks > 0) ? 1u : 0u);
+                    umma_tf32_ts(tmem_base + CC_ACC1, xb + CR_KH + 8 * ks, db, idesc_n(64), 1u);
                 }
-                if (a == 0) {
+                if (hb == 0) {
 #pragma unroll
                     for (int ks = 0; ks < CR_KACT / 8; ++ks) {
                         const uint64_t db = umma_desc(wa + ks * 2 * (64 * 16), 64 * 16, 128);
@@ -656,23 +671,25 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
                         umma_tf32_ts(tmem_base + CC_ACC1, tmem_base + CC_ACTLO + 8 * ks, db, idesc_n(64), 1u);
                     }
                 }
-                umma_commit(bar_m);
+                umma_commit(bar_m0 + 8 * b);
             }
             __syncwarp();
-            if (a != POL_NA - 1) continue;
-            // ---- M2: fc2, once per agent row
+            if (hb != CR_HB - 1) continue;
+            // ---- fc2, once per agent row, operand / accumulator buffer i & 1
             for (int i = 0; i < POL_NA; ++i) {
-                mbar_wait(bar_a, pa); pa ^= 1u;
+                const int bi = i & 1;
+                if (bi) { mbar_wait(bar_a0 + 8, pa1); pa1 ^= 1u; } else { mbar_wait(bar_a0, pa0); pa0 ^= 1u; }
                 tc_fence_after();
                 __syncwarp();
                 if (elect_one()) {
+                    const uint32_t a2 = tmem_base + CC_XB * bi, acc = tmem_base + (bi ? CC_ACC2_1 : CC_ACC2_0);
 #pragma unroll
                     for (int ks = 0; ks < POL_HID / 8; ++ks) {
                         const uint64_t db = umma_desc(w2 + ks * 2 * (64 * 16), 64 * 16, 128);
-                        umma_tf32_ts(tmem_base + CC_ACC2, tmem_base + C_A2HI + 8 * ks, db, idesc_n(64), ks > 0 ? 1u : 0u);
-                        umma_tf32_ts(tmem_base + CC_ACC2, tmem_base + C_A2LO + 8 * ks, db, idesc_n(64), 1u);
+                        umma_tf32_ts(acc, a2 + 8 * ks, db, idesc_n(64), ks > 0 ? 1u : 0u);
+                        umma_tf32_ts(acc, a2 + 64 + 8 * ks, db, idesc_n(64), 1u);
                     }
-                    umma_commit(bar_m);
+                    umma_commit(bar_m0 + 8 * bi);
                 }
                 __syncwarp();
             }
@@ -681,24 +698,30 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
         // =============================================================== workers: four threads per env row (column quarters)
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int c0 = CPT * qt;
-        constexpr int KQ = POL_OBS / TPR;                                       // observation inputs per thread and block: 36
-        uint32_t pm = 0, px = 0;
+        uint32_t pm0 = 0u, pm1 = 0u;                                            // phase parities of mma_done[0] / [1]
         bool first = true;
-        for (int64_t j = 0; j < n_blocks; ++j) {
-            const int a = (int)(j % POL_NA);
-            const int64_t e = tile_of(j) * POL_M + row;
+        for (int64_t g = 0; g < n_hb; ++g) {
+            const int hb = (int)(g % CR_HB), b = (int)(g & 1);
+            const int64_t e = tile_of(g) * POL_M + row;
             const bool live = e < prm.n;
-            // ---- P0: observation block of agent a -> TMEM (fc1 of the previous block has completed: every worker waited)
-            if (prm.use_tma) { mbar_wait(bar_x, px); px ^= 1u; }
-            else cp_async_wait_all();
-            group_sync<1, N_WORKERS>();
+            const float* stage = reinterpret_cast<const float*>(smem + CO_ST + (g % CR_NST) * CR_ST_BYTES);
+            // ---- P0: half-block g -> TMEM operand buffer b
+            if (prm.use_tma) mbar_wait(bar_x0 + 8 * (uint32_t)(g % CR_NST), (uint32_t)((g / CR_NST) & 1));
+            else { request(g); cp_async_wait_all(); group_sync<1, N_WORKERS>(); }
+            if (hb >= 2) { if (b) { mbar_wait(bar_m0 + 8, pm1); pm1 ^= 1u; } else { mbar_wait(bar_m0, pm0); pm0 ^= 1u; } tc_fence_after(); }   // the MMAs of half-block g - 2 have read this buffer
+            const uint32_t xhi = CC_XB * b, xlo = xhi + CR_KH;
 #pragma unroll
-            for (int c = 0; c < KQ / 4; ++c) {
-                const int k0 = KQ * qt + 4 * c;
-                split_st4(lane_base, C_XHI + k0, C_XLO + k0, stage[(k0 + 0) * POL_M + row], stage[(k0 + 1) * POL_M + row],
+            for (int c = 0; c < 4; ++c) {                                       // K [0, 64): chunks of 16, four per thread
+                const int k0 = 16 * c + 4 * qt;
+                split_st4(lane_base, xhi + k0, xlo + k0, stage[(k0 + 0) * POL_M + row], stage[(k0 + 1) * POL_M + row],
                           stage[(k0 + 2) * POL_M + row], stage[(k0 + 3) * POL_M + row]);
             }
-            if (a == 0 && qt < 3) {                                             // the env's 20 action values (+ 4 zero columns): 8 per thread
+            if (qt < 2) {                                                       // K [64, 72)
+                const int k0 = 64 + 4 * qt;
+                split_st4(lane_base, xhi + k0, xlo + k0, stage[(k0 + 0) * POL_M + row], stage[(k0 + 1) * POL_M + row],
+                          stage[(k0 + 2) * POL_M + row], stage[(k0 + 3) * POL_M + row]);
+            }
+            if (hb == 0 && qt < 3) {                                            // the env's 20 action values (+ 4 zero columns): 8 per thread
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -710,30 +733,29 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_a);
-            if (!prm.use_tma) {
-                group_sync<1, N_WORKERS>();                                     // every thread has read the staging block
-                if (j + 1 < n_blocks) request(j + 1);
-            }
-            if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small arrays have landed
-            mbar_wait(bar_m, pm); pm ^= 1u;                                     // fc1 of this block has completed
-            tc_fence_after();
-            if (a != POL_NA - 1) continue;
+            mbar_arrive(bar_a0 + 8 * b);
+            if (!prm.use_tma) group_sync<1, N_WORKERS>();                       // every thread has read the staging buffer (LDGSTS path refills it)
+            if (hb != CR_HB - 1) continue;
 
-            // ---- per agent row: E1 (bias, LayerNorm, ReLU) -> M2 (fc2) -> E2 (ReLU, fc3)
+            // ---- per agent row: E1 (bias, LayerNorm, ReLU -> A2[i & 1]) | fc2 | E2 (ReLU, fc3); E1 of agent i + 1 runs under fc2 of agent i
+            if (first) { mbar_wait(bar_w, 0u); first = false; }                 // the small arrays have landed
+            mbar_wait(bar_m0, pm0); pm0 ^= 1u;                              // fc1 is complete: the tile's last two half-blocks
+            mbar_wait(bar_m0 + 8, pm1); pm1 ^= 1u;
+            tc_fence_after();
             float y1[CPT];
             tmem_ld16(lane_base + CC_ACC1 + c0, y1);
             tmem_wait_ld();
-            for (int i = 0; i < POL_NA; ++i) {
+            auto e1 = [&](int i) {
                 float v[CPT];
                 float s = 0.0f, ss = 0.0f;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) { v[c] = __fadd_rn(y1[c], vec[CV_B1A + i * POL_HID + c0 + c]); s = __fadd_rn(s, v[c]); ss = fmaf(v[c], v[c], ss); }
-                lnp[qt * POL_M + row] = make_float2(s, ss);
+                float2* ln = lnp + (i & 1) * (TPR * POL_M);
+                ln[qt * POL_M + row] = make_float2(s, ss);
                 group_sync<1, N_WORKERS>();
                 float S = 0.0f, SS = 0.0f;
 #pragma unroll
-                for (int q4 = 0; q4 < TPR; ++q4) { const float2 t = lnp[q4 * POL_M + row]; S = __fadd_rn(S, t.x); SS = __fadd_rn(SS, t.y); }
+                for (int q4 = 0; q4 < TPR; ++q4) { const float2 t = ln[q4 * POL_M + row]; S = __fadd_rn(S, t.x); SS = __fadd_rn(SS, t.y); }
                 const float mean = __fmul_rn(S, 1.0f / POL_HID);
                 const float var = fmaxf(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
                 const float rstd = rsqrtf(__fadd_rn(var, 1e-5f));
@@ -742,25 +764,32 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
                     const float t = fmaf(__fmul_rn(__fsub_rn(v[c], mean), rstd), vec[CV_LNG + c0 + c], vec[CV_LNB + c0 + c]);
                     v[c] = fmaxf(t, 0.0f);                                       // hid_activation = relu
                 }
+                const uint32_t a2 = CC_XB * (i & 1);
 #pragma unroll
                 for (int c = 0; c < CPT / 4; ++c)
-                    split_st4(lane_base, C_A2HI + c0 + 4 * c, C_A2LO + c0 + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    split_st4(lane_base, a2 + c0 + 4 * c, a2 + 64 + c0 + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(bar_a);
-                mbar_wait(bar_m, pm); pm ^= 1u;
+                mbar_arrive(bar_a0 + 8 * (i & 1));
+            };
+            e1(0);
+            for (int i = 0; i < POL_NA; ++i) {
+                const int bi = i & 1;
+                if (i + 1 < POL_NA) e1(i + 1);                                  // (its operand buffer was released by E2 of agent i - 1)
+                if (bi) { mbar_wait(bar_m0 + 8, pm1); pm1 ^= 1u; } else { mbar_wait(bar_m0, pm0); pm0 ^= 1u; }
                 tc_fence_after();
                 float u[CPT];
-                tmem_ld16(lane_base + CC_ACC2 + c0, u);
+                tmem_ld16(lane_base + (bi ? CC_ACC2_1 : CC_ACC2_0) + c0, u);
                 tmem_wait_ld();
                 float part = 0.0f;
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) part = fmaf(fmaxf(__fadd_rn(u[c], vec[CV_B2 + c0 + c]), 0.0f), vec[CV_W3 + c0 + c], part);
-                fcp[qt * POL_M + row] = part;
+                float* fc = fcp + bi * (TPR * POL_M);
+                fc[qt * POL_M + row] = part;
                 tc_fence_before();
                 group_sync<1, N_WORKERS>();
                 if (qt == 0 && live)
-                    prm.value[e * POL_NA + i] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fcp[row], fcp[POL_M + row]), fcp[2 * POL_M + row]), fcp[3 * POL_M + row]), vec[CV_B3]);
+                    prm.value[e * POL_NA + i] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fc[row], fc[POL_M + row]), fc[2 * POL_M + row]), fc[3 * POL_M + row]), vec[CV_B3]);
             }
         }
     }
@@ -1014,7 +1043,8 @@ int pfail(FpPolicy* p, int code, const std::string& msg) {
 
 // The ring as a 3-D tensor [24 slots][30 = agent x feature][n_pad envs] (innermost first); a tile is the box [24][6][128] at
 // (env block, agent * 6, 0); envs past n_pad read as zeros.  Rings narrower than a tile: *use_tma = 0 (LDGSTS path).
-static int ring_tensor_map(FpPolicy* p, const float* d_ring, int64_t n_pad, CUtensorMap* tmap, int32_t* use_tma, const char* who) {
+static int ring_tensor_map(FpPolicy* p, const float* d_ring, int64_t n_pad, CUtensorMap* tmap, int32_t* use_tma, const char* who,
+                           int box_slots = POL_H) {
     std::memset(tmap, 0, sizeof(*tmap));
     *use_tma = 0;
     if (n_pad >= POL_M && ((uintptr_t)d_ring & 15) == 0) {
@@ -1022,7 +1052,7 @@ static int ring_tensor_map(FpPolicy* p, const float* d_ring, int64_t n_pad, CUte
         if (!enc) return pfail(p, FP_ECUDA, std::string(who) + ": cuTensorMapEncodeTiled is not available from this driver");
         const cuuint64_t gdim[3] = {(cuuint64_t)n_pad, (cuuint64_t)(POL_NA * POL_F), (cuuint64_t)POL_H};
         const cuuint64_t gstride[2] = {(cuuint64_t)n_pad * 4, (cuuint64_t)n_pad * 4 * (POL_NA * POL_F)};
-        const cuuint32_t box[3] = {POL_M, POL_F, POL_H}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {POL_M, POL_F, (cuuint32_t)box_slots}, estr[3] = {1, 1, 1};
         const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_ring), gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1312,7 +1342,7 @@ int fp_critic_value(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pa
     prm.Wc1rot = p->d_Wc1rot; prm.W2 = p->d_Wc2; prm.Wa = p->d_Wca; prm.vec = p->d_cvec;
     prm.actions = d_actions; prm.value = d_value;
     alignas(64) CUtensorMap tmap;
-    { const int rc = ring_tensor_map(p, d_ring, n_pad, &tmap, &prm.use_tma, "fp_critic_value"); if (rc != FP_OK) return rc; }
+    { const int rc = ring_tensor_map(p, d_ring, n_pad, &tmap, &prm.use_tma, "fp_critic_value", POL_H / 2); if (rc != FP_OK) return rc; }   // half-block boxes
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const int64_t tiles = (n_envs + POL_M - 1) / POL_M;
