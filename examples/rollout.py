@@ -9,7 +9,8 @@ The policy is the reference's shared-parameter RNNAgent (madrl/agents/rnn_agent.
 kernel straight from the env's observation ring; pass --weights model.pt (a checkpoint written by train_agent.py:
 {"model_state_dict": ...}, train_agent.py:144-147) or let the script initialise it like the reference does
 (init_std 0.1).  With --record N the Transition fields (model.py:230-242) of the first N envs go into a device replay
-ring, from which `learner_batch` hands the learner the unpack_data tensors.
+ring, from which `learner_batch` hands the learner the unpack_data tensors; with --critic the Transition's value /
+next_value are filled by the reference's MLPCritic on the tcgen05 critic kernel (MADDPG.value, model.py:217, :225-226).
 """
 import argparse
 import os
@@ -35,12 +36,22 @@ def reference_init(seed=0):
             "rnn.bias_hh": u((192,), 0.125), "fc2.weight": torch.randn(4, 64, generator=g) * 0.1, "fc2.bias": u((4,), 0.125)}
 
 
+def reference_critic_init(seed=1):
+    """MLPCritic weights (madrl/critics/mlp_critic.py, input 745) initialised like reference_init."""
+    g = torch.Generator().manual_seed(seed)
+    u = lambda shape, k: (torch.rand(shape, generator=g) * 2 - 1) * k
+    return {"fc1.weight": torch.randn(64, 745, generator=g) * 0.1, "fc1.bias": u((64,), 745 ** -0.5), "layernorm.weight": torch.ones(64),
+            "layernorm.bias": torch.zeros(64), "fc2.weight": torch.randn(64, 64, generator=g) * 0.1, "fc2.bias": u((64,), 0.125),
+            "fc3.weight": torch.randn(1, 64, generator=g) * 0.1, "fc3.bias": u((1,), 0.125)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=65536, help="total environments over all ranks")
     ap.add_argument("--steps", type=int, default=95)
     ap.add_argument("--weights", default=None, help="checkpoint with the policy's state_dict (policy_dicts.0.* keys)")
     ap.add_argument("--record", type=int, default=1024, help="envs per rank whose transitions go into the device replay ring")
+    ap.add_argument("--critic", action="store_true", help="fill value / next_value with the critic kernel (value_dicts.0.* of --weights, or the reference's initialisation)")
     args = ap.parse_args()
     from flexgpu.policy import DevicePolicy, DeviceRollout, TRANSITION_FIELDS, learner_batch
     from flexgpu.predictor import DeviceReplayBuffer
@@ -53,15 +64,18 @@ def main():
     offset, count = sharding.shard(args.envs, rank, world)             # env index range of this rank
     env = BatchedFlexProvisionEnv(None, n_envs=count, device=dev, seed=0, env_offset=offset)
     if args.weights:
-        sd = torch.load(args.weights, map_location="cpu")
-        sd = sd.get("model_state_dict", sd)
-        sd = {k.split("policy_dicts.0.", 1)[1]: v for k, v in sd.items() if k.startswith("policy_dicts.0.")} or sd
+        ckpt = torch.load(args.weights, map_location="cpu")
+        ckpt = ckpt.get("model_state_dict", ckpt)
+        sd = {k.split("policy_dicts.0.", 1)[1]: v for k, v in ckpt.items() if k.startswith("policy_dicts.0.")} or ckpt
+        csd = {k.split("value_dicts.0.", 1)[1]: v for k, v in ckpt.items() if k.startswith("value_dicts.0.")} or reference_critic_init()
     else:
-        sd = reference_init()
+        sd, csd = reference_init(), reference_critic_init()
     policy = DevicePolicy(sd, device=dev, std=1.0, seed=1 + rank)      # fixed_policy_std 1.0 (default.yaml)
+    if args.critic:
+        policy.load_critic(csd)
     rec = min(args.record, count)
     replay = DeviceReplayBuffer(max(rec * 8, 5000), TRANSITION_FIELDS, device=dev) if rec else None    # replay_buffer_size 5000
-    rollout = DeviceRollout(env, policy, replay=replay, record_envs=rec)
+    rollout = DeviceRollout(env, policy, replay=replay, record_envs=rec, value_fn="native" if (args.critic and rec) else None)
     rollout.reset()                                                    # env.reset() + init_hidden (model.py:208-211)
     rollout.step()                                                     # warm-up: allocations, module load
     env.episode_stats(reset=True)
