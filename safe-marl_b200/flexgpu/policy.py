@@ -260,7 +260,8 @@ class DeviceRollout:
     def _value(self, action, name):
         """The critic on (the ring as it stands, action) for the recorded envs: [R, 5] fp32, contiguous."""
         if self.value_fn == "native":
-            return self.policy.value(self.ring, action, out=self.policy._buf(name, (self.N, N_AGENTS, 1))).view(self.N, N_AGENTS)[:self.R]
+            out = self.policy._buf(name, (self.R, N_AGENTS, 1))              # the recorded envs only
+            return self.policy.value(self.ring.ring, action[:self.R], slot=self.ring.slot, n_envs=self.R, out=out).view(self.R, N_AGENTS)
         with torch.no_grad():
             return self.value_fn(self._dense_obs(), action[:self.R]).reshape(self.R, N_AGENTS).float().contiguous()
 
