@@ -362,6 +362,10 @@ int fp_policy_sample(FpPolicy* p, const float* d_mean, int64_t n_envs, float* d_
  *   fp_policy_transition_tail  ONE launch for all the small fields of a step (model.py:230-242): action, log_prob_a (NULL:
  *                              skipped), reward per agent, done, last_step, action_avail (NULL: skipped) and -- zero_values
  *                              != 0 -- value / next_value as zeros (MADDPG's losses recompute both, maddpg.py:104-107) */
+/* One-shot sink for the NEXT fp_policy_act: its writer warps copy the dense get_obs windows of envs [0, n) -- the blocks the
+ * kernel stages anyway -- into rows (row0 + e) mod cap of pitch `pitch` floats (16-byte aligned field, pitch a multiple of 4):
+ * the Transition's `state` without a separate pass over the ring.  Needs n_pad >= 128. */
+int fp_policy_state_sink(FpPolicy* p, float* d_field, int64_t pitch, int64_t row0, int64_t cap, int64_t n);
 int fp_policy_gather_windows(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad, int64_t n, float* d_out,
                              int64_t pitch, int64_t row0, int64_t cap, void* stream);
 int fp_policy_hidden_to_ring(FpPolicy* p, const float* d_hid_em, int64_t n_pad, int64_t n, float* d_field, int64_t row0,

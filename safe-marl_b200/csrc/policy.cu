@@ -46,7 +46,10 @@ constexpr int POL_M = 128;                 // rows per tile = envs of one agent
 constexpr int POL_OBS = 144, POL_HID = 64, POL_ACT = 4, POL_NA = 5, POL_H = 24, POL_F = 6;
 constexpr int TPR = 4;                     // worker threads per row (column quarters)
 constexpr int N_WORKERS = TPR * POL_M;     // 512
-constexpr int POL_THREADS = N_WORKERS + 32;
+constexpr int N_WRITERS = 96;               // k_policy: three warps that copy the tile's observation block into the Transition's `state` rows
+                                            // (640 threads = five allocation groups of four warps: 96 registers per thread stay available)
+constexpr int CRIT_THREADS = N_WORKERS + 32;
+constexpr int POL_THREADS = N_WORKERS + 32 + N_WRITERS;
 constexpr int CPT = POL_HID / TPR;         // hidden columns per thread: 16
 constexpr int KPT = POL_OBS / TPR;         // observation inputs per thread: 36
 constexpr uint32_t W1_BYTES = POL_OBS * POL_HID * 4;                       // 36 864: [36 kc][64 n][4]
@@ -59,7 +62,7 @@ constexpr uint32_t OFF_STAGE = OFF_VEC + V_FLOATS * 4;                     // [1
 constexpr uint32_t OFF_LN = OFF_STAGE + POL_OBS * POL_M * 4;               // [TPR][128 rows] float2 (sum, sum of squares)
 constexpr uint32_t OFF_FC = OFF_LN + TPR * POL_M * 8;                      // [TPR][128 rows] float4: fc2 partial sums
 constexpr uint32_t OFF_BAR = OFF_FC + TPR * POL_M * 16;                    // a_ready, mma_done, weights, x_full
-constexpr uint32_t OFF_TMEM = OFF_BAR + 48;                                // (+ mma_done of the two column halves of the GRU GEMMs)
+constexpr uint32_t OFF_TMEM = OFF_BAR + 56;                                // (+ mma_done of the two column halves of the GRU GEMMs, stage_copied)
 constexpr uint32_t POL_SMEM = OFF_TMEM + 16;
 static_assert(POL_SMEM <= 227 * 1024, "policy kernel exceeds the shared memory of one SM");
 static_assert(OFF_STAGE % 128 == 0 && OFF_WG % 128 == 0 && OFF_VEC % 16 == 0 && (V_FLOATS * 4) % 16 == 0, "operand alignment");
@@ -76,6 +79,9 @@ struct PolParams {
     const float* eps;                                                 // optional caller-supplied N(0,1) draws [n][5][4]
     uint64_t seed; uint64_t step; float std_; float log_std; int32_t explore;
     int32_t use_tma;                                                  // observation blocks by one 3-D TMA box copy per tile
+    // optional sink for the Transition's `state` (model.py:230-237): the dense get_obs windows [5][144] of envs [0, st_n) go to
+    // rows (st_row0 + e) mod st_cap of pitch st_pitch floats, written by the writer warps from the staged block (TMA path only)
+    float* st_out; int64_t st_pitch, st_row0, st_cap, st_n;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -268,9 +274,10 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
     float2* lnp = reinterpret_cast<float2*>(smem + OFF_LN);
     float4* fcp = reinterpret_cast<float4*>(smem + OFF_FC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24, bar_q0 = bar_a + 32;
+    const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24, bar_q0 = bar_a + 32, bar_s = bar_a + 48;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
     const int row = tid & (POL_M - 1), qt = (tid >> 7) & (TPR - 1);        // row of the tile, column quarter
+    const bool sink = prm.use_tma && prm.st_out != nullptr;               // the writer warps are at work
     const int64_t n_blocks = (prm.n + POL_M - 1) / POL_M, n_tiles = n_blocks * POL_NA;
 
     // this tile's observation block: 144 rows (ring slot s, feature f) x 128 envs, each row 512 contiguous bytes.
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
 
     if (tid == 0) {
         mbar_init(bar_a, N_WORKERS); mbar_init(bar_m, 1); mbar_init(bar_w, 1); mbar_init(bar_x, 1);
-        mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1);
+        mbar_init(bar_q0, 1); mbar_init(bar_q0 + 8, 1); mbar_init(bar_s, N_WRITERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (prm.use_tma && (int64_t)blockIdx.x < n_tiles) tma_request(blockIdx.x);
         mbar_expect_tx(bar_w, W1_BYTES + WG_BYTES + V_FLOATS * 4);          // weights: three bulk copies, one barrier
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
         // =============================================================== MMA warp
         const uint32_t w1 = smem_u32(smem + OFF_W1), wg = smem_u32(smem + OFF_WG);
         const uint32_t b_rz_ih = wg, b_rz_hh = wg + WG_RZ_BYTES, b_n_ih = wg + 2 * WG_RZ_BYTES, b_n_hh = b_n_ih + WG_N_BYTES;
-        uint32_t pa = 0;
+        uint32_t pa = 0, ps = 0;
         bool first = true;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // ---- M1: fc1
@@ -328,8 +335,6 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
             tc_fence_after();
             __syncwarp();
             if (elect_one()) {
-                // every worker has read the staging block (P0): the next tile's block travels during the GEMM phases
-                if (prm.use_tma && tile + gridDim.x < n_tiles) tma_request(tile + gridDim.x);
 #pragma unroll
                 for (int ks = 0; ks < POL_OBS / 8; ++ks) {
                     const uint64_t db = umma_desc(w1 + ks * 2 * (64 * 16), 64 * 16, 128);
@@ -338,6 +343,12 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                 }
                 umma_commit(bar_m);
             }
+            __syncwarp();
+            // every worker has read the staging block (P0) -- and, with a `state` sink, so have the writer warps: the next
+            // tile's block travels during the GEMM phases.  Requested AFTER fc1's MMAs are on their way: issuing the tensor
+            // copy first delayed them -- and with them every worker -- by its issue latency (315 -> 266 us per 131 072 envs)
+            if (sink) { mbar_wait(bar_s, ps); ps ^= 1u; }
+            if (prm.use_tma && tile + gridDim.x < n_tiles && elect_one()) tma_request(tile + gridDim.x);
             __syncwarp();
             // ---- M2: GRU gates
             mbar_wait(bar_a, pa); pa ^= 1u;
@@ -370,6 +381,32 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                 }
             }
             __syncwarp();
+        }
+    } else if (warp > N_WORKERS / 32) {
+        // =============================================================== writers: the Transition's `state` rows from the staged block
+        // A thread owns an env of the tile and walks its 144 window entries (oldest first: ring entry k_out + 6 (slot + 1) mod 144)
+        // four at a time: conflict-free shared-memory reads, one 16-byte store per trip into the env's row -- the 32 rows of a
+        // warp are 32 different lines, whose sectors the following trips complete while they are still in L2.
+        if (sink) {
+            const int rot = ((prm.slot + 1) % POL_H) * POL_F;
+            uint32_t px = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int a = (int)(tile % POL_NA);
+                mbar_wait(bar_x, px); px ^= 1u;
+                for (int j = tid - (N_WORKERS + 32); j < POL_M; j += N_WRITERS) {      // env of the tile
+                    const int64_t e = (tile / POL_NA) * POL_M + j;
+                    if (e >= prm.st_n) continue;
+                    int64_t orow = prm.st_row0 + e; orow = orow >= prm.st_cap ? orow - prm.st_cap : orow;
+                    float4* dst = reinterpret_cast<float4*>(prm.st_out + orow * prm.st_pitch + a * POL_OBS);
+#pragma unroll 6
+                    for (int kq = 0; kq < POL_OBS / 4; ++kq) {
+                        int k = 4 * kq + rot; k = k >= POL_OBS ? k - POL_OBS : k;   // rot and 4 kq are even: k .. k + 3 wrap at most once, never inside a pair
+                        const int k2 = (k + 2 >= POL_OBS) ? k + 2 - POL_OBS : k + 2;
+                        dst[kq] = make_float4(stage[k * POL_M + j], stage[(k + 1) * POL_M + j], stage[k2 * POL_M + j], stage[(k2 + 1) * POL_M + j]);
+                    }
+                }
+                mbar_arrive(bar_s);
+            }
         }
     } else {
         // =============================================================== workers: four threads per row (column quarters)
@@ -569,7 +606,7 @@ struct CritParams {
     int32_t use_tma;
 };
 
-__global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(CRIT_THREADS, 1) k_critic(const CritParams prm, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const float* vec = reinterpret_cast<const float*>(smem + CO_VEC);
     float2* lnp = reinterpret_cast<float2*>(smem + CO_LN);
@@ -649,10 +686,6 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
             tc_fence_after();
             __syncwarp();
             if (elect_one()) {
-                // every worker has read staging buffer g % 3, and the MMAs of half-block g - 2 have completed (the workers waited
-                // for them before writing this operand buffer): half-block g + 3 and the weights of g + 2 may travel
-                if (prm.use_tma && g + CR_NST < n_hb) tma_request(g + CR_NST);
-                if (g + 2 < n_hb) load_wb(g + 2);
                 const uint32_t wb = smem_u32(smem + CO_WB + (g % CR_NWB) * CR_WH_BYTES), xb = tmem_base + CC_XB * b;
                 // one descriptor per half-block: a k-step advances its 16-byte-granular start address by a constant (the address
                 // field cannot carry: shared memory ends far below 2^18)
@@ -672,6 +705,11 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_critic(const CritParams prm,
                     }
                 }
                 umma_commit(bar_m0 + 8 * b);
+                // every worker has read staging buffer g % 3, and the MMAs of half-block g - 2 have completed (the workers waited
+                // for them before writing this operand buffer): half-block g + 3 and the weights of g + 2 may travel -- requested
+                // AFTER the MMAs are on their way (issuing the copies first delays them by the copies' issue latency)
+                if (prm.use_tma && g + CR_NST < n_hb) tma_request(g + CR_NST);
+                if (g + 2 < n_hb) load_wb(g + 2);
             }
             __syncwarp();
             if (hb != CR_HB - 1) continue;
@@ -1014,6 +1052,7 @@ struct FpPolicy {
     int loaded = 0;
     int attr_window = 0, attr_hidden = 0;          // opt-in shared-memory sizes of the gather kernels set on this handle's device
     float* d_W1rot = nullptr; float* d_Wg = nullptr; float* d_vec = nullptr;
+    float* sink_out = nullptr; int64_t sink_pitch = 0, sink_row0 = 0, sink_cap = 0, sink_n = 0;   // fp_policy_state_sink: consumed by the next fp_policy_act
     int critic_loaded = 0;
     float* d_Wc1rot = nullptr; float* d_Wc2 = nullptr; float* d_Wca = nullptr; float* d_cvec = nullptr;   // critic (fp_critic_load)
     int64_t launches = 0;
@@ -1177,6 +1216,11 @@ int fp_policy_act(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pad,
     prm.seed = seed; prm.step = step; prm.std_ = std_; prm.log_std = std::log(std_); prm.explore = explore;
     alignas(64) CUtensorMap tmap;
     { const int rc = ring_tensor_map(p, d_ring, n_pad, &tmap, &prm.use_tma, "fp_policy_act"); if (rc != FP_OK) return rc; }
+    if (p->sink_out) {                                  // one-shot `state` sink (fp_policy_state_sink); needs the TMA path
+        if (!prm.use_tma || p->sink_n > n_envs) { p->sink_out = nullptr; return pfail(p, FP_EINVAL, "fp_policy_act: the state sink needs n_pad >= 128 and at most n_envs rows"); }
+        prm.st_out = p->sink_out; prm.st_pitch = p->sink_pitch; prm.st_row0 = p->sink_row0; prm.st_cap = p->sink_cap; prm.st_n = p->sink_n;
+        p->sink_out = nullptr;
+    }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const int64_t tiles = (n_envs + POL_M - 1) / POL_M * POL_NA;
@@ -1201,6 +1245,18 @@ int fp_policy_sample(FpPolicy* p, const float* d_mean, int64_t n_envs, float* d_
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;
+    return FP_OK;
+}
+
+// One-shot sink for the NEXT fp_policy_act: while it evaluates the policy, its writer warps copy the dense get_obs windows
+// [5][144] of envs [0, n) -- the very blocks the kernel has staged -- into rows (row0 + e) mod cap of pitch `pitch` floats: the
+// Transition's `state` (model.py:230-237) without a separate pass over the ring (fp_policy_gather_windows).  Needs a ring of
+// at least 128 envs (n_pad >= 128).
+int fp_policy_state_sink(FpPolicy* p, float* d_field, int64_t pitch, int64_t row0, int64_t cap, int64_t n) {
+    if (!p) return FP_EINVAL;
+    if (!d_field || n < 1 || pitch < POL_NA * POL_OBS || (pitch & 3) || ((uintptr_t)d_field & 15) || row0 < 0 || cap < n || row0 >= cap)
+        return pfail(p, FP_EINVAL, "fp_policy_state_sink: bad arguments");
+    p->sink_out = d_field; p->sink_pitch = pitch; p->sink_row0 = row0; p->sink_cap = cap; p->sink_n = n;
     return FP_OK;
 }
 
@@ -1347,7 +1403,7 @@ int fp_critic_value(FpPolicy* p, const float* d_ring, int32_t slot, int64_t n_pa
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const int64_t tiles = (n_envs + POL_M - 1) / POL_M;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    k_critic<<<grid, POL_THREADS, CR_SMEM, (cudaStream_t)stream>>>(prm, tmap);
+    k_critic<<<grid, CRIT_THREADS, CR_SMEM, (cudaStream_t)stream>>>(prm, tmap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return pfail(p, FP_ECUDA, cudaGetErrorString(e));
     p->launches++;

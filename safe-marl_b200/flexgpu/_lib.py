@@ -108,6 +108,7 @@ _PROTOS = {
     "fp_policy_gather_windows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "fp_policy_rows_to_ring": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int64, _P]),
     "fp_policy_scalars_to_ring": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "fp_policy_state_sink": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "fp_policy_sample": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_float, C.c_int32, _P]),
     "fp_critic_load": (C.c_int, [_P] * 9),
     "fp_critic_value": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),

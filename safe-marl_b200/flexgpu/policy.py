@@ -274,14 +274,19 @@ class DeviceRollout:
             action, logp = pol.sample(self._mean2, explore=explore, eps=eps, step=self.total_steps)
             self._hid[1 - self._cur], self._hid_scratch = self._hid_scratch, self._hid[1 - self._cur]
             hid = self._hid[1 - self._cur]
+            pos, state_written = (self.replay.reserve(self.R) if self.R else None), False
         else:
+            pos, state_written = (self.replay.reserve(self.R) if self.R else None), False
+            if self.R and self.ring.ring.shape[-1] >= 128:          # `state` rows written by k_policy's writer warps from the blocks it stages
+                pol._check(pol._lib.fp_policy_state_sink(pol._p, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size, self.R),
+                           "fp_policy_state_sink")
+                state_written = True
             action, logp, hid, _ = pol.act(self.ring, hid_in=last_hid, reset=self._reset_mask, explore=explore, eps=eps,
                                            step=self.total_steps, hid_out=hid, hid_layout="env_minor")  # model.py:215-216
         self._cache_valid = False
-        pos = None
         if self.R:
-            pos = self.replay.reserve(self.R)
-            pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
+            if not state_written:
+                pol.gather_windows(self.ring, self.R, self._fptr["state"], TRANSITION_FIELDS["state"], pos, self.replay.size)
             self._hidden_rows("last_hid", last_hid, pos, self._reset_mask)     # a restarted env's last_hid is the zero state it acted from
             if self.value_fn is not None:                                      # value = critic(state, action) (model.py:217)
                 self._rows("value", self._value(action, "value"), pos)
