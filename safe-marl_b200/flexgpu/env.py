@@ -347,7 +347,8 @@ class BatchedFlexProvisionEnv:
         The default call (pushing, fp32 -- what the rollout loop does once per step, model.py:223) returns a
         strided VIEW [N, na, 6*history] of the handle's window ring (fp_get_obs_view): the push writes 48
         bytes per agent and nothing is re-materialised.  The view is read-only, valid until the next pushing
-        call, contiguous along the last dimension and mergeable over the first two (`.view(N * na, -1)`
+        call OR RESET (a reset zeroes the window ring of the envs it resets: copy `next_obs` before an
+        auto-reset if it is to be stored), contiguous along the last dimension and mergeable over the first two (`.view(N * na, -1)`
         works; use `.contiguous()` or contiguous=True for a packed copy).  push=False, fp64 and
         contiguous=True go through their own buffers."""
         if push and dtype == torch.float32 and not contiguous:
