@@ -205,11 +205,38 @@ __device__ __forceinline__ void split_st4(uint32_t lane_base, uint32_t col_hi, u
 // Gate non-linearities from the SFU exponential (ex2.approx, 2 ulp) and reciprocal: absolute error ~2e-7 on (0, 1) /
 // (-1, 1), i.e. fp32 rounding level -- the accurate library tanhf / expf cost 4x the instructions, and the gates are
 // 96 evaluations per thread and tile.
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-x))); }
 __device__ __forceinline__ float tanh_fast(float x) {
     const float ax = fminf(fabsf(x), 15.0f);                       // tanh(15) == 1 in fp32; keeps e^{2x} finite
     const float t = __fsub_rn(1.0f, __fdividef(2.0f, __fadd_rn(__expf(__fmul_rn(2.0f, ax)), 1.0f)));
     return copysignf(t, x);
+}
+
+// Four reciprocals from ONE SFU reciprocal: 1 / (a0 a1 a2 a3), multiplied back (9 FMULs).  The GRU cell is SFU-bound (16 lanes
+// per clock and SM): its 24 reciprocals per 8 hidden units become 6.  The caller bounds every a_i by 2^29 (clamped gate
+// arguments), so the product stays finite; each quotient carries 4 roundings (~2.4e-7 relative at most).
+__device__ __forceinline__ float rcp_sfu(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void rcp4(float a0, float a1, float a2, float a3, float& i0, float& i1, float& i2, float& i3) {
+    const float p01 = __fmul_rn(a0, a1), p23 = __fmul_rn(a2, a3);
+    const float R = rcp_sfu(__fmul_rn(p01, p23));
+    const float r01 = __fmul_rn(R, p23), r23 = __fmul_rn(R, p01);
+    i0 = __fmul_rn(r01, a1); i1 = __fmul_rn(r01, a0); i2 = __fmul_rn(r23, a3); i3 = __fmul_rn(r23, a2);
+}
+// 8 sigmoids of (x[i] + b[i]) in place: 1 / (1 + e^{-t}), t clamped at -20 (sigmoid(-20) = 2e-9: below the SFU's error)
+__device__ __forceinline__ void sigmoid8(float (&x)[8], const float* __restrict__ b) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __fadd_rn(1.0f, __expf(fminf(-__fadd_rn(x[i], b[i]), 20.0f)));
+    rcp4(x[0], x[1], x[2], x[3], x[0], x[1], x[2], x[3]);
+    rcp4(x[4], x[5], x[6], x[7], x[4], x[5], x[6], x[7]);
+}
+// 8 tanh in place: sign(u) (1 - 2 / (e^{2|u|} + 1)), |u| clamped at 10 (tanh(10) == 1 in fp32)
+__device__ __forceinline__ void tanh8(float (&u)[8]) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(__expf(__fmul_rn(2.0f, fminf(fabsf(u[i]), 10.0f))), 1.0f);
+    rcp4(a[0], a[1], a[2], a[3], a[0], a[1], a[2], a[3]);
+    rcp4(a[4], a[5], a[6], a[7], a[4], a[5], a[6], a[7]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = copysignf(fmaf(-2.0f, a[i], 1.0f), u[i]);
 }
 
 // select_action (utils/util.py:50-64, continuous / action_enforcebound) of one (env, agent) row from its fc2 output m:
@@ -503,11 +530,14 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                     tmem_ld8(lane_base + C_GIN + 32 * hc + 8 * qt, gi);
                     tmem_ld8(lane_base + C_GHN + 32 * hc + 8 * qt, gh);
                     tmem_wait_ld();
+                    sigmoid8(rp, vec + V_BRZ + cc);                             // r
+                    sigmoid8(zp, vec + V_BRZ + 64 + cc);                        // z
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gi[i] = fmaf(rp[i], __fadd_rn(gh[i], vec[V_BHN + cc + i]), __fadd_rn(gi[i], vec[V_BIN + cc + i]));
+                    tanh8(gi);                                                  // n = tanh(gi_n + r gh_n)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float r = sigmoid_fast(__fadd_rn(rp[i], vec[V_BRZ + cc + i]));
-                        const float z = sigmoid_fast(__fadd_rn(zp[i], vec[V_BRZ + 64 + cc + i]));
-                        const float nn = tanh_fast(fmaf(r, __fadd_rn(gh[i], vec[V_BHN + cc + i]), __fadd_rn(gi[i], vec[V_BIN + cc + i])));
+                        const float z = zp[i], nn = gi[i];
                         const float hn = fmaf(z, __fsub_rn(h[8 * hc + i], nn), nn);   // (1 - z) n + z h
                         h[8 * hc + i] = hn;
                         p0 = fmaf(hn, vec[V_W2 + cc + i], p0); p1 = fmaf(hn, vec[V_W2 + 64 + cc + i], p1);
