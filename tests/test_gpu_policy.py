@@ -98,6 +98,37 @@ def test_policy_rows_are_independent_and_ragged_sizes(gold, cuda):
     pol.close()
 
 
+def test_policy_saturated_gates_stay_finite(gold, cuda):
+    """GRU weights x 32 (still TF32-exact): gate pre-activations of +-100 and more.  The kernel takes its reciprocals four
+    at a time from the reciprocal of a product and clamps the gate arguments to keep that product finite -- the result
+    must stay finite and agree with a plain fp64 evaluation (bound 1e-4: the x 32 amplifies fc1's fp32 rounding)."""
+    from flexgpu.policy import DevicePolicy
+    w = {k: np.array(gold["wt_" + k], dtype=np.float32) for k in KEYS}
+    for k in ("rnn.weight_ih", "rnn.weight_hh", "rnn.bias_ih", "rnn.bias_hh"):
+        w[k] = w[k] * np.float32(32.0)
+    pol = DevicePolicy(w, device=cuda)
+    obs = gold["obs1"]
+    n = obs.shape[0]
+    h0 = (np.random.default_rng(3).uniform(-1, 1, (n, 5, 64))).astype(np.float32)
+    ring = make_ring(obs, 11, cuda)
+    _, _, hid, mean = pol.act(ring, slot=11, n_envs=n, hid_in=torch.from_numpy(h0).to(cuda), explore=False, want_mean=True,
+                              hid_out=torch.empty(n, 5, 64, device=cuda))
+    t = {k: torch.from_numpy(v).double() for k, v in w.items()}
+    x = torch.cat([torch.from_numpy(obs).double(), torch.eye(5, dtype=torch.float64).expand(n, 5, 5)], dim=-1)
+    a = torch.relu(torch.nn.functional.layer_norm(x @ t["fc1.weight"].T + t["fc1.bias"], (64,), t["layernorm.weight"], t["layernorm.bias"]))
+    gi = a @ t["rnn.weight_ih"].T + t["rnn.bias_ih"]
+    gh = torch.from_numpy(h0).double() @ t["rnn.weight_hh"].T + t["rnn.bias_hh"]
+    assert float((gi + gh).abs().max()) > 40.0                   # the clamps are exercised
+    r = torch.sigmoid(gi[..., :64] + gh[..., :64]); z = torch.sigmoid(gi[..., 64:128] + gh[..., 64:128])
+    nn_ = torch.tanh(gi[..., 128:] + r * gh[..., 128:])
+    h1 = (1 - z) * nn_ + z * torch.from_numpy(h0).double()
+    m = h1 @ t["fc2.weight"].T + t["fc2.bias"]
+    got_h, got_m = hid.cpu().double(), mean.cpu().double()
+    assert bool(torch.isfinite(got_h).all()) and bool(torch.isfinite(got_m).all())
+    assert float((got_h - h1).abs().max()) < 1e-4 and float((got_m - m).abs().max()) < 1e-4
+    pol.close()
+
+
 def test_policy_philox_sampling(gold, cuda):
     """Device-side exploration noise: N(0, 1) draws keyed by (seed, row, step) -- reproducible, step-dependent."""
     from flexgpu.policy import DevicePolicy
