@@ -63,7 +63,8 @@ constexpr uint32_t OFF_LN = OFF_STAGE + POL_OBS * POL_M * 4;               // [T
 constexpr uint32_t OFF_FC = OFF_LN + TPR * POL_M * 8;                      // [TPR][128 rows] float4: fc2 partial sums
 constexpr uint32_t OFF_BAR = OFF_FC + TPR * POL_M * 16;                    // a_ready, mma_done, weights, x_full
 constexpr uint32_t OFF_TMEM = OFF_BAR + 56;                                // (+ mma_done of the two column halves of the GRU GEMMs, stage_copied)
-constexpr uint32_t POL_SMEM = OFF_TMEM + 16;
+constexpr uint32_t OFF_Z = (OFF_TMEM + 16 + 15) / 16 * 16;                                // [128 rows] float4: the row's four normals, drawn ahead
+constexpr uint32_t POL_SMEM = OFF_Z + POL_M * 16;
 static_assert(POL_SMEM <= 227 * 1024, "policy kernel exceeds the shared memory of one SM");
 static_assert(OFF_STAGE % 128 == 0 && OFF_WG % 128 == 0 && OFF_VEC % 16 == 0 && (V_FLOATS * 4) % 16 == 0, "operand alignment");
 // TMEM columns (512 = the whole TMEM: one CTA per SM)
@@ -242,26 +243,27 @@ __device__ __forceinline__ void tanh8(float (&u)[8]) {
 // select_action (utils/util.py:50-64, continuous / action_enforcebound) of one (env, agent) row from its fc2 output m:
 // explore: x = m + std eps, action = tanh(x), log_prob = Normal(m, std).log_prob(x) - log(1 - action^2 + 1e-6), with eps from the
 // caller's array or Philox4x32-10 keyed by (seed; row, step) + Box-Muller; otherwise status 'test': action = tanh(m).
-__device__ __forceinline__ void select_action_row(const float (&m)[4], int64_t r_glob, int explore, const float* __restrict__ eps,
-                                                  uint64_t seed, uint64_t step, float std_, float log_std, float (&act)[4], float (&lp)[4]) {
+// the row's four standard normals: the caller's array, or Philox4x32-10 keyed by the seed, counter = (row, step) + Box-Muller.
+// They do not depend on the network's output: k_policy draws them while its workers wait for the GRU GEMMs.
+__device__ __forceinline__ float4 draw_normals(int64_t r_glob, const float* __restrict__ eps, uint64_t seed, uint64_t step) {
+    if (eps != nullptr) return __ldg(reinterpret_cast<const float4*>(eps) + r_glob);
+    U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
+    ctr.z = (uint32_t)step; ctr.w = (uint32_t)(step >> 32);
+    const U4 rr = philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // Box-Muller on (0, 1] x [0, 1) uniforms
+    const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
+    const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+    float s0, cs0, s1, cs1;
+    __sincosf(6.283185307179586f * u1, &s0, &cs0);
+    __sincosf(6.283185307179586f * u3, &s1, &cs1);
+    return make_float4(ra * cs0, ra * s0, rb * cs1, rb * s1);
+}
+// explore, given the draw zz: x = m + std z, action = tanh(x), log_prob as above; otherwise status 'test': action = tanh(m)
+__device__ __forceinline__ void select_action_drawn(const float (&m)[4], int explore, const float4 zz, float std_, float log_std,
+                                                    float (&act)[4], float (&lp)[4]) {
     if (explore) {
-        float z[4];
-        if (eps != nullptr) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(eps) + r_glob);
-            z[0] = t.x; z[1] = t.y; z[2] = t.z; z[3] = t.w;
-        } else {                                                 // Philox4x32-10 keyed by the seed, counter = (row, step)
-            U4 ctr; ctr.x = (uint32_t)r_glob; ctr.y = (uint32_t)((uint64_t)r_glob >> 32);
-            ctr.z = (uint32_t)step; ctr.w = (uint32_t)(step >> 32);
-            const U4 rr = philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
-            // Box-Muller on (0, 1] x [0, 1) uniforms
-            const float u0 = ((float)(rr.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u1 = (float)(rr.y >> 8) * (1.0f / 16777216.0f);
-            const float u2 = ((float)(rr.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u3 = (float)(rr.w >> 8) * (1.0f / 16777216.0f);
-            const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
-            float s0, cs0, s1, cs1;
-            __sincosf(6.283185307179586f * u1, &s0, &cs0);
-            __sincosf(6.283185307179586f * u3, &s1, &cs1);
-            z[0] = ra * cs0; z[1] = ra * s0; z[2] = rb * cs1; z[3] = rb * s1;
-        }
+        const float z[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float x = fmaf(std_, z[i], m[i]);              // Normal(mean, std).rsample()
@@ -277,6 +279,11 @@ __device__ __forceinline__ void select_action_row(const float (&m)[4], int64_t r
 #pragma unroll
         for (int i = 0; i < 4; ++i) { act[i] = tanh_fast(m[i]); lp[i] = 0.0f; }   // status == 'test' (util.py:82-85)
     }
+}
+__device__ __forceinline__ void select_action_row(const float (&m)[4], int64_t r_glob, int explore, const float* __restrict__ eps,
+                                                  uint64_t seed, uint64_t step, float std_, float log_std, float (&act)[4], float (&lp)[4]) {
+    const float4 zz = explore ? draw_normals(r_glob, eps, seed, step) : make_float4(0.f, 0.f, 0.f, 0.f);
+    select_action_drawn(m, explore, zz, std_, log_std, act, lp);
 }
 
 // select_action alone, from stored fc2 outputs (fp_policy_act's d_mean): a second draw for the same policy evaluation --
@@ -300,6 +307,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
     float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
     float2* lnp = reinterpret_cast<float2*>(smem + OFF_LN);
     float4* fcp = reinterpret_cast<float4*>(smem + OFF_FC);
+    float4* zdraw = reinterpret_cast<float4*>(smem + OFF_Z);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const uint32_t bar_a = smem_u32(smem + OFF_BAR), bar_m = bar_a + 8, bar_w = bar_a + 16, bar_x = bar_a + 24, bar_q0 = bar_a + 32, bar_s = bar_a + 48;
     const int tid = threadIdx.x, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
@@ -515,6 +523,9 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_a);
+            // the exploration draw of this row (Philox + Box-Muller: ~140 dependent instructions of the sampling thread) does not
+            // depend on the network: drawn here, while the tensor pipe works on the GRU GEMMs, kept in shared memory (same thread)
+            if (qt == 0 && live && prm.explore) zdraw[row] = draw_normals(r_glob, prm.eps, prm.seed, prm.step);
 
             // ---- E2: GRU cell (torch.nn.GRUCell: r, z, n gate order) -> h'; fc2 partial sums
             {
@@ -571,7 +582,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                 }
                 if (prm.mean != nullptr) reinterpret_cast<float4*>(prm.mean)[r_glob] = make_float4(m[0], m[1], m[2], m[3]);
                 float act[4], lp[4];
-                select_action_row(m, r_glob, prm.explore, prm.eps, prm.seed, prm.step, prm.std_, prm.log_std, act, lp);
+                select_action_drawn(m, prm.explore, zdraw[row], prm.std_, prm.log_std, act, lp);
                 reinterpret_cast<float4*>(prm.action)[r_glob] = make_float4(act[0], act[1], act[2], act[3]);
                 if (prm.logp != nullptr) reinterpret_cast<float4*>(prm.logp)[r_glob] = make_float4(lp[0], lp[1], lp[2], lp[3]);
             }
