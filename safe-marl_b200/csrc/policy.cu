@@ -55,7 +55,7 @@ constexpr int KPT = POL_OBS / TPR;         // observation inputs per thread: 36
 constexpr uint32_t W1_BYTES = POL_OBS * POL_HID * 4;                       // 36 864: [36 kc][64 n][4]
 constexpr uint32_t WG_RZ_BYTES = POL_HID * 128 * 4, WG_N_BYTES = POL_HID * 64 * 4;   // [16 kc][N][4]
 constexpr uint32_t WG_BYTES = 2 * WG_RZ_BYTES + 2 * WG_N_BYTES;            // 98 304: rz_ih, rz_hh, n_ih, n_hh
-// small arrays (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (b_ih + b_hh), b_in[64], b_hn[64], W2[4][64] (fp32), b2[4] (+12 pad)
+// small arrays (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (-(b_ih + b_hh) log2 e), b_in[64], b_hn[64] (x 2 log2 e), W2[4][64] (fp32), b2[4] (+12 pad)
 constexpr int V_B1A = 0, V_LNG = 320, V_LNB = 384, V_BRZ = 448, V_BIN = 576, V_BHN = 640, V_W2 = 704, V_B2 = 960, V_FLOATS = 992;
 constexpr uint32_t OFF_W1 = 0, OFF_WG = OFF_W1 + W1_BYTES, OFF_VEC = OFF_WG + WG_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_VEC + V_FLOATS * 4;                     // [144][128] fp32 = 73 728
@@ -222,27 +222,28 @@ __device__ __forceinline__ void rcp4(float a0, float a1, float a2, float a3, flo
     const float r01 = __fmul_rn(R, p23), r23 = __fmul_rn(R, p01);
     i0 = __fmul_rn(r01, a1); i1 = __fmul_rn(r01, a0); i2 = __fmul_rn(r23, a3); i3 = __fmul_rn(r23, a2);
 }
-// 8 sigmoids of (x[i] + b[i]) in place: 1 / (1 + e^{-t}), t clamped at -20 (sigmoid(-20) = 2e-9: below the SFU's error)
-__device__ __forceinline__ void sigmoid8(float (&x)[8], const float* __restrict__ b) {
+// The gate arguments come out of ONE fused multiply-add in the SFU exponential's own unit (base 2): the loader stores the r / z
+// biases as -(b_ih + b_hh) log2(e) and the n-gate biases times 2 log2(e) (POL_L2E below).
+// 8 sigmoids 1 / (1 + 2^t), t = -(x[i] + b[i]) log2(e) clamped at 20 log2(e) (sigmoid(-20) = 2e-9: below the SFU's error); nb = the stored bias
+constexpr float POL_L2E = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_sfu(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void sigmoid8(float (&x)[8], const float* __restrict__ nb) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = __fadd_rn(1.0f, __expf(fminf(-__fadd_rn(x[i], b[i]), 20.0f)));
+    for (int i = 0; i < 8; ++i) x[i] = __fadd_rn(1.0f, ex2_sfu(fminf(fmaf(x[i], -POL_L2E, nb[i]), 20.0f * POL_L2E)));
     rcp4(x[0], x[1], x[2], x[3], x[0], x[1], x[2], x[3]);
     rcp4(x[4], x[5], x[6], x[7], x[4], x[5], x[6], x[7]);
 }
-// 8 tanh in place: sign(u) (1 - 2 / (e^{2|u|} + 1)), |u| clamped at 10 (tanh(10) == 1 in fp32)
-__device__ __forceinline__ void tanh8(float (&u)[8]) {
+// 8 tanh in place, of u = v / (2 log2(e)): sign(v) (1 - 2 / (2^|v| + 1)), |u| clamped at 10 (tanh(10) == 1 in fp32)
+__device__ __forceinline__ void tanh8_scaled(float (&v)[8]) {
     float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(__expf(__fmul_rn(2.0f, fminf(fabsf(u[i]), 10.0f))), 1.0f);
+    for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(ex2_sfu(fminf(fabsf(v[i]), 20.0f * POL_L2E)), 1.0f);
     rcp4(a[0], a[1], a[2], a[3], a[0], a[1], a[2], a[3]);
     rcp4(a[4], a[5], a[6], a[7], a[4], a[5], a[6], a[7]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = copysignf(fmaf(-2.0f, a[i], 1.0f), u[i]);
+    for (int i = 0; i < 8; ++i) v[i] = copysignf(fmaf(-2.0f, a[i], 1.0f), v[i]);
 }
 
-// select_action (utils/util.py:50-64, continuous / action_enforcebound) of one (env, agent) row from its fc2 output m:
-// explore: x = m + std eps, action = tanh(x), log_prob = Normal(m, std).log_prob(x) - log(1 - action^2 + 1e-6), with eps from the
-// caller's array or Philox4x32-10 keyed by (seed; row, step) + Box-Muller; otherwise status 'test': action = tanh(m).
 // the row's four standard normals: the caller's array, or Philox4x32-10 keyed by the seed, counter = (row, step) + Box-Muller.
 // They do not depend on the network's output: k_policy draws them while its workers wait for the GRU GEMMs.
 __device__ __forceinline__ float4 draw_normals(int64_t r_glob, const float* __restrict__ eps, uint64_t seed, uint64_t step) {
@@ -544,8 +545,9 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                     sigmoid8(rp, vec + V_BRZ + cc);                             // r
                     sigmoid8(zp, vec + V_BRZ + 64 + cc);                        // z
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) gi[i] = fmaf(rp[i], __fadd_rn(gh[i], vec[V_BHN + cc + i]), __fadd_rn(gi[i], vec[V_BIN + cc + i]));
-                    tanh8(gi);                                                  // n = tanh(gi_n + r gh_n)
+                    for (int i = 0; i < 8; ++i)                                 // 2 log2(e) (gi_n + b_in + r (gh_n + b_hn))
+                        gi[i] = fmaf(rp[i], fmaf(gh[i], 2.0f * POL_L2E, vec[V_BHN + cc + i]), fmaf(gi[i], 2.0f * POL_L2E, vec[V_BIN + cc + i]));
+                    tanh8_scaled(gi);                                           // n = tanh(gi_n + r gh_n)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float z = zp[i], nn = gi[i];
@@ -1217,8 +1219,12 @@ int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const fl
         for (int k = 0; k < POL_HID; ++k) vec[V_W2 + o * POL_HID + k] = fc2_w[(size_t)o * POL_HID + k];      // fc2 runs in fp32: unrounded
     for (int a = 0; a < POL_NA; ++a)
         for (int n = 0; n < POL_HID; ++n) vec[V_B1A + a * POL_HID + n] = fc1_b[n] + fc1_w[(size_t)n * KIN + POL_OBS + a];   // one-hot column folded in
-    for (int n = 0; n < POL_HID; ++n) { vec[V_LNG + n] = ln_g[n]; vec[V_LNB + n] = ln_b[n]; vec[V_BIN + n] = b_ih[128 + n]; vec[V_BHN + n] = b_hh[128 + n]; }
-    for (int n = 0; n < 128; ++n) vec[V_BRZ + n] = b_ih[n] + b_hh[n];
+    for (int n = 0; n < POL_HID; ++n) { vec[V_LNG + n] = ln_g[n]; vec[V_LNB + n] = ln_b[n]; }
+    // gate biases in the exponential's unit (see sigmoid8 / tanh8_scaled)
+    for (int n = 0; n < POL_HID; ++n) {
+        vec[V_BIN + n] = (float)((double)b_ih[128 + n] * (2.0 * (double)POL_L2E)); vec[V_BHN + n] = (float)((double)b_hh[128 + n] * (2.0 * (double)POL_L2E));
+    }
+    for (int n = 0; n < 128; ++n) vec[V_BRZ + n] = (float)(-((double)b_ih[n] + (double)b_hh[n]) * (double)POL_L2E);
     for (int n = 0; n < POL_ACT; ++n) vec[V_B2 + n] = fc2_b[n];
     cudaFree(p->d_W1rot); cudaFree(p->d_Wg); cudaFree(p->d_vec);
     p->d_W1rot = p->d_Wg = p->d_vec = nullptr;
