@@ -55,7 +55,7 @@ constexpr int KPT = POL_OBS / TPR;         // observation inputs per thread: 36
 constexpr uint32_t W1_BYTES = POL_OBS * POL_HID * 4;                       // 36 864: [36 kc][64 n][4]
 constexpr uint32_t WG_RZ_BYTES = POL_HID * 128 * 4, WG_N_BYTES = POL_HID * 64 * 4;   // [16 kc][N][4]
 constexpr uint32_t WG_BYTES = 2 * WG_RZ_BYTES + 2 * WG_N_BYTES;            // 98 304: rz_ih, rz_hh, n_ih, n_hh
-// small arrays (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (-(b_ih + b_hh) log2 e), b_in[64], b_hn[64] (x 2 log2 e), W2[4][64] (fp32), b2[4] (+12 pad)
+// small arrays (floats): b1a[5][64], ln_g[64], ln_b[64], b_rz[128] (-(b_ih + b_hh) log2 e), b_in[64], b_hn[64] (x 2 log2 e), W2[64][4] (fp32, unit-major), b2[4] (+12 pad)
 constexpr int V_B1A = 0, V_LNG = 320, V_LNB = 384, V_BRZ = 448, V_BIN = 576, V_BHN = 640, V_W2 = 704, V_B2 = 960, V_FLOATS = 992;
 constexpr uint32_t OFF_W1 = 0, OFF_WG = OFF_W1 + W1_BYTES, OFF_VEC = OFF_WG + WG_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_VEC + V_FLOATS * 4;                     // [144][128] fp32 = 73 728
@@ -553,8 +553,8 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
                         const float z = zp[i], nn = gi[i];
                         const float hn = fmaf(z, __fsub_rn(h[8 * hc + i], nn), nn);   // (1 - z) n + z h
                         h[8 * hc + i] = hn;
-                        p0 = fmaf(hn, vec[V_W2 + cc + i], p0); p1 = fmaf(hn, vec[V_W2 + 64 + cc + i], p1);
-                        p2 = fmaf(hn, vec[V_W2 + 128 + cc + i], p2); p3 = fmaf(hn, vec[V_W2 + 192 + cc + i], p3);
+                        const float4 w2 = *reinterpret_cast<const float4*>(vec + V_W2 + 4 * (cc + i));   // fc2's column of unit cc + i: one LDS.128
+                        p0 = fmaf(hn, w2.x, p0); p1 = fmaf(hn, w2.y, p1); p2 = fmaf(hn, w2.z, p2); p3 = fmaf(hn, w2.w, p3);
                     }
                 }
                 pq ^= 1u;
@@ -1216,7 +1216,7 @@ int fp_policy_load(FpPolicy* p, const float* fc1_w, const float* fc1_b, const fl
         pack_n(Wg, 2 * WG_RZ_BYTES / 4 + WG_N_BYTES / 4, w_hh);
     }
     for (int o = 0; o < POL_ACT; ++o)
-        for (int k = 0; k < POL_HID; ++k) vec[V_W2 + o * POL_HID + k] = fc2_w[(size_t)o * POL_HID + k];      // fc2 runs in fp32: unrounded
+        for (int k = 0; k < POL_HID; ++k) vec[V_W2 + 4 * k + o] = fc2_w[(size_t)o * POL_HID + k];      // fc2 runs in fp32: unrounded
     for (int a = 0; a < POL_NA; ++a)
         for (int n = 0; n < POL_HID; ++n) vec[V_B1A + a * POL_HID + n] = fc1_b[n] + fc1_w[(size_t)n * KIN + POL_OBS + a];   // one-hot column folded in
     for (int n = 0; n < POL_HID; ++n) { vec[V_LNG + n] = ln_g[n]; vec[V_LNB + n] = ln_b[n]; }
