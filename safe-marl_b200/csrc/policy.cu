@@ -206,8 +206,11 @@ __device__ __forceinline__ void split_st4(uint32_t lane_base, uint32_t col_hi, u
 // Gate non-linearities from the SFU exponential (ex2.approx, 2 ulp) and reciprocal: absolute error ~2e-7 on (0, 1) /
 // (-1, 1), i.e. fp32 rounding level -- the accurate library tanhf / expf cost 4x the instructions, and the gates are
 // 96 evaluations per thread and tile.
+// min that propagates a NaN operand (fminf would return the clamp and hide a poisoned row)
+__device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float tanh_fast(float x) {
-    const float ax = fminf(fabsf(x), 15.0f);                       // tanh(15) == 1 in fp32; keeps e^{2x} finite
+    const float ax = min_nan(fabsf(x), 15.0f);                       // tanh(15) == 1 in fp32; keeps e^{2x} finite
     const float t = __fsub_rn(1.0f, __fdividef(2.0f, __fadd_rn(__expf(__fmul_rn(2.0f, ax)), 1.0f)));
     return copysignf(t, x);
 }
@@ -229,7 +232,7 @@ constexpr float POL_L2E = 1.4426950408889634f;
 __device__ __forceinline__ float ex2_sfu(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void sigmoid8(float (&x)[8], const float* __restrict__ nb) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = __fadd_rn(1.0f, ex2_sfu(fminf(fmaf(x[i], -POL_L2E, nb[i]), 20.0f * POL_L2E)));
+    for (int i = 0; i < 8; ++i) x[i] = __fadd_rn(1.0f, ex2_sfu(min_nan(fmaf(x[i], -POL_L2E, nb[i]), 20.0f * POL_L2E)));
     rcp4(x[0], x[1], x[2], x[3], x[0], x[1], x[2], x[3]);
     rcp4(x[4], x[5], x[6], x[7], x[4], x[5], x[6], x[7]);
 }
@@ -237,7 +240,7 @@ __device__ __forceinline__ void sigmoid8(float (&x)[8], const float* __restrict_
 __device__ __forceinline__ void tanh8_scaled(float (&v)[8]) {
     float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(ex2_sfu(fminf(fabsf(v[i]), 20.0f * POL_L2E)), 1.0f);
+    for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(ex2_sfu(min_nan(fabsf(v[i]), 20.0f * POL_L2E)), 1.0f);
     rcp4(a[0], a[1], a[2], a[3], a[0], a[1], a[2], a[3]);
     rcp4(a[4], a[5], a[6], a[7], a[4], a[5], a[6], a[7]);
 #pragma unroll
@@ -508,12 +511,12 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy(const PolParams prm, 
 #pragma unroll
                 for (int j = 0; j < TPR; ++j) { const float2 t = lnp[j * POL_M + row]; S = __fadd_rn(S, t.x); SS = __fadd_rn(SS, t.y); }
                 const float mean = __fmul_rn(S, 1.0f / POL_HID);
-                const float var = fmaxf(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
+                const float var = max_nan(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
                 const float rstd = rsqrtf(__fadd_rn(var, 1e-5f));
 #pragma unroll
                 for (int i = 0; i < CPT; ++i) {
                     const float y = fmaf(__fmul_rn(__fsub_rn(v[i], mean), rstd), vec[V_LNG + c0 + i], vec[V_LNB + c0 + i]);
-                    v[i] = fmaxf(y, 0.0f);                                       // hid_activation = relu
+                    v[i] = max_nan(y, 0.0f);                                      // hid_activation = relu
                 }
 #pragma unroll
                 for (int c = 0; c < CPT / 4; ++c) {
@@ -838,12 +841,12 @@ __global__ void __launch_bounds__(CRIT_THREADS, 1) k_critic(const CritParams prm
 #pragma unroll
                 for (int q4 = 0; q4 < TPR; ++q4) { const float2 t = ln[q4 * POL_M + row]; S = __fadd_rn(S, t.x); SS = __fadd_rn(SS, t.y); }
                 const float mean = __fmul_rn(S, 1.0f / POL_HID);
-                const float var = fmaxf(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
+                const float var = max_nan(fmaf(-mean, mean, __fmul_rn(SS, 1.0f / POL_HID)), 0.0f);   // biased, as torch.nn.LayerNorm
                 const float rstd = rsqrtf(__fadd_rn(var, 1e-5f));
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     const float t = fmaf(__fmul_rn(__fsub_rn(v[c], mean), rstd), vec[CV_LNG + c0 + c], vec[CV_LNB + c0 + c]);
-                    v[c] = fmaxf(t, 0.0f);                                       // hid_activation = relu
+                    v[c] = max_nan(t, 0.0f);                                      // hid_activation = relu
                 }
                 const uint32_t a2 = CC_XB * (i & 1);
 #pragma unroll
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(CRIT_THREADS, 1) k_critic(const CritParams prm
                 tmem_wait_ld();
                 float part = 0.0f;
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) part = fmaf(fmaxf(__fadd_rn(u[c], vec[CV_B2 + c0 + c]), 0.0f), vec[CV_W3 + c0 + c], part);
+                for (int c = 0; c < CPT; ++c) part = fmaf(max_nan(__fadd_rn(u[c], vec[CV_B2 + c0 + c]), 0.0f), vec[CV_W3 + c0 + c], part);
                 float* fc = fcp + bi * (TPR * POL_M);
                 fc[qt * POL_M + row] = part;
                 tc_fence_before();

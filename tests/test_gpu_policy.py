@@ -129,6 +129,28 @@ def test_policy_saturated_gates_stay_finite(gold, cuda):
     pol.close()
 
 
+def test_policy_nan_observation_poisons_its_row_only(gold, cuda):
+    """A NaN in one (env, agent) observation window reaches that row's outputs as NaN (the clamps of the gate arguments
+    propagate it, as torch would) and leaves every other row's bits untouched."""
+    from flexgpu.policy import DevicePolicy
+    pol = DevicePolicy({k: gold["wt_" + k] for k in KEYS}, device=cuda)
+    obs = np.array(gold["obs1"], dtype=np.float32)
+    n = obs.shape[0]
+    outs = []
+    for poison in (False, True):
+        o = obs.copy()
+        if poison:
+            o[37, 2, 100] = np.nan
+        ring = make_ring(o, 5, cuda)
+        _, _, hid, mean = pol.act(ring, slot=5, n_envs=n, hid_in=None, explore=False, want_mean=True, hid_out=torch.empty(n, 5, 64, device=cuda))
+        outs.append((hid.cpu().numpy().copy(), mean.cpu().numpy().copy()))
+    (h0, m0), (h1, m1) = outs
+    assert np.isnan(h1[37, 2]).all() and np.isnan(m1[37, 2]).all()
+    keep = np.ones((n, 5), dtype=bool); keep[37, 2] = False
+    assert np.array_equal(h0[keep], h1[keep]) and np.array_equal(m0[keep], m1[keep])
+    pol.close()
+
+
 def test_policy_philox_sampling(gold, cuda):
     """Device-side exploration noise: N(0, 1) draws keyed by (seed, row, step) -- reproducible, step-dependent."""
     from flexgpu.policy import DevicePolicy
