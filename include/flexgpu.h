@@ -170,7 +170,8 @@ int fp_reset_random_retry(FpHandle* h, uint64_t seed, int64_t env_offset, const 
 /* Replaces step() (:241-356): d_actions[N][na*4] (agent-major, k = P_red, P_esc, P_esd, Q_pv)
  * of dtype act_dtype; outputs d_reward[N] fp64, d_done[N] uint8, d_info[N][FP_INFO_STRIDE]
  * fp64 (d_info may be NULL).  d_mask (may be NULL): envs with a zero byte are not stepped
- * (their outputs are left untouched). */
+ * (their outputs are left untouched).  A NaN action is a solver failure for its env (np.clip keeps the NaN, the
+ * reference's NLP gets a NaN injection and its solve raises, :314-337): roll-back, -200, solver_failed, terminate. */
 int fp_step(FpHandle* h, const void* d_actions, int act_dtype, double* d_reward,
             uint8_t* d_done, double* d_info, const uint8_t* d_mask, void* stream);
 

@@ -466,6 +466,8 @@ static void env_core(const FoNet* c, const double* P, const double* Q, const dou
     Sweep sw;
     sweep(c, pl, ql, c->pf_tol, c->pf_max_iter, &sw);
     int ok = sw.ok && !inject;
+    /* a NaN action: np.clip keeps it, the reference's NLP gets a NaN injection and its solve raises (:314-337) */
+    if (!is_reset) for (int k = 0; k < 4 * na; ++k) if (act[k] != act[k]) ok = 0;
     double e_next[8];
     const double inv_eta_dis = 1.0 / c->eta_dis;
     for (int i = 0; i < na; ++i) {

@@ -255,6 +255,8 @@ class RefFlexEnv:
         self.power_reduction = {b: self.current_active_demand[b] * self.percentage_reduction[b] for b in G['buildings']}  # :293
         solvable = False
         try:
+            if np.isnan(actions).any():                                             # np.clip keeps a NaN: the NLP gets a NaN injection
+                raise pf_ref.SolverFailure("NaN action")                             # and the solve raises (:314)
             res = self._solve(self.initial_ess_energy)                              # :298-308 (Q2: E_init)
             self.current_voltage = res['Voltages']
             self.current_ess_energy = res['Next ESS Energy']

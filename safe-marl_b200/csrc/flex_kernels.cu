@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(FP_CTA_THREADS) k_env(const EnvParams prm) {
         if (lane < na) {
             e_next = e_init + c.delta_t * (c.eta_ch * sp.ch - c.inv_eta_dis * sp.dis);
             e_bad = e_next < c.e_next_lb;                                // E_next in NonNegativeReals (pf.py:46)
+            // a NaN action: np.clip keeps it, the reference's NLP gets a NaN injection and its solve raises (:314-337)
+            if (MODE == MODE_STEP) e_bad = e_bad || (a0 != a0) || (a1 != a1) || (a2 != a2) || (a3 != a3);
         }
         const bool ok = sw.ok && !__any_sync(FULL, e_bad);              // warp-uniform
 
