@@ -33,14 +33,17 @@ for combo in itertools.product(*knobs.values()):
     env.reset(return_obs=False)
     acts = torch.rand(4, E, 5, 4, device=dev)
     ts, to = [], []
+    NOFLUSH = bool(os.environ.get("NOFLUSH"))              # NOFLUSH=1: no flush between steps -- the GPU then idles before each launch and the events also see the launch path (+11-13 us): not a kernel time
     for k in range(30):
-        flush.zero_()
+        if not NOFLUSH:
+            flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); env.step(acts[k % 4], want_info=True); b.record(); torch.cuda.synchronize()
         if k >= 5:
             ts.append(a.elapsed_time(b) * 1e3)
     for k in range(12):
-        flush.zero_()
+        if not NOFLUSH:
+            flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); env.step(acts[k % 4], want_info=True, return_obs="ring"); b.record(); torch.cuda.synchronize()
         if k >= 4:
